@@ -1,0 +1,200 @@
+"""ctypes front-end of the C restatement in ``oracle/wlsqm_oracle.c``.
+
+TEST INFRASTRUCTURE ONLY -- the checker for the CUDA path.  Nothing under
+``python-wlsqm_b200/`` may import this module (tests/test_no_oracle_in_product.py enforces it).
+
+The classes mirror the reference's Python surface so that parity tests read like the
+reference's own tests:
+
+* :class:`OracleSolver`   ~ ``wlsqm.ExpertSolver``      (wlsqm/fitter/expert.pyx:66-781)
+* :func:`fit_many`        ~ ``wlsqm.fit_?D_many[_parallel]`` (wlsqm/fitter/simple.pyx:131-604)
+* :func:`interpolate_fit` ~ ``wlsqm.interpolate_fit``   (wlsqm/fitter/interp.pyx:34-143)
+* :func:`load_reference`  imports the compiled, unmodified reference from ``oracle/_ref`` if present.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import importlib
+import os
+import subprocess
+import sys
+from pathlib import Path
+
+import numpy as np
+
+HERE = Path(__file__).resolve().parent
+_LIB = HERE / "_build" / "libwlsqm_oracle.so"
+
+ALGO_BASIC, ALGO_ITERATIVE = 1, 2
+WEIGHT_UNIFORM, WEIGHT_CENTER = 1, 2
+
+_lib = None
+
+
+def build(force: bool = False) -> Path:
+    src = HERE / "wlsqm_oracle.c"
+    if force or not _LIB.exists() or _LIB.stat().st_mtime < src.stat().st_mtime:
+        subprocess.check_call(["make", "-C", str(HERE), "-s", "-B" if force else "-s"])
+    return _LIB
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = C.CDLL(str(_LIB))
+        _lib.wo_number_of_dofs.restype = C.c_int
+        _lib.wo_solve_flat.restype = C.c_int
+        _lib.wo_interpolate.restype = C.c_int
+        _lib.wo_remap.restype = C.c_int
+    return _lib
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def number_of_dofs(dimension: int, order: int) -> int:
+    return lib().wo_number_of_dofs(int(dimension), int(order))
+
+
+def remap(n: int, mask: int):
+    o2r = np.empty(n, np.int32)
+    r2o = np.empty(n, np.int32)
+    nr = lib().wo_remap(_p(o2r), _p(r2o), C.c_int(n), C.c_longlong(int(mask)))
+    return nr, o2r, r2o
+
+
+class OracleSolver:
+    """prepare once / solve many, one scalar thread (wlsqm/fitter/expert.pyx:92-655)."""
+
+    def __init__(self, dimension, nk, order, knowns, weighting_method, algorithm=ALGO_BASIC,
+                 do_sens=False, max_iter=10):
+        self.dim = int(dimension)
+        self.nk = np.ascontiguousarray(nk, np.int32)
+        self.order = np.ascontiguousarray(order, np.int32)
+        self.knowns = np.ascontiguousarray(knowns, np.int64)
+        self.wm = np.ascontiguousarray(weighting_method, np.int32)
+        self.algorithm, self.do_sens, self.max_iter = int(algorithm), bool(do_sens), int(max_iter)
+        n = self.ncases = len(self.nk)
+        self.maxnk = int(self.nk.max()) if n else 0
+        self.maxno = number_of_dofs(self.dim, int(self.order.max())) if n else 1
+        self.c = np.zeros((n, self.maxnk * self.maxno))
+        self.w = np.zeros((n, self.maxnk))
+        self.LU = np.zeros((n, self.maxno * self.maxno))
+        self.As = np.zeros((n, self.maxno * self.maxno))
+        self.row = np.zeros((n, self.maxno))
+        self.col = np.zeros((n, self.maxno))
+        self.ipiv = np.zeros((n, self.maxno), np.int32)
+        self.iters = np.zeros(n, np.int32)
+
+    def _pad_xk(self, xk):
+        xk = np.asarray(xk, np.float64)
+        if self.dim == 1:
+            xk = xk.reshape(self.ncases, -1, 1)
+        return np.ascontiguousarray(xk[:, :self.maxnk, :])
+
+    def prepare(self, xi, xk):
+        self.xi = np.ascontiguousarray(np.asarray(xi, np.float64).reshape(self.ncases, self.dim))
+        self.xk = self._pad_xk(xk)
+        lib().wo_prepare_flat(self.dim, C.c_long(self.ncases), C.c_long(self.maxnk), self.maxno,
+                              _p(self.nk), _p(self.order), _p(self.knowns), _p(self.wm),
+                              _p(self.c), _p(self.w), _p(self.LU), _p(self.As), _p(self.row),
+                              _p(self.col), _p(self.ipiv), _p(self.xi), _p(self.xk))
+
+    def conds(self):
+        """2-norm condition number of the scaled matrix (impl.pyx:662-682)."""
+        out = np.full(self.ncases, np.nan)
+        for i in range(self.ncases):
+            no = number_of_dofs(self.dim, int(self.order[i]))
+            nr = no - bin(int(self.knowns[i]) & ((1 << no) - 1)).count("1")
+            if nr < 1:
+                continue
+            s = np.linalg.svd(self.As[i, :nr * nr].reshape(nr, nr), compute_uv=False)
+            out[i] = s[0] / s[-1]
+        return out
+
+    def solve(self, fk, fi, sens=None):
+        """fi is updated in place (first no_j columns of row j), like the reference."""
+        fkc = np.ascontiguousarray(np.asarray(fk, np.float64)[:, :self.maxnk])
+        fic = np.ascontiguousarray(fi, np.float64)
+        sn = None
+        if self.do_sens:
+            sn = np.ascontiguousarray(sens[:, :self.maxnk, :], np.float64)
+            assert sn.shape[2] == fic.shape[1]
+        it = lib().wo_solve_flat(self.dim, C.c_long(self.ncases), C.c_long(self.maxnk), self.maxno,
+                                 _p(self.nk), _p(self.order), _p(self.knowns), _p(self.wm),
+                                 _p(self.c), _p(self.w), _p(self.LU), _p(self.row), _p(self.col),
+                                 _p(self.ipiv), _p(fkc), _p(fic), C.c_long(fic.shape[1]), _p(sn),
+                                 self.algorithm, self.max_iter, _p(self.xi), _p(self.xk),
+                                 _p(self.iters))
+        fi[...] = fic
+        self.fi = fic.copy()
+        if sn is not None:
+            sens[:, :self.maxnk, :] = sn
+        return it
+
+    def interpolate(self, x, I, diff=0):
+        x = np.ascontiguousarray(np.asarray(x, np.float64).reshape(len(I), self.dim))
+        I = np.ascontiguousarray(I, np.int64)
+        out = np.empty(len(I))
+        rc = lib().wo_interpolate(self.dim, _p(self.order), _p(self.xi), _p(self.fi),
+                                  C.c_long(self.fi.shape[1]), _p(I), _p(x), C.c_long(len(I)),
+                                  int(diff), _p(out))
+        if rc:
+            raise ValueError("invalid diff")
+        return out
+
+
+def fit_many(dimension, xk, fk, nk, xi, fi, sens, do_sens, order, knowns, weighting_method,
+             algorithm=ALGO_BASIC, max_iter=10):
+    """fit_?D[_iterative]_many[_parallel] (wlsqm/fitter/simple.pyx:731-1170): prepare+solve."""
+    s = OracleSolver(dimension, nk, order, knowns, weighting_method, algorithm, do_sens, max_iter)
+    s.prepare(xi, xk)
+    return s.solve(fk, fi, sens)
+
+
+def interpolate_fit(xi, fi, dimension, order, x, diff=0):
+    xi = np.ascontiguousarray(np.atleast_1d(np.asarray(xi, np.float64)))
+    fi = np.ascontiguousarray(fi, np.float64)
+    x = np.ascontiguousarray(np.asarray(x, np.float64).reshape(-1, dimension))
+    out = np.empty(len(x))
+    order_a = np.array([order], np.int32)
+    rc = lib().wo_interpolate(int(dimension), _p(order_a), _p(xi), _p(fi), C.c_long(len(fi)), None,
+                              _p(x), C.c_long(len(x)), int(diff), _p(out))
+    if rc:
+        raise ValueError("invalid diff")
+    return out
+
+
+def mgetrf(A, ipiv):
+    n, _, nlhs = A.shape
+    At = np.ascontiguousarray(A.transpose(2, 1, 0))  # [l][m][j] == Fortran (j,m) per system
+    pt = np.zeros((nlhs, n), np.int32)
+    lib().wo_mgetrf(n, C.c_long(nlhs), _p(At), _p(pt))
+    A[...] = At.transpose(2, 1, 0)
+    ipiv[...] = pt.T
+
+
+def mgetrs(LU, ipiv, b):
+    n, _, nlhs = LU.shape
+    At = np.ascontiguousarray(LU.transpose(2, 1, 0))
+    pt = np.ascontiguousarray(ipiv.T, np.int32)
+    bt = np.ascontiguousarray(b.T)
+    lib().wo_mgetrs(n, C.c_long(nlhs), _p(At), _p(pt), _p(bt))
+    b[...] = bt.T
+
+
+def load_reference():
+    """Import the compiled unmodified reference from oracle/_ref (None if it is not built)."""
+    ref = HERE / "_ref"
+    if not (ref / "wlsqm" / "__init__.py").exists():
+        return None
+    if str(ref) not in sys.path:
+        sys.path.insert(0, str(ref))
+    os.environ.setdefault("OMP_WAIT_POLICY", "passive")
+    os.environ.setdefault("OPENBLAS_NUM_THREADS", "1")
+    try:
+        return importlib.import_module("wlsqm")
+    except Exception:  # pragma: no cover - e.g. ABI mismatch on a foreign box
+        return None
