@@ -1,0 +1,376 @@
+#!/usr/bin/env python
+"""bench.py -- the headline benchmark: ExpertSolver.solve on the 1M-point 2D order-4 (15 DOF, k=30) stream.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--n POINTS]
+
+BASELINE.json metric: "local fits/s and ExpertSolver.solve pts/s (2D order-4, 1M pts) vs FP64/HBM roofline";
+configs[1]: "ExpertSolver 2D order-4 (15 DOF), 1M points, k=30, prepare once then solve() time steps with
+varying fk".  One *step* = one solve() over the whole cloud with a fresh fk.
+
+  value      points/s, whole job, fk/fi resident in HBM (CUDA tensors handed to the public API, zero copy);
+             CUDA events on the stream the kernel runs on; max over ranks.
+  e2e        the same call with HOST (pinned) numpy arrays: H2D of fk and D2H of fi inside the timed region.
+  roofline   dominant kernel = solve_kernel: algorithmic bytes/point = 8*(nr*nk + nr*n_known + nk + 2*no)
+             (4080 B for this config) / mean launch duration, against MEASURED_PEAKS.json hbm_gbs.
+  cpu_baseline  the unmodified reference (oracle/_ref, OpenMP) on a bounded sample of the same workload,
+             on this box's host cores (rank 0, N=1 only).
+  prepare    fits/s of ExpertSolver.prepare on the same cloud and its FP64 flop rate (extra keys).
+
+--impl reference times the reference's own CPU implementation of the same path on the host cores
+(bounded sample per step), same metric/unit/config.
+Multi-GPU (torchrun): points shard by contiguous ranges, one solver per rank, no data-path collective;
+weak scaling (every rank owns --n points); value = all points / max-over-ranks time.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+for _p in (ROOT, ROOT / "python-wlsqm_b200"):
+    if str(_p) not in sys.path:
+        sys.path.insert(0, str(_p))
+
+import workloads as wl  # noqa: E402
+
+DIM, ORDER, K, KNOWNS = 2, 4, 30, 0
+NO = 15
+NR = NO - bin(KNOWNS).count("1")
+BYTES_PER_POINT = 8 * (NR * K + NR * (NO - NR) + K + 2 * NO)          # 4080
+FLOPS_PREP = 33540                                                     # SURVEY.md 8d, cfg2 knowns=0 incl. operator
+METRIC = "ExpertSolver.solve points/s (2D order-4, 15 DOF, k=30, 1M-point cloud)"
+UNIT = "points/s"
+
+
+def _peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            p = [t.strip() for t in ln.split(",")]
+            if len(p) < 9:
+                continue
+            try:
+                sm.append(float(p[1]))
+                mx.append(float(p[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_workload(n: int, seed: int):
+    x = wl.cloud(n, DIM, seed=seed)
+    hoods = wl.hoods_knn(x, K)
+    f = wl.field(x)
+    return x, hoods, f
+
+
+def meta(n):
+    return (np.full(n, K, np.int32), np.full(n, ORDER, np.int32), np.full(n, KNOWNS, np.int64),
+            np.full(n, 1, np.int32))   # WEIGHT_UNIFORM
+
+
+# ------------------------------------------------------------------------------------------------------
+def run_reference(args, rank, world):
+    """The reference's own CPU path (oracle/_ref, else the C port) on a bounded sample per step."""
+    if rank != 0:
+        return
+    sys.path.insert(0, str(ROOT / "oracle"))
+    import oracle as orc
+    ref = orc.load_reference()
+    cores = os.cpu_count() or 1
+    n = min(args.n, args.ref_sample)
+    x, hoods, f = build_workload(n, 42)
+    nk, od, kn, wm = meta(n)
+    xk = np.ascontiguousarray(x[hoods])
+    fks = [np.ascontiguousarray(wl.field_step(f, t)[hoods]) for t in range(4)]
+    fi = np.zeros((n, NO))
+    best = None
+    if ref is not None:
+        kind = "reference"
+        cands = sorted({1, cores})
+        for nt in cands:
+            s = ref.ExpertSolver(DIM, nk, od, kn, wm, algorithm=ref.ALGO_BASIC, do_sens=False, ntasks=nt)
+            s.prepare(x, xk)
+            for w in range(args.warmup):
+                s.solve(fks[w % 4], fi)
+            t0 = time.perf_counter()
+            for t in range(args.steps):
+                s.solve(fks[t % 4], fi)
+            dt = time.perf_counter() - t0
+            if best is None or dt < best[0]:
+                best = (dt, nt)
+            del s
+    else:
+        kind = "port"
+        s = orc.OracleSolver(DIM, nk, od, kn, wm)
+        s.prepare(x, xk)
+        for w in range(args.warmup):
+            s.solve(fks[w % 4], fi)
+        t0 = time.perf_counter()
+        for t in range(args.steps):
+            s.solve(fks[t % 4], fi)
+        best = (time.perf_counter() - t0, 1)
+    dt, nt = best
+    val = n * args.steps / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "cfg2: ExpertSolver 2D order-4 k=30 knowns=0 WEIGHT_UNIFORM ALGO_BASIC, solve() per step",
+                   "points_per_step": n, "note": "bounded sample of the 1M-point workload (reference arena caps one "
+                                                 "ExpertSolver at ~343k cases, SURVEY.md 0.3)"},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": nt, "kind": kind,
+                         "sample": f"{n} of {args.n} points per step, {args.steps} steps, best of ntasks in {{1,{cores}}}"},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def cpu_baseline(args):
+    """bounded sample of the same workload on the host cores: ~10-30 s of CPU work"""
+    sys.path.insert(0, str(ROOT / "oracle"))
+    import oracle as orc
+    ref = orc.load_reference()
+    cores = os.cpu_count() or 1
+    n = min(args.n, 100_000)
+    x, hoods, f = build_workload(n, 42)
+    nk, od, kn, wm = meta(n)
+    xk = np.ascontiguousarray(x[hoods])
+    fks = [np.ascontiguousarray(wl.field_step(f, t)[hoods]) for t in range(2)]
+    fi = np.zeros((n, NO))
+    steps = 10
+    out = {}
+    if ref is not None:
+        best = None
+        for nt in sorted({1, cores}):
+            s = ref.ExpertSolver(DIM, nk, od, kn, wm, algorithm=ref.ALGO_BASIC, do_sens=False, ntasks=nt)
+            t0 = time.perf_counter()
+            s.prepare(x, xk)
+            tp = time.perf_counter() - t0
+            s.solve(fks[0], fi)
+            t0 = time.perf_counter()
+            for t in range(steps):
+                s.solve(fks[t % 2], fi)
+            dt = time.perf_counter() - t0
+            if best is None or dt < best[0]:
+                best = (dt, nt, tp)
+            del s
+        dt, nt, tp = best
+        out = {"value": n * steps / dt, "unit": UNIT, "cores": nt, "kind": "reference",
+               "sample": f"{n} points x {steps} solve() steps (prepare {n / tp:.3g} fits/s at ntasks={nt})",
+               "prepare_fits_per_s": n / tp}
+    else:
+        s = orc.OracleSolver(DIM, nk, od, kn, wm)
+        t0 = time.perf_counter()
+        s.prepare(x, xk)
+        tp = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        for t in range(steps):
+            s.solve(fks[t % 2], fi)
+        dt = time.perf_counter() - t0
+        out = {"value": n * steps / dt, "unit": UNIT, "cores": 1, "kind": "port",
+               "sample": f"{n} points x {steps} solve() steps, scalar C port", "prepare_fits_per_s": n / tp}
+    return out
+
+
+# ------------------------------------------------------------------------------------------------------
+def run_b200(args, rank, world, local_rank):
+    import torch
+    import wlsqm_b200 as wlsqm
+
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: wlsqm_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    n = args.n
+    x, hoods, f = build_workload(n, 42 + rank)
+    nk, od, kn, wm = meta(n)
+    x_d = torch.from_numpy(x).to(dev)
+    hoods_d = torch.from_numpy(hoods.astype(np.int64)).to(dev)
+    xk_d = x_d[hoods_d]                                   # (n, K, 2), the caller-side gather of the examples
+    NBUF = 4                                              # distinct fk buffers, each 240 MB > L2 (126 MB)
+    fk_d = []
+    for t in range(NBUF):
+        ft = torch.from_numpy(wl.field_step(f, t)).to(dev)
+        fk_d.append(ft[hoods_d].contiguous())
+    fi_d = torch.zeros((n, NO), dtype=torch.float64, device=dev)
+    del hoods_d
+
+    s = wlsqm.ExpertSolver(DIM, nk, od, kn, wm, algorithm=wlsqm.ALGO_BASIC, do_sens=False, ntasks=1, device=local_rank)
+    # ---- prepare (timed separately; reported as fits/s) ----
+    s.prepare(x_d, xk_d)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    prep_ms = []
+    for _ in range(3):
+        e0.record()
+        s.prepare(x_d, xk_d)
+        e1.record()
+        torch.cuda.synchronize()
+        prep_ms.append(e0.elapsed_time(e1))
+    prep_ms = min(prep_ms)
+    del xk_d
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---- value: device-resident solve steps ----
+    for w in range(args.warmup):
+        s.solve(fk_d[w % NBUF], fi_d)
+    sampler = ClockSampler(local_rank)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    evs[0].record()
+    for t in range(args.steps):
+        s.solve(fk_d[t % NBUF], fi_d)
+        evs[t + 1].record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    total_ms = evs[0].elapsed_time(evs[-1])
+    per_launch_ms = [evs[i].elapsed_time(evs[i + 1]) for i in range(args.steps)]
+    kern_ms = float(np.mean(per_launch_ms))
+
+    # ---- e2e: same public call, host (pinned) numpy arrays, H2D + D2H inside the timed region ----
+    fk_h = [wlsqm.pinned_empty((n, K)) for _ in range(2)]
+    for t in range(2):
+        fk_h[t][...] = fk_d[t].cpu().numpy()
+    fi_h = wlsqm.pinned_empty((n, NO))
+    fi_h[...] = 0.0
+    e2e_steps = max(3, min(args.steps, 10))
+    for w in range(2):
+        s.solve(fk_h[w % 2], fi_h)
+    barrier()
+    e0.record()
+    for t in range(e2e_steps):
+        s.solve(fk_h[t % 2], fi_h)
+    e1.record()
+    barrier()
+    e2e_ms = e0.elapsed_time(e1)
+    chk = float(np.abs(fi_h - fi_d.cpu().numpy()).max()) if (e2e_steps - 1) % 2 == (args.steps - 1) % NBUF % 2 else None
+
+    # ---- max over ranks ----
+    if dist is not None:
+        tt = torch.tensor([total_ms, e2e_ms, prep_ms, kern_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        total_ms, e2e_ms, prep_ms, kern_ms = (float(v) for v in tt.tolist())
+    if rank == 0:
+        peak, peak_src = _peaks()
+        achieved = BYTES_PER_POINT * n / (kern_ms * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": world * n * args.steps / (total_ms * 1e-3), "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "cfg2: ExpertSolver 2D order-4 k=30 knowns=0 WEIGHT_UNIFORM ALGO_BASIC, "
+                                   "prepare once then solve() per step with varying fk",
+                       "points_per_gpu": n, "sharding": "contiguous point ranges per GPU, no data-path collective",
+                       "l2": "inputs larger than L2: operators 3.6 GB + rotating fk buffers of 240 MB each per step",
+                       "bytes_per_point": BYTES_PER_POINT},
+            "e2e": {"value": world * n * e2e_steps / (e2e_ms * 1e-3), "unit": UNIT,
+                    "h2d_bytes_per_step": int(n * K * 8), "d2h_bytes_per_step": int(n * NO * 8),
+                    "steps": e2e_steps, "host_buffers": "pinned"},
+            "gpu_launches": args.steps,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "kernel": "wlsqm::solve_kernel<1,false,false>", "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": BYTES_PER_POINT * n, "launch_ms": kern_ms},
+            "prepare": {"fits_per_s": n / (prep_ms * 1e-3), "ms": prep_ms,
+                        "fp64_gflops_algorithmic": FLOPS_PREP * n / (prep_ms * 1e-3) / 1e9},
+            "clocks": clocks,
+        }
+        traffic_file = ROOT / "profiles" / "solve_kernel_traffic.json"
+        if traffic_file.exists():
+            try:
+                tj = json.loads(traffic_file.read_text())
+                if tj.get("points") == n:
+                    line["roofline"]["traffic"] = tj.get("dram_bytes_per_launch")
+            except Exception:
+                pass
+        if world == 1 and not args.no_cpu:
+            line["cpu_baseline"] = cpu_baseline(args)
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--n", type=int, default=1_000_000, help="points per GPU")
+    ap.add_argument("--ref-sample", type=int, default=200_000, help="points per step of the --impl reference arm")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    os.environ.setdefault("OMP_WAIT_POLICY", "passive")
+    os.environ.setdefault("OPENBLAS_NUM_THREADS", "1")
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_b200(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

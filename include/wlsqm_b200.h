@@ -1,0 +1,144 @@
+/*
+ * wlsqm_b200.h -- C ABI of the B200-native wlsqm hot path (libwlsqm_b200.so).
+ *
+ * This is the drop-in boundary: plain pointers, sizes and strides, no torch / numpy types.
+ * Every entry point names the reference interface it replaces (paths relative to the root of
+ * Technologicat/python-wlsqm).  The reference has no FFI of its own -- its boundary is the Python
+ * surface of four Cython modules (wlsqm/__init__.py:25-28) -- so these functions are what a thin
+ * Cython / ctypes shim behind those Python names binds (INTEGRATION.md shows that shim).
+ *
+ * Conventions
+ *   - All data is float64; nk/order/weighting_method are int32, knowns int64 (simple.pyx:149-159).
+ *   - Strides are in ELEMENTS, not bytes.  The last axis of xi/xk/fi/sens is contiguous, exactly as
+ *     the reference's memoryview signatures demand; fk may be strided on both axes.
+ *   - Data pointers (xi, xk, fk, fi, sens, x, I, out, A, b, ipiv) may be HOST or DEVICE memory; the
+ *     library asks the CUDA runtime which.  Device pointers are used in place (zero copy, work is
+ *     enqueued on the solver's stream and the call returns without synchronising unless it has to
+ *     return a value).  Host pointers are staged through device buffers owned by the library and
+ *     the call returns when the results are in host memory.  Host arrays must have a unit stride on
+ *     their last axis (fk included) -- rows may be pitched.
+ *   - Metadata pointers (nk, order, knowns, weighting_method) are always HOST memory.
+ *   - Return value: 0 on success, otherwise one of WLSQM_E_*; wlsqm_last_error() has the message.
+ *     The Python shim maps WLSQM_E_VALUE -> ValueError, WLSQM_E_MEMORY -> MemoryError,
+ *     WLSQM_E_NOTREADY / WLSQM_E_CUDA -> RuntimeError (the reference's exception surface,
+ *     expert.pyx:131-189,493-494,673-674,742-743).
+ *   - There is no CPU fallback: without a CUDA device every compute entry point fails with WLSQM_E_CUDA.
+ */
+#ifndef WLSQM_B200_H
+#define WLSQM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define WLSQM_API __attribute__((visibility("default")))
+#else
+#define WLSQM_API
+#endif
+
+#define WLSQM_OK 0
+#define WLSQM_E_VALUE (-1)
+#define WLSQM_E_MEMORY (-2)
+#define WLSQM_E_CUDA (-3)
+#define WLSQM_E_NOTREADY (-4)
+
+/* wlsqm/fitter/defs.pyx:69-75 */
+#define WLSQM_ALGO_BASIC 1
+#define WLSQM_ALGO_ITERATIVE 2
+#define WLSQM_WEIGHT_UNIFORM 1
+#define WLSQM_WEIGHT_CENTER 2
+
+/* interpolate: evaluate every derivative slot of the model in one pass (extension, out is [nx][out_s0]) */
+#define WLSQM_DIFF_ALL (-1)
+
+typedef struct wlsqm_solver wlsqm_solver_t;
+
+/* ---- library ---------------------------------------------------------------------------------- */
+WLSQM_API int wlsqm_b200_abi_version(void);
+WLSQM_API const char* wlsqm_last_error(void);                 /* thread-local message of the last failure */
+WLSQM_API int wlsqm_device_count(void);                       /* CUDA devices visible; 0 if none */
+
+/* number_of_dofs: wlsqm/fitter/infra.pyx:67-112, exported as wlsqm/fitter/expert.pyx:57-63.
+ * Returns -1 for a bad dimension, -2 for a bad order (no error state is set). */
+WLSQM_API int wlsqm_number_of_dofs(int dimension, int order);
+
+/* page-locked host buffers for the staged (host-pointer) path */
+WLSQM_API void* wlsqm_pinned_alloc(int64_t bytes);
+WLSQM_API void wlsqm_pinned_free(void* p);
+
+/* ---- ExpertSolver: wlsqm/fitter/expert.pyx:66-781 ------------------------------------------------ */
+
+/* ExpertSolver.__init__ (expert.pyx:92-263) + CaseManager_new/Case_new/commit (infra.pyx:308-471,545-632).
+ * `device` is the CUDA ordinal that will own the solver's state.  ntasks has no meaning here. */
+WLSQM_API int wlsqm_solver_create(int dimension, int64_t ncases, const int32_t* nk, const int32_t* order,
+                        const int64_t* knowns, const int32_t* weighting_method, int algorithm, int do_sens,
+                        int max_iter, int debug, int device, wlsqm_solver_t** out);
+
+/* ExpertSolver.__del__ (expert.pyx:267-286) / CaseManager_del (infra.pyx:497) */
+WLSQM_API int wlsqm_solver_destroy(wlsqm_solver_t* s);
+
+/* Enqueue the solver's work on a caller-owned CUDA stream (cudaStream_t) instead of its own. */
+WLSQM_API int wlsqm_solver_set_stream(wlsqm_solver_t* s, void* cuda_stream);
+WLSQM_API int wlsqm_solver_synchronize(wlsqm_solver_t* s);
+
+/* ExpertSolver.prepare (expert.pyx:309-426) -> expert_prepare_one_{1,2,3}D (expert.pyx:788-817):
+ * make_c_*D, make_A, preprocess_A (impl.pyx:70-689).  xi: [ncases][dim] (row stride xi_s0),
+ * xk: [ncases][>=nk][dim] (strides xk_s0, xk_s1; 1D: pass dim = 1 with xk_s1 = element stride). */
+WLSQM_API int wlsqm_solver_prepare(wlsqm_solver_t* s, const double* xi, int64_t xi_s0, const double* xk, int64_t xk_s0,
+                         int64_t xk_s1);
+
+/* ExpertSolver.solve (expert.pyx:467-655) -> impl.solve / solve_iterative (impl.pyx:731-1083).
+ * fk [ncases][>=nk] (strides fk_s0, fk_s1); fi [ncases][>=no] in/out (row stride fi_s0): knowns are
+ * read, the first no_j entries of row j are written after every case has been solved
+ * (expert.pyx:548-557); sens [ncases][>=nk][>=no] (strides sens_s0, sens_s1) or NULL; required if the
+ * solver was created with do_sens.  *iters_out (may be NULL) receives the reference's return value:
+ * max refinement iterations taken, 0 for ALGO_BASIC. */
+WLSQM_API int wlsqm_solver_solve(wlsqm_solver_t* s, const double* fk, int64_t fk_s0, int64_t fk_s1, double* fi,
+                       int64_t fi_s0, double* sens, int64_t sens_s0, int64_t sens_s1, int32_t* iters_out);
+
+/* per-case refinement iteration counts of the last ALGO_ITERATIVE solve (host int32[ncases]) */
+WLSQM_API int wlsqm_solver_iterations(wlsqm_solver_t* s, int32_t* out);
+
+/* ExpertSolver.interpolate(mode='nearest') with the model index I given
+ * (expert_interpolate_nearest, expert.pyx:830-895 -> interpolate_nD, interp.pyx:252-937).
+ * x [nx][dim] (row stride x_s0), I int64[nx], diff = a DOF slot index i{1,2,3}_* or WLSQM_DIFF_ALL,
+ * out [nx] (or [nx][out_s0] for WLSQM_DIFF_ALL).  Evaluates the solver-owned copy of the last
+ * solution, as the reference evaluates Case.fi.  Invalid diff -> WLSQM_E_VALUE. */
+WLSQM_API int wlsqm_solver_interpolate(wlsqm_solver_t* s, const double* x, int64_t x_s0, const int64_t* I, int64_t nx,
+                             int diff, double* out, int64_t out_s0);
+
+/* ExpertSolver.conds (expert.pyx:429-464): 2-norm condition numbers of the scaled matrices; needs debug. */
+WLSQM_API int wlsqm_solver_conds(wlsqm_solver_t* s, double* out);
+
+/* ExpertSolver.memory_used (expert.pyx:289-306): device bytes owned by the solver (used, reserved). */
+WLSQM_API int wlsqm_solver_memory(wlsqm_solver_t* s, int64_t* used, int64_t* total);
+
+/* the solver-owned copy of the last solution, [ncases][max no] -> out (row stride out_s0) */
+WLSQM_API int wlsqm_solver_get_fi(wlsqm_solver_t* s, double* out, int64_t out_s0);
+
+/* ---- one-shot fits: wlsqm/fitter/simple.pyx:60-604 ------------------------------------------------- */
+/* fit_{1,2,3}D[_iterative]_many[_parallel] (generic_fit_*_many*, simple.pyx:731-1170): create +
+ * prepare + solve + destroy.  algorithm selects the _iterative variants.  Returns iterations in *iters_out. */
+WLSQM_API int wlsqm_fit_many(int dimension, int64_t ncases, const double* xk, int64_t xk_s0, int64_t xk_s1,
+                   const double* fk, int64_t fk_s0, int64_t fk_s1, const int32_t* nk, const double* xi,
+                   int64_t xi_s0, double* fi, int64_t fi_s0, double* sens, int64_t sens_s0, int64_t sens_s1,
+                   int do_sens, const int32_t* order, const int64_t* knowns, const int32_t* weighting_method,
+                   int algorithm, int max_iter, int device, int32_t* iters_out);
+
+/* interpolate_fit (interp.pyx:34-143): one model (xi[dim], fi[no]) evaluated at x [nx][dim]. */
+WLSQM_API int wlsqm_interpolate_fit(int dimension, int order, const double* xi, const double* fi, const double* x,
+                          int64_t x_s0, int64_t nx, int diff, double* out, int device);
+
+/* ---- batched general drivers: wlsqm/utils/lapackdrivers.pyx:1551-1723 ------------------------------ */
+/* A (n,n,nlhs) Fortran-contiguous, b (n,nlhs) Fortran, ipiv (n,nlhs) int32 Fortran, 1-based; in place. */
+WLSQM_API int wlsqm_mgetrf(int n, int64_t nlhs, double* A, int32_t* ipiv, int device);                 /* mgeneralfactor[p] */
+WLSQM_API int wlsqm_mgetrs(int n, int64_t nlhs, const double* LU, const int32_t* ipiv, double* b, int device); /* mgeneralfactored[p] */
+WLSQM_API int wlsqm_mgesv(int n, int64_t nlhs, double* A, int32_t* ipiv, double* b, int device);       /* mgeneral[p] */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WLSQM_B200_H */

@@ -1,0 +1,782 @@
+// wlsqm_capi.cu -- the C ABI declared in include/wlsqm_b200.h: solver handle, device state, staging of
+// host arrays, launch configuration.  No numerics live here; see wlsqm_prepare.cu / wlsqm_solve.cu /
+// wlsqm_interp.cu / wlsqm_lapack.cu.  There is deliberately no CPU code path: every compute entry
+// point needs a CUDA device and fails with WLSQM_E_CUDA otherwise.
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/wlsqm_b200.h"
+#include "wlsqm_common.cuh"
+#include "wlsqm_kernels.h"
+
+using namespace wlsqm;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CU(expr)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e__ = (expr);                                                                  \
+        if (e__ != cudaSuccess)                                                                    \
+            return fail(e__ == cudaErrorMemoryAllocation ? WLSQM_E_MEMORY : WLSQM_E_CUDA, "%s: %s", #expr, \
+                        cudaGetErrorString(e__));                                                  \
+    } while (0)
+
+constexpr size_t SMEM_PER_SM = 228 * 1024;      // B200: 228 KB per SM, 227 KB per CTA, 1 KB reserved per CTA
+constexpr size_t SMEM_PER_CTA = 227 * 1024;
+
+inline int even(int v) { return (v + 1) & ~1; }
+
+int env_int(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return (v && *v) ? atoi(v) : dflt;
+}
+
+// 1 = device-accessible (device or managed), 0 = host (pinned or pageable)
+int is_device_ptr(const void* p) {
+    if (!p) return 0;
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int reserve(size_t bytes) {
+        if (bytes <= cap) return WLSQM_OK;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        if (bytes == 0) return WLSQM_OK;
+        cudaError_t e = cudaMalloc(&p, bytes);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            return fail(WLSQM_E_MEMORY, "cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+        }
+        cap = bytes;
+        return WLSQM_OK;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+// strided 3-level copy  dst[i][a][b] <- src[i*s0 + a*s1 + b*s2], dst dense
+__global__ void gather3_kernel(double* __restrict__ dst, const double* __restrict__ src, long long n, int na, int nb,
+                               long long s0, long long s1, long long s2) {
+    const long long per = (long long)na * nb;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n * per;
+         t += (long long)gridDim.x * blockDim.x) {
+        const long long i = t / per;
+        const int r = (int)(t - i * per);
+        const int a = r / nb, b = r - a * nb;
+        dst[t] = src[i * s0 + a * s1 + b * s2];
+    }
+}
+
+}  // namespace
+
+struct wlsqm_solver {
+    int dim = 0, device = 0, algorithm = 1, do_sens = 0, max_iter = 0, debug = 0;
+    long long ncases = 0;
+    int maxnk = 0, maxno = 1, maxnr = 0, maxnq = 0;
+    bool uniform = true, any_knowns = false, uniform_no = true;
+    CaseMeta uni{};
+    long long op_stride = 0, op_total = 0;
+    std::vector<CaseMeta> hmeta;
+    CaseMeta* dmeta = nullptr;
+    signed char* dorder = nullptr;
+    double* op = nullptr;
+    double* fi_case = nullptr;
+    double* xi_dev = nullptr;
+    double* As = nullptr;
+    int as_stride = 0;
+    int* iters_dev = nullptr;   // [0] = max, [1..ncases] per case (ITERATIVE only)
+    bool ready = false;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int sm_count = 148;
+    DevBuf xk_keep;             // dense copy of xk (ALGO_ITERATIVE needs the geometry at solve time)
+    DevBuf st_xk, st_fk, st_fi, st_sens, st_x, st_I, st_out;
+    long long bytes_state = 0;
+};
+
+namespace {
+
+long long staging_bytes(const wlsqm_solver* s) {
+    return (long long)(s->xk_keep.cap + s->st_xk.cap + s->st_fk.cap + s->st_fi.cap + s->st_sens.cap + s->st_x.cap +
+                       s->st_I.cap + s->st_out.cap);
+}
+
+int use_device(const wlsqm_solver* s) {
+    CU(cudaSetDevice(s->device));
+    return WLSQM_OK;
+}
+
+// ---- launch configuration ------------------------------------------------------------------------
+struct LaunchCfg { int blocks, threads; size_t smem; };
+
+int config_prepare(const wlsqm_solver* s, PrepareParams& P, LaunchCfg& L) {
+    const int nk = std::max(s->maxnk, 1), no = s->maxno, nr = std::max(s->maxnr, 1), nq = std::max(s->maxnq, 1);
+    const int cs = no | 1, lda = nr | 1, sq = nq | 1;
+    int off = 0;
+    off += even(nk * cs);       P.off_w = off;
+    off += even(nk);            P.off_a = off;
+    off += even(nr * lda);      P.off_rs = off;
+    off += even(nr);            P.off_s = off;
+    off += even(nr * sq);       P.off_i = off;
+    off += 36;
+    P.warp_doubles = off;
+    const size_t per_warp = (size_t)off * 8;
+    if (per_warp > SMEM_PER_CTA)
+        return fail(WLSQM_E_VALUE, "case too large for shared memory (nk=%d, no=%d): %zu bytes per fit", nk, no, per_warp);
+    int warps = env_int("WLSQM_PREP_WARPS", 8);
+    warps = std::max(1, std::min(warps, PREP_MAX_THREADS / 32));
+    while (warps > 1 && warps * per_warp > SMEM_PER_CTA) --warps;
+    L.threads = warps * 32;
+    L.smem = warps * per_warp;
+    int ctas = (int)(SMEM_PER_SM / (L.smem + 1024));
+    ctas = std::max(1, std::min(ctas, std::max(1, 48 / warps)));
+    long long need = (s->ncases + warps - 1) / warps;
+    L.blocks = (int)std::max<long long>(1, std::min<long long>((long long)s->sm_count * ctas, need));
+    return WLSQM_OK;
+}
+
+int config_solve(const wlsqm_solver* s, SolveParams& P, LaunchCfg& L) {
+    const bool iter = s->algorithm == WLSQM_ALGO_ITERATIVE;
+    const int stage_doubles = std::max(2, even(s->maxnq * s->maxnr));
+    const size_t stage_bytes = (size_t)stage_doubles * 8;
+    int S = env_int("WLSQM_SOLVE_STAGES", stage_bytes <= 8192 ? 3 : 2);
+    S = std::max(1, std::min(S, 8));
+    int warps = env_int("WLSQM_SOLVE_WARPS", 8);
+    warps = std::max(1, std::min(warps, SOLVE_MAX_THREADS / 32));
+    size_t per_warp = 0;
+    int off_f, off_fi, off_r, off_xk, wd;
+    for (;;) {
+        off_f = S * stage_doubles;
+        off_fi = off_f + std::max(2, even(s->maxnq));
+        off_r = off_fi + 36;
+        off_xk = off_r + (iter ? std::max(2, even(s->maxnk)) : 0);
+        wd = off_xk + (iter ? std::max(2, even(s->maxnk * s->dim)) : 0);
+        wd = (wd + 15) & ~15;                      // 128 B granularity per warp slice
+        per_warp = (size_t)wd * 8 + (size_t)S * 8;
+        if (warps * per_warp <= SMEM_PER_CTA) break;
+        if (warps > 4) --warps;
+        else if (S > 2) --S;
+        else if (warps > 1) --warps;
+        else if (S > 1) --S;
+        else return fail(WLSQM_E_VALUE, "operator block too large for shared memory (%zu bytes)", stage_bytes);
+    }
+    P.stages = S;
+    P.stage_doubles = stage_doubles;
+    P.off_f = off_f; P.off_fi = off_fi; P.off_r = off_r; P.off_xk = off_xk;
+    P.warp_doubles = wd;
+    P.bar_off_bytes = warps * wd * 8;
+    L.threads = warps * 32;
+    L.smem = (size_t)P.bar_off_bytes + (size_t)warps * S * 8;
+    int ctas = (int)(SMEM_PER_SM / (L.smem + 1024));
+    ctas = std::max(1, std::min(ctas, std::max(1, env_int("WLSQM_SOLVE_MAXWARPS_SM", 48) / warps)));
+    long long need = (s->ncases + warps - 1) / warps;
+    L.blocks = (int)std::max<long long>(1, std::min<long long>((long long)s->sm_count * ctas, need));
+    return WLSQM_OK;
+}
+
+// copy a pitched host/device 2-D array of doubles into a dense device buffer (rows x width)
+int to_dense(double* dst, const double* src, long long rows, long long width, long long pitch, cudaStream_t st) {
+    if (rows == 0 || width == 0) return WLSQM_OK;
+    if (rows == 1 || pitch == width) {
+        CU(cudaMemcpyAsync(dst, src, (size_t)rows * width * 8, cudaMemcpyDefault, st));
+        return WLSQM_OK;
+    }
+    CU(cudaMemcpy2DAsync(dst, (size_t)width * 8, src, (size_t)pitch * 8, (size_t)width * 8, (size_t)rows,
+                         cudaMemcpyDefault, st));
+    return WLSQM_OK;
+}
+int from_dense(double* dst, long long pitch, const double* src, long long src_pitch, long long rows, long long width,
+               cudaStream_t st) {
+    if (rows == 0 || width == 0) return WLSQM_OK;
+    if (rows == 1 || (pitch == width && src_pitch == width)) {
+        CU(cudaMemcpyAsync(dst, src, (size_t)rows * width * 8, cudaMemcpyDefault, st));
+        return WLSQM_OK;
+    }
+    CU(cudaMemcpy2DAsync(dst, (size_t)pitch * 8, src, (size_t)src_pitch * 8, (size_t)width * 8, (size_t)rows,
+                         cudaMemcpyDefault, st));
+    return WLSQM_OK;
+}
+
+bool ranges_overlap(const void* a, long long abytes, const void* b, long long bbytes) {
+    const char* a0 = (const char*)a;
+    const char* b0 = (const char*)b;
+    return a0 < b0 + bbytes && b0 < a0 + abytes;
+}
+
+}  // namespace
+
+extern "C" {
+
+int wlsqm_b200_abi_version(void) { return 1; }
+const char* wlsqm_last_error(void) { return g_err.c_str(); }
+
+int wlsqm_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int wlsqm_number_of_dofs(int dimension, int order) { return number_of_dofs(dimension, order); }
+
+void* wlsqm_pinned_alloc(int64_t bytes) {
+    void* p = nullptr;
+    if (bytes <= 0) return nullptr;
+    if (cudaHostAlloc(&p, (size_t)bytes, cudaHostAllocDefault) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+void wlsqm_pinned_free(void* p) {
+    if (p) cudaFreeHost(p);
+}
+
+int wlsqm_solver_create(int dimension, int64_t ncases, const int32_t* nk, const int32_t* order, const int64_t* knowns,
+                        const int32_t* wm, int algorithm, int do_sens, int max_iter, int debug, int device,
+                        wlsqm_solver_t** out) {
+    if (!out) return fail(WLSQM_E_VALUE, "out is NULL");
+    *out = nullptr;
+    if (dimension < 1 || dimension > 3) return fail(WLSQM_E_VALUE, "Dimension must be 1, 2 or 3, got %d", dimension);
+    if (algorithm != WLSQM_ALGO_BASIC && algorithm != WLSQM_ALGO_ITERATIVE)
+        return fail(WLSQM_E_VALUE, "Unknown algorithm specifier %d; see wlsqm.fitter.defs for valid specifiers ALGO_*",
+                    algorithm);
+    if (ncases < 0) return fail(WLSQM_E_VALUE, "ncases must be >= 0");
+    if (ncases > 0 && (!nk || !order || !knowns || !wm)) return fail(WLSQM_E_VALUE, "NULL metadata array");
+    if (wlsqm_device_count() < 1) return fail(WLSQM_E_CUDA, "no CUDA device available (there is no CPU fallback)");
+    if (device < 0 || device >= wlsqm_device_count()) return fail(WLSQM_E_VALUE, "bad device ordinal %d", device);
+
+    wlsqm_solver* s = new (std::nothrow) wlsqm_solver();
+    if (!s) return fail(WLSQM_E_MEMORY, "out of host memory");
+    s->dim = dimension; s->device = device; s->algorithm = algorithm; s->do_sens = do_sens ? 1 : 0;
+    s->max_iter = max_iter; s->debug = debug ? 1 : 0; s->ncases = ncases;
+    try {
+        s->hmeta.resize((size_t)ncases);
+    } catch (...) {
+        delete s;
+        return fail(WLSQM_E_MEMORY, "out of host memory");
+    }
+    long long off = 0;
+    for (long long i = 0; i < ncases; ++i) {
+        const int no = number_of_dofs(dimension, order[i]);
+        if (no < 0) { delete s; return fail(WLSQM_E_VALUE, "case %lld: order must be 0..4, got %d", i, order[i]); }
+        if (nk[i] < 0) { delete s; return fail(WLSQM_E_VALUE, "case %lld: nk must be >= 0, got %d", i, nk[i]); }
+        if (wm[i] != WLSQM_WEIGHT_UNIFORM && wm[i] != WLSQM_WEIGHT_CENTER) {
+            delete s;
+            return fail(WLSQM_E_VALUE, "case %lld: unknown weighting method %d", i, wm[i]);
+        }
+        CaseMeta& m = s->hmeta[(size_t)i];
+        memset(&m, 0, sizeof m);
+        m.knowns = knowns[i] & ((1LL << no) - 1);
+        m.nkn = (signed char)__builtin_popcountll((unsigned long long)m.knowns);
+        m.nk = nk[i]; m.no = (short)no; m.nr = (short)(no - m.nkn);
+        m.order = (signed char)order[i]; m.wm = (signed char)wm[i];
+        m.op_off = off;
+        off += even((m.nk + m.nkn) * (int)m.nr);
+        s->maxnk = std::max(s->maxnk, m.nk);
+        s->maxno = std::max(s->maxno, no);
+        s->maxnr = std::max(s->maxnr, (int)m.nr);
+        s->maxnq = std::max(s->maxnq, m.nk + m.nkn);
+        if (m.knowns) s->any_knowns = true;
+        if (i > 0) {
+            const CaseMeta& f = s->hmeta[0];
+            if (m.nk != f.nk || m.order != f.order || m.knowns != f.knowns || m.wm != f.wm) s->uniform = false;
+            if (m.no != f.no) s->uniform_no = false;
+        }
+    }
+    s->op_total = off;
+    if (ncases > 0) {
+        s->uni = s->hmeta[0];
+        s->uni.op_off = 0;
+        s->op_stride = even((s->uni.nk + s->uni.nkn) * (int)s->uni.nr);
+    }
+
+    int rc = use_device(s);
+    if (rc) { delete s; return rc; }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) s->sm_count = prop.multiProcessorCount;
+    cudaError_t e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { delete s; return fail(WLSQM_E_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
+    s->own_stream = true;
+
+    auto alloc = [&](void** p, size_t bytes) -> int {
+        *p = nullptr;
+        if (bytes == 0) return WLSQM_OK;
+        cudaError_t e2 = cudaMalloc(p, bytes);
+        if (e2 != cudaSuccess) {
+            cudaGetLastError();
+            return fail(WLSQM_E_MEMORY, "cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e2));
+        }
+        s->bytes_state += (long long)bytes;
+        return WLSQM_OK;
+    };
+    rc = WLSQM_OK;
+    if (!rc && !s->uniform) rc = alloc((void**)&s->dmeta, sizeof(CaseMeta) * (size_t)ncases);
+    if (!rc && !s->uniform_no) rc = alloc((void**)&s->dorder, (size_t)ncases);
+    if (!rc) rc = alloc((void**)&s->op, (size_t)s->op_total * 8);
+    if (!rc) rc = alloc((void**)&s->fi_case, (size_t)ncases * s->maxno * 8);
+    if (!rc) rc = alloc((void**)&s->xi_dev, (size_t)ncases * dimension * 8);
+    if (!rc && s->debug) {
+        s->as_stride = s->maxnr * s->maxnr;
+        rc = alloc((void**)&s->As, (size_t)ncases * s->as_stride * 8);
+    }
+    if (!rc && algorithm == WLSQM_ALGO_ITERATIVE) rc = alloc((void**)&s->iters_dev, ((size_t)ncases + 1) * 4);
+    if (rc) { wlsqm_solver_destroy(s); return rc; }
+    if (s->dmeta)
+        cudaMemcpyAsync(s->dmeta, s->hmeta.data(), sizeof(CaseMeta) * (size_t)ncases, cudaMemcpyHostToDevice, s->stream);
+    if (s->dorder) {
+        std::vector<signed char> ho((size_t)ncases);
+        for (long long i = 0; i < ncases; ++i) ho[(size_t)i] = s->hmeta[(size_t)i].order;
+        cudaMemcpyAsync(s->dorder, ho.data(), (size_t)ncases, cudaMemcpyHostToDevice, s->stream);
+        cudaStreamSynchronize(s->stream);
+    }
+    if (s->fi_case) cudaMemsetAsync(s->fi_case, 0, (size_t)ncases * s->maxno * 8, s->stream);
+    e = cudaStreamSynchronize(s->stream);
+    if (e != cudaSuccess) {
+        wlsqm_solver_destroy(s);
+        return fail(WLSQM_E_CUDA, "solver initialisation: %s", cudaGetErrorString(e));
+    }
+    *out = s;
+    return WLSQM_OK;
+}
+
+int wlsqm_solver_destroy(wlsqm_solver_t* s) {
+    if (!s) return WLSQM_OK;
+    cudaSetDevice(s->device);
+    if (s->stream) cudaStreamSynchronize(s->stream);
+    cudaFree(s->dmeta); cudaFree(s->dorder); cudaFree(s->op); cudaFree(s->fi_case); cudaFree(s->xi_dev);
+    cudaFree(s->As); cudaFree(s->iters_dev);
+    s->xk_keep.release(); s->st_xk.release(); s->st_fk.release(); s->st_fi.release(); s->st_sens.release();
+    s->st_x.release(); s->st_I.release(); s->st_out.release();
+    if (s->own_stream && s->stream) cudaStreamDestroy(s->stream);
+    cudaGetLastError();
+    delete s;
+    return WLSQM_OK;
+}
+
+int wlsqm_solver_set_stream(wlsqm_solver_t* s, void* cuda_stream) {
+    if (!s) return fail(WLSQM_E_VALUE, "NULL solver");
+    if (s->own_stream && s->stream) {
+        cudaSetDevice(s->device);
+        cudaStreamSynchronize(s->stream);
+        cudaStreamDestroy(s->stream);
+    }
+    s->stream = (cudaStream_t)cuda_stream;
+    s->own_stream = false;
+    return WLSQM_OK;
+}
+
+int wlsqm_solver_synchronize(wlsqm_solver_t* s) {
+    if (!s) return fail(WLSQM_E_VALUE, "NULL solver");
+    int rc = use_device(s);
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(s->stream));
+    return WLSQM_OK;
+}
+
+int wlsqm_solver_prepare(wlsqm_solver_t* s, const double* xi, int64_t xi_s0, const double* xk, int64_t xk_s0,
+                         int64_t xk_s1) {
+    if (!s) return fail(WLSQM_E_VALUE, "NULL solver");
+    s->ready = false;
+    if (s->ncases == 0) { s->ready = true; return WLSQM_OK; }
+    if (!xi || !xk) return fail(WLSQM_E_VALUE, "xi and xk must not be NULL");
+    int rc = use_device(s);
+    if (rc) return rc;
+    const int dim = s->dim;
+    const long long n = s->ncases;
+    const bool iter = s->algorithm == WLSQM_ALGO_ITERATIVE;
+
+    // origins: always kept (interpolate and ALGO_ITERATIVE need them)
+    rc = to_dense(s->xi_dev, xi, n, dim, xi_s0, s->stream);
+    if (rc) return rc;
+
+    const double* xk_use = xk;
+    long long s0 = xk_s0, s1 = xk_s1;
+    const bool xk_dev = is_device_ptr(xk);
+    if (!xk_dev || iter) {
+        DevBuf& buf = iter ? s->xk_keep : s->st_xk;
+        const long long row = (long long)s->maxnk * dim;
+        rc = buf.reserve((size_t)n * row * 8);
+        if (rc) return rc;
+        if (xk_s1 == dim) {
+            rc = to_dense((double*)buf.p, xk, n, row, xk_s0, s->stream);
+            if (rc) return rc;
+        } else if (xk_dev) {
+            gather3_kernel<<<s->sm_count * 8, 256, 0, s->stream>>>((double*)buf.p, xk, n, s->maxnk, dim, xk_s0, xk_s1, 1);
+            CU(cudaGetLastError());
+        } else {
+            return fail(WLSQM_E_VALUE, "host xk must have contiguous neighbour rows (stride %lld != %d)", (long long)xk_s1, dim);
+        }
+        xk_use = (const double*)buf.p;
+        s0 = row;
+        s1 = dim;
+    }
+
+    PrepareParams P{};
+    P.meta = s->dmeta; P.uni = s->uni; P.op_stride = s->op_stride; P.ncases = n;
+    P.xi = s->xi_dev; P.xi_s0 = dim;
+    P.xk = xk_use; P.xk_s0 = s0; P.xk_s1 = s1;
+    P.op = s->op; P.As = s->As; P.as_stride = s->as_stride;
+    LaunchCfg L;
+    rc = config_prepare(s, P, L);
+    if (rc) return rc;
+    CU(launch_prepare(dim, P, L.blocks, L.threads, L.smem, s->stream));
+    if (!xk_dev) {
+        // the call owns the host array only until it returns
+        CU(cudaStreamSynchronize(s->stream));
+        if (!iter) s->st_xk.release();
+    }
+    s->ready = true;
+    return WLSQM_OK;
+}
+
+int wlsqm_solver_solve(wlsqm_solver_t* s, const double* fk, int64_t fk_s0, int64_t fk_s1, double* fi, int64_t fi_s0,
+                       double* sens, int64_t sens_s0, int64_t sens_s1, int32_t* iters_out) {
+    if (!s) return fail(WLSQM_E_VALUE, "NULL solver");
+    if (!s->ready) return fail(WLSQM_E_NOTREADY, "Solver is not in the ready state; prepare() must be called before solve()");
+    if (iters_out) *iters_out = 0;
+    if (s->ncases == 0) return WLSQM_OK;
+    if (!fk || !fi) return fail(WLSQM_E_VALUE, "fk and fi must not be NULL");
+    if (s->do_sens && !sens) return fail(WLSQM_E_VALUE, "sens must be given when do_sens is set");
+    int rc = use_device(s);
+    if (rc) return rc;
+    const long long n = s->ncases;
+    const bool iter = s->algorithm == WLSQM_ALGO_ITERATIVE;
+    const bool fk_dev = is_device_ptr(fk), fi_dev = is_device_ptr(fi);
+    const bool sens_dev = s->do_sens ? (is_device_ptr(sens) != 0) : true;
+    cudaStream_t st = s->stream;
+
+    SolveParams P{};
+    P.meta = s->dmeta; P.uni = s->uni; P.op_stride = s->op_stride; P.ncases = n; P.op = s->op;
+    P.algorithm = s->algorithm; P.max_iter = s->max_iter;
+    P.fi_case = s->fi_case; P.fi_case_ld = s->maxno;
+    P.xi = s->xi_dev; P.xi_s0 = s->dim;
+    P.xk = (const double*)s->xk_keep.p; P.xk_s0 = (long long)s->maxnk * s->dim; P.xk_s1 = s->dim;
+    if (iter) {
+        CU(cudaMemsetAsync(s->iters_dev, 0, 4, st));
+        P.iters_max = s->iters_dev;
+        P.iters_case = s->iters_dev + 1;
+    }
+
+    // fk
+    if (fk_dev) {
+        P.fk = fk; P.fk_s0 = fk_s0; P.fk_s1 = fk_s1;
+    } else {
+        if (fk_s1 != 1 && s->maxnk > 1) return fail(WLSQM_E_VALUE, "host fk must have unit stride on its last axis");
+        rc = s->st_fk.reserve((size_t)n * s->maxnk * 8);
+        if (rc) return rc;
+        rc = to_dense((double*)s->st_fk.p, fk, n, s->maxnk, fk_s0, st);
+        if (rc) return rc;
+        P.fk = (const double*)s->st_fk.p; P.fk_s0 = s->maxnk; P.fk_s1 = 1;
+    }
+    // fi (known values in; unknowns out)
+    bool deferred = false;
+    if (fi_dev) {
+        P.fi_in = fi; P.fi_in_s0 = fi_s0;
+        // the caller's fk may be a view into fi (expert.pyx:548-555): then write back only after all cases are solved
+        bool alias = false;
+        if (fk_dev) {
+            if (fk_s0 < 0 || fk_s1 < 0 || fi_s0 < 0) alias = true;
+            else
+                alias = ranges_overlap(fk, ((n - 1) * fk_s0 + (long long)(s->maxnk - 1) * fk_s1 + 1) * 8, fi,
+                                       ((n - 1) * fi_s0 + s->maxno) * 8);
+        }
+        if (alias) deferred = true;
+        else { P.fi_out = fi; P.fi_out_s0 = fi_s0; }
+    } else {
+        if (s->any_knowns) {
+            rc = s->st_fi.reserve((size_t)n * s->maxno * 8);
+            if (rc) return rc;
+            rc = to_dense((double*)s->st_fi.p, fi, n, s->maxno, fi_s0, st);
+            if (rc) return rc;
+            P.fi_in = (const double*)s->st_fi.p; P.fi_in_s0 = s->maxno;
+        }
+    }
+    // sens
+    if (s->do_sens) {
+        if (sens_dev) {
+            P.sens = sens; P.sens_s0 = sens_s0; P.sens_s1 = sens_s1;
+        } else {
+            rc = s->st_sens.reserve((size_t)n * s->maxnk * s->maxno * 8);
+            if (rc) return rc;
+            P.sens = (double*)s->st_sens.p; P.sens_s0 = (long long)s->maxnk * s->maxno; P.sens_s1 = s->maxno;
+        }
+    }
+
+    LaunchCfg L;
+    rc = config_solve(s, P, L);
+    if (rc) return rc;
+    CU(launch_solve(s->dim, P, L.blocks, L.threads, L.smem, st));
+    if (deferred) CU(launch_scatter_fi(s->dmeta, s->uni, n, s->fi_case, s->maxno, fi, fi_s0, st));
+
+    // results to host
+    if (!fi_dev) {
+        if (s->uniform_no) {
+            rc = from_dense(fi, fi_s0, s->fi_case, s->maxno, n, s->uni.no, st);
+            if (rc) return rc;
+        } else {
+            std::vector<double> tmp((size_t)n * s->maxno);
+            CU(cudaMemcpyAsync(tmp.data(), s->fi_case, tmp.size() * 8, cudaMemcpyDeviceToHost, st));
+            CU(cudaStreamSynchronize(st));
+            for (long long i = 0; i < n; ++i)
+                memcpy(fi + i * fi_s0, tmp.data() + (size_t)i * s->maxno, (size_t)s->hmeta[(size_t)i].no * 8);
+        }
+    }
+    if (s->do_sens && !sens_dev) {
+        const long long plane = (long long)s->maxnk * s->maxno;
+        if (s->uniform && s->uni.nk == s->maxnk && sens_s1 == s->maxno && sens_s0 == plane) {
+            CU(cudaMemcpyAsync(sens, s->st_sens.p, (size_t)n * plane * 8, cudaMemcpyDeviceToHost, st));
+        } else {
+            std::vector<double> tmp((size_t)n * plane);
+            CU(cudaMemcpyAsync(tmp.data(), s->st_sens.p, tmp.size() * 8, cudaMemcpyDeviceToHost, st));
+            CU(cudaStreamSynchronize(st));
+            for (long long i = 0; i < n; ++i) {
+                const CaseMeta& m = s->hmeta[(size_t)i];
+                for (int k = 0; k < m.nk; ++k)
+                    memcpy(sens + i * sens_s0 + (long long)k * sens_s1, tmp.data() + (size_t)i * plane + (size_t)k * s->maxno,
+                           (size_t)m.no * 8);
+            }
+        }
+    }
+    int32_t it = 0;
+    if (iter) CU(cudaMemcpyAsync(&it, s->iters_dev, 4, cudaMemcpyDeviceToHost, st));
+    if (iter || !fk_dev || !fi_dev || !sens_dev) CU(cudaStreamSynchronize(st));
+    if (iters_out) *iters_out = it;
+    return WLSQM_OK;
+}
+
+int wlsqm_solver_iterations(wlsqm_solver_t* s, int32_t* out) {
+    if (!s || !out) return fail(WLSQM_E_VALUE, "NULL argument");
+    if (s->algorithm != WLSQM_ALGO_ITERATIVE) {
+        memset(out, 0, (size_t)s->ncases * 4);
+        return WLSQM_OK;
+    }
+    int rc = use_device(s);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(out, s->iters_dev + 1, (size_t)s->ncases * 4, cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    return WLSQM_OK;
+}
+
+int wlsqm_solver_interpolate(wlsqm_solver_t* s, const double* x, int64_t x_s0, const int64_t* I, int64_t nx, int diff,
+                             double* out, int64_t out_s0) {
+    if (!s) return fail(WLSQM_E_VALUE, "NULL solver");
+    if (!s->ready) return fail(WLSQM_E_NOTREADY, "Solver is not in the ready state; prepare() must be called first");
+    if (nx == 0) return WLSQM_OK;
+    if (!x || !I || !out) return fail(WLSQM_E_VALUE, "x, I and out must not be NULL");
+    const int size = number_of_dofs(s->dim, 4);
+    if (diff != WLSQM_DIFF_ALL && (diff < 0 || diff >= size)) return fail(WLSQM_E_VALUE, "invalid diff %d", diff);
+    int rc = use_device(s);
+    if (rc) return rc;
+    cudaStream_t st = s->stream;
+    const bool x_dev = is_device_ptr(x), I_dev = is_device_ptr(I), out_dev = is_device_ptr(out);
+    const long long ow = diff == WLSQM_DIFF_ALL ? s->maxno : 1;
+    InterpParams P{};
+    P.dim = s->dim; P.nx = nx; P.diff = diff;
+    P.xi = s->xi_dev; P.xi_s0 = s->dim; P.fi = s->fi_case; P.fi_s0 = s->maxno;
+    P.order = s->dorder; P.order_uniform = s->uni.order;
+    if (x_dev) { P.x = x; P.x_s0 = x_s0; }
+    else {
+        rc = s->st_x.reserve((size_t)nx * s->dim * 8);
+        if (rc) return rc;
+        rc = to_dense((double*)s->st_x.p, x, nx, s->dim, x_s0, st);
+        if (rc) return rc;
+        P.x = (const double*)s->st_x.p; P.x_s0 = s->dim;
+    }
+    if (I_dev) P.I = (const long long*)I;
+    else {
+        rc = s->st_I.reserve((size_t)nx * 8);
+        if (rc) return rc;
+        CU(cudaMemcpyAsync(s->st_I.p, I, (size_t)nx * 8, cudaMemcpyHostToDevice, st));
+        P.I = (const long long*)s->st_I.p;
+    }
+    if (out_dev) { P.out = out; P.out_s0 = diff == WLSQM_DIFF_ALL ? out_s0 : 1; }
+    else {
+        rc = s->st_out.reserve((size_t)nx * ow * 8);
+        if (rc) return rc;
+        if (diff == WLSQM_DIFF_ALL && !s->uniform_no) CU(cudaMemsetAsync(s->st_out.p, 0, (size_t)nx * ow * 8, st));
+        P.out = (double*)s->st_out.p; P.out_s0 = ow;
+    }
+    CU(launch_interpolate(P, st));
+    if (!out_dev) {
+        if (diff == WLSQM_DIFF_ALL) rc = from_dense(out, out_s0, (const double*)s->st_out.p, ow, nx, ow, st);
+        else { CU(cudaMemcpyAsync(out, s->st_out.p, (size_t)nx * 8, cudaMemcpyDeviceToHost, st)); }
+        if (rc) return rc;
+    }
+    if (!x_dev || !I_dev || !out_dev) CU(cudaStreamSynchronize(st));
+    return WLSQM_OK;
+}
+
+int wlsqm_solver_conds(wlsqm_solver_t* s, double* out) {
+    if (!s || !out) return fail(WLSQM_E_VALUE, "NULL argument");
+    if (!s->ready) return fail(WLSQM_E_NOTREADY, "Solver is not in the ready state; prepare() must be called before conds()");
+    if (!s->debug) return fail(WLSQM_E_NOTREADY, "Not in debug mode; condition number data has not been computed");
+    if (s->ncases == 0) return WLSQM_OK;
+    int rc = use_device(s);
+    if (rc) return rc;
+    const bool out_dev = is_device_ptr(out);
+    double* d = out;
+    if (!out_dev) {
+        rc = s->st_out.reserve((size_t)s->ncases * 8);
+        if (rc) return rc;
+        d = (double*)s->st_out.p;
+    }
+    CU(launch_cond(s->maxnr, s->ncases, s->dmeta, s->uni, s->As, s->as_stride, d, s->stream));
+    if (!out_dev) CU(cudaMemcpyAsync(out, d, (size_t)s->ncases * 8, cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    return WLSQM_OK;
+}
+
+int wlsqm_solver_memory(wlsqm_solver_t* s, int64_t* used, int64_t* total) {
+    if (!s) return fail(WLSQM_E_VALUE, "NULL solver");
+    if (used) *used = s->bytes_state;
+    if (total) *total = s->bytes_state + staging_bytes(s);
+    return WLSQM_OK;
+}
+
+int wlsqm_solver_get_fi(wlsqm_solver_t* s, double* out, int64_t out_s0) {
+    if (!s || !out) return fail(WLSQM_E_VALUE, "NULL argument");
+    if (s->ncases == 0) return WLSQM_OK;
+    int rc = use_device(s);
+    if (rc) return rc;
+    rc = from_dense(out, out_s0, s->fi_case, s->maxno, s->ncases, s->maxno, s->stream);
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(s->stream));
+    return WLSQM_OK;
+}
+
+int wlsqm_fit_many(int dimension, int64_t ncases, const double* xk, int64_t xk_s0, int64_t xk_s1, const double* fk,
+                   int64_t fk_s0, int64_t fk_s1, const int32_t* nk, const double* xi, int64_t xi_s0, double* fi,
+                   int64_t fi_s0, double* sens, int64_t sens_s0, int64_t sens_s1, int do_sens, const int32_t* order,
+                   const int64_t* knowns, const int32_t* wm, int algorithm, int max_iter, int device,
+                   int32_t* iters_out) {
+    wlsqm_solver_t* s = nullptr;
+    int rc = wlsqm_solver_create(dimension, ncases, nk, order, knowns, wm, algorithm, do_sens, max_iter, 0, device, &s);
+    if (rc) return rc;
+    rc = wlsqm_solver_prepare(s, xi, xi_s0, xk, xk_s0, xk_s1);
+    if (!rc) rc = wlsqm_solver_solve(s, fk, fk_s0, fk_s1, fi, fi_s0, sens, sens_s0, sens_s1, iters_out);
+    if (!rc) rc = wlsqm_solver_synchronize(s);
+    std::string keep = g_err;
+    wlsqm_solver_destroy(s);
+    g_err = keep;
+    return rc;
+}
+
+int wlsqm_interpolate_fit(int dimension, int order, const double* xi, const double* fi, const double* x, int64_t x_s0,
+                          int64_t nx, int diff, double* out, int device) {
+    if (dimension < 1 || dimension > 3) return fail(WLSQM_E_VALUE, "dimension must be 1, 2 or 3; got %d", dimension);
+    const int no = number_of_dofs(dimension, order);
+    if (no < 0) return fail(WLSQM_E_VALUE, "order must be 0, 1, 2, 3 or 4; got %d", order);
+    const int size = number_of_dofs(dimension, 4);
+    if (diff != WLSQM_DIFF_ALL && (diff < 0 || diff >= size)) return fail(WLSQM_E_VALUE, "invalid diff %d", diff);
+    if (nx == 0) return WLSQM_OK;
+    if (!xi || !fi || !x || !out) return fail(WLSQM_E_VALUE, "NULL argument");
+    if (wlsqm_device_count() < 1) return fail(WLSQM_E_CUDA, "no CUDA device available (there is no CPU fallback)");
+    CU(cudaSetDevice(device));
+    const long long ow = diff == WLSQM_DIFF_ALL ? no : 1;
+    DevBuf bm, bx, bo;
+    int rc = bm.reserve((size_t)(dimension + no) * 8);
+    if (!rc && !is_device_ptr(x)) rc = bx.reserve((size_t)nx * dimension * 8);
+    if (!rc && !is_device_ptr(out)) rc = bo.reserve((size_t)nx * ow * 8);
+    auto done = [&](int r) { bm.release(); bx.release(); bo.release(); return r; };
+    if (rc) return done(rc);
+    cudaStream_t st = nullptr;
+    double* dm = (double*)bm.p;
+    cudaError_t e = cudaMemcpyAsync(dm, xi, (size_t)dimension * 8, cudaMemcpyDefault, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dm + dimension, fi, (size_t)no * 8, cudaMemcpyDefault, st);
+    if (e != cudaSuccess) return done(fail(WLSQM_E_CUDA, "interpolate_fit upload: %s", cudaGetErrorString(e)));
+    InterpParams P{};
+    P.dim = dimension; P.nx = nx; P.diff = diff; P.I = nullptr;
+    P.xi = dm; P.xi_s0 = dimension; P.fi = dm + dimension; P.fi_s0 = no; P.order = nullptr; P.order_uniform = order;
+    if (bx.p) {
+        rc = to_dense((double*)bx.p, x, nx, dimension, x_s0, st);
+        if (rc) return done(rc);
+        P.x = (const double*)bx.p; P.x_s0 = dimension;
+    } else { P.x = x; P.x_s0 = x_s0; }
+    P.out = bo.p ? (double*)bo.p : out; P.out_s0 = ow;
+    e = launch_interpolate(P, st);
+    if (e == cudaSuccess && bo.p) e = cudaMemcpyAsync(out, bo.p, (size_t)nx * ow * 8, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return done(fail(WLSQM_E_CUDA, "interpolate_fit: %s", cudaGetErrorString(e)));
+    return done(WLSQM_OK);
+}
+
+static int lapack_common(int n, int64_t nlhs, double* A, int32_t* ipiv, double* b, int device, int do_factor, int do_solve) {
+    if (n < 0 || nlhs < 0) return fail(WLSQM_E_VALUE, "n and nlhs must be >= 0");
+    if (n == 0 || nlhs == 0) return WLSQM_OK;
+    if (wlsqm_device_count() < 1) return fail(WLSQM_E_CUDA, "no CUDA device available (there is no CPU fallback)");
+    CU(cudaSetDevice(device));
+    const size_t na = (size_t)n * n * nlhs * 8, np = (size_t)n * nlhs * 4, nb = (size_t)n * nlhs * 8;
+    DevBuf ba, bp, bb;
+    const bool a_dev = is_device_ptr(A), p_dev = is_device_ptr(ipiv), b_dev = b ? is_device_ptr(b) != 0 : true;
+    int rc = WLSQM_OK;
+    if (!a_dev) rc = ba.reserve(na);
+    if (!rc && !p_dev) rc = bp.reserve(np);
+    if (!rc && !b_dev) rc = bb.reserve(nb);
+    auto done = [&](int r) { ba.release(); bp.release(); bb.release(); return r; };
+    if (rc) return done(rc);
+    cudaStream_t st = nullptr;
+    double* dA = a_dev ? A : (double*)ba.p;
+    int* dP = p_dev ? ipiv : (int*)bp.p;
+    double* dB = b_dev ? b : (double*)bb.p;
+    cudaError_t e = cudaSuccess;
+    if (!a_dev) e = cudaMemcpyAsync(dA, A, na, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess && !p_dev && !do_factor) e = cudaMemcpyAsync(dP, ipiv, np, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess && do_solve && !b_dev) e = cudaMemcpyAsync(dB, b, nb, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess && do_factor) e = launch_getrf(n, nlhs, dA, dP, st);
+    if (e == cudaSuccess && do_solve) e = launch_getrs(n, nlhs, dA, dP, dB, st);
+    if (e == cudaSuccess && do_factor && !a_dev) e = cudaMemcpyAsync(A, dA, na, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess && do_factor && !p_dev) e = cudaMemcpyAsync(ipiv, dP, np, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess && do_solve && !b_dev) e = cudaMemcpyAsync(b, dB, nb, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e == cudaErrorInvalidValue) return done(fail(WLSQM_E_VALUE, "n = %d is too large for the shared-memory LU", n));
+    if (e != cudaSuccess) return done(fail(WLSQM_E_CUDA, "batched LU: %s", cudaGetErrorString(e)));
+    return done(WLSQM_OK);
+}
+
+int wlsqm_mgetrf(int n, int64_t nlhs, double* A, int32_t* ipiv, int device) {
+    if (!A || !ipiv) return fail(WLSQM_E_VALUE, "NULL argument");
+    return lapack_common(n, nlhs, A, ipiv, nullptr, device, 1, 0);
+}
+int wlsqm_mgetrs(int n, int64_t nlhs, const double* LU, const int32_t* ipiv, double* b, int device) {
+    if (!LU || !ipiv || !b) return fail(WLSQM_E_VALUE, "NULL argument");
+    return lapack_common(n, nlhs, const_cast<double*>(LU), const_cast<int32_t*>(ipiv), b, device, 0, 1);
+}
+int wlsqm_mgesv(int n, int64_t nlhs, double* A, int32_t* ipiv, double* b, int device) {
+    if (!A || !ipiv || !b) return fail(WLSQM_E_VALUE, "NULL argument");
+    return lapack_common(n, nlhs, A, ipiv, b, device, 1, 1);
+}
+
+}  // extern "C"

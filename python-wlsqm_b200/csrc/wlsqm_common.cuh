@@ -1,0 +1,182 @@
+// wlsqm_common.cuh -- shared device/host definitions for the wlsqm B200 kernels.
+//
+// DOF slot tables (exponents of dx,dy,dz per slot) follow the reference's slot order, which is ABI:
+//   wlsqm/fitter/defs.pyx:91-103 (1D), :107-133 (2D), :137-183 (3D, irregular order
+//   X2,XY,Y2,YZ,Z2,XZ / X3,X2Y,XY2,Y3,Y2Z,YZ2,Z3,XZ2,X2Z,XYZ / X4,...,XYZ2).
+// Everything here is written for sm_100a only.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define WLSQM_MAXNO 35          // 3D order 4
+#define WLSQM_ALGO_BASIC 1      // defs.pyx:69-70
+#define WLSQM_ALGO_ITERATIVE 2
+#define WLSQM_WEIGHT_UNIFORM 1  // defs.pyx:74-75
+#define WLSQM_WEIGHT_CENTER 2
+
+namespace wlsqm {
+
+// Per-case record (32 B, one aligned load per warp).  Built on the host at solver creation
+// (replaces the reference's Case struct, infra.pxd:124-182, and remap(), infra.pyx:145-200).
+struct __align__(16) CaseMeta {
+    long long op_off;   // offset (in doubles, even) of this case's operator block
+    long long knowns;   // bitmask, already restricted to the low `no` bits
+    int nk;             // neighbours used by this case
+    short no;           // DOFs of the full model
+    short nr;           // unknown DOFs = no - popcount(knowns)
+    signed char order, wm, nkn, pad0;
+    int pad1;
+};
+static_assert(sizeof(CaseMeta) == 32, "CaseMeta must be 32 bytes");
+
+// exponents (a,b,c) of every DOF slot; 1D and 2D tables are padded with c = 0 / b = c = 0
+struct SlotExp { unsigned char a, b, c; };
+
+__host__ __device__ constexpr SlotExp slot_exp_1d(int s) { return SlotExp{(unsigned char)s, 0, 0}; }
+__host__ __device__ constexpr SlotExp slot_exp_2d(int s) {
+    // order-major, within an order X^(d)Y^0, X^(d-1)Y^1, ..., Y^d
+    int d = 0, base = 0;
+    while (base + d + 1 <= s) { base += d + 1; ++d; }
+    int b = s - base;
+    return SlotExp{(unsigned char)(d - b), (unsigned char)b, 0};
+}
+__host__ __device__ constexpr SlotExp slot_exp_3d(int s) {
+    constexpr unsigned char T[35][3] = {
+        {0,0,0},
+        {1,0,0},{0,1,0},{0,0,1},
+        {2,0,0},{1,1,0},{0,2,0},{0,1,1},{0,0,2},{1,0,1},
+        {3,0,0},{2,1,0},{1,2,0},{0,3,0},{0,2,1},{0,1,2},{0,0,3},{1,0,2},{2,0,1},{1,1,1},
+        {4,0,0},{3,1,0},{2,2,0},{1,3,0},{0,4,0},{0,3,1},{0,2,2},{0,1,3},{0,0,4},{1,0,3},
+        {2,0,2},{3,0,1},{2,1,1},{1,2,1},{1,1,2}};
+    return SlotExp{T[s][0], T[s][1], T[s][2]};
+}
+template <int DIM> __host__ __device__ constexpr SlotExp slot_exp(int s) {
+    return DIM == 1 ? slot_exp_1d(s) : (DIM == 2 ? slot_exp_2d(s) : slot_exp_3d(s));
+}
+template <int DIM> __host__ __device__ constexpr int max_no() { return DIM == 1 ? 5 : (DIM == 2 ? 15 : 35); }
+
+__host__ __device__ inline int number_of_dofs(int dim, int order) {   // infra.pyx:67-112
+    if (dim < 1 || dim > 3) return -1;
+    if (order < 0 || order > 4) return -2;
+    const int N[3][5] = {{1,2,3,4,5},{1,3,6,10,15},{1,4,10,20,35}};
+    return N[dim-1][order];
+}
+
+// ---------------------------------------------------------------------------------------------
+// device helpers
+// ---------------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+
+// scaled powers p[a] = d^a / a!  (a = 0..4)
+struct Pow5 { double p[5]; };
+__device__ __forceinline__ Pow5 scaled_powers(double d) {
+    Pow5 r;
+    r.p[0] = 1.0; r.p[1] = d; r.p[2] = 0.5 * (d * d);
+    r.p[3] = (1.0 / 6.0) * ((d * d) * d);
+    r.p[4] = (1.0 / 24.0) * ((d * d) * (d * d));
+    return r;
+}
+
+// Monomial c^(s) = dx^a dy^b dz^c / (a! b! c!) of slot S (compile-time), from per-axis scaled powers.
+// Reference: make_c_{1,2,3}D, wlsqm/fitter/impl.pyx:449-544 / 286-432 / 70-269.
+// UNIT0 = true asserts p[0] == 1 on every axis (plain scaled powers) so zero exponents are skipped;
+// the derivative evaluator passes shifted tables whose p[0] may be 0 and uses UNIT0 = false.
+template <int DIM, int S, bool UNIT0 = true>
+__device__ __forceinline__ double monomial(const Pow5& px, const Pow5& py, const Pow5& pz) {
+    constexpr SlotExp e = slot_exp<DIM>(S);
+    if (!UNIT0) {
+        double v = px.p[e.a];
+        if (DIM >= 2) v *= py.p[e.b];
+        if (DIM >= 3) v *= pz.p[e.c];
+        return v;
+    }
+    double v = px.p[e.a];
+    if (DIM >= 2 && e.b > 0) v = (e.a > 0) ? v * py.p[e.b] : py.p[e.b];
+    if (DIM >= 3 && e.c > 0) v = (e.a + e.b > 0) ? v * pz.p[e.c] : pz.p[e.c];
+    return v;
+}
+
+// compile-time loop helper
+template <int I, int N, typename F>
+__device__ __forceinline__ void static_for(F&& f) {
+    if constexpr (I < N) { f(std::integral_constant<int, I>{}); static_for<I + 1, N>(f); }
+}
+
+// Model value at offset (dx,dy,dz) from the origin: sum_s fi[s] * monomial_s, highest slots first
+// (small terms first).  Same quantity as taylor_{1,2,3}D (wlsqm/fitter/polyeval.pyx:874-948 /
+// 550-734 / 82-354), which hard-codes one nested Horner form per (dimension, order); here one
+// table-driven sum serves all of them.  `fi` may live in shared or global memory.
+template <int DIM>
+__device__ __forceinline__ double eval_taylor(int no, const double* __restrict__ fi,
+                                              double dx, double dy, double dz) {
+    const Pow5 px = scaled_powers(dx);
+    const Pow5 py = scaled_powers(DIM >= 2 ? dy : 0.0);
+    const Pow5 pz = scaled_powers(DIM >= 3 ? dz : 0.0);
+    double acc = 0.0;
+    static_for<0, max_no<DIM>()>([&](auto I) {
+        constexpr int S = max_no<DIM>() - 1 - decltype(I)::value;
+        if (S < no) acc = fma(fi[S], monomial<DIM, S>(px, py, pz), acc);
+    });
+    return acc;
+}
+
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// ---- mbarrier + 1D bulk-TMA wrappers (cp.async.bulk, SASS: UBLKCP) ---------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+}
+// global -> shared bulk copy, completion signalled on `bar` (bytes: multiple of 16, 16B aligned)
+__device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem, uint32_t bytes,
+                                            uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            smem_u32(dst_smem)),
+        "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+// shared -> global bulk store (bulk async-group completion)
+__device__ __forceinline__ void tma_store_1d(void* dst_gmem, const void* src_smem, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem),
+                 "r"(smem_u32(src_smem)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() {
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+// streaming (evict-first) global accesses for data touched exactly once per pass
+__device__ __forceinline__ double ld_stream(const double* p) { return __ldcs(p); }
+__device__ __forceinline__ void st_stream(double* p, double v) { __stcs(p, v); }
+
+#endif  // __CUDACC__
+}  // namespace wlsqm

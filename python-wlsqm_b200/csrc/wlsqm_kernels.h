@@ -1,0 +1,67 @@
+// wlsqm_kernels.h -- parameter blocks and launchers shared by the kernels and the C-ABI layer.
+#pragma once
+#include <cuda_runtime.h>
+#include "wlsqm_common.cuh"
+
+namespace wlsqm {
+
+constexpr int PREP_MAX_THREADS = 512;
+constexpr int SOLVE_MAX_THREADS = 512;
+
+// All strides are in elements (doubles), all offsets into per-warp shared memory in doubles.
+struct PrepareParams {
+    const CaseMeta* meta;   // per-case records, or nullptr when the batch is uniform
+    CaseMeta uni;           // the uniform record (op_off ignored)
+    long long op_stride;    // uniform batches: doubles per operator block
+    long long ncases;
+    const double* xi; long long xi_s0;               // [ncases][dim]
+    const double* xk; long long xk_s0, xk_s1;        // [ncases][nk][dim], last axis contiguous
+    double* op;                                      // operator blocks (output)
+    double* As; int as_stride;                       // debug: scaled matrices [ncases][as_stride] or nullptr
+    int warp_doubles, off_w, off_a, off_rs, off_s, off_i;
+};
+
+struct SolveParams {
+    const CaseMeta* meta;
+    CaseMeta uni;
+    long long op_stride;
+    long long ncases;
+    const double* op;
+    const double* fk; long long fk_s0, fk_s1;        // [ncases][nk] fully strided (simple.pyx:149-159)
+    const double* fi_in; long long fi_in_s0;         // caller's fi (known values are read from it)
+    double* fi_case; int fi_case_ld;                 // solver-owned copy of the solution (Case.fi)
+    double* fi_out; long long fi_out_s0;             // caller's fi on the device, or nullptr (deferred write-back)
+    double* sens; long long sens_s0, sens_s1;        // [ncases][nk][no], last axis contiguous, or nullptr
+    int algorithm, max_iter;
+    const double* xi; long long xi_s0;               // ALGO_ITERATIVE: geometry kept at prepare()
+    const double* xk; long long xk_s0, xk_s1;
+    int* iters_max;                                  // max refinement iterations over all cases
+    int* iters_case;                                 // optional per-case iteration counts
+    int stages, stage_doubles;                       // TMA ring per warp
+    int warp_doubles, off_f, off_fi, off_r, off_xk;  // per-warp smem carve-up (doubles)
+    int bar_off_bytes;                               // start of the mbarrier array
+};
+
+struct InterpParams {
+    int dim;
+    long long nx;
+    const double* x; long long x_s0;                 // [nx][dim]
+    const long long* I;                              // [nx] model index, or nullptr (single model 0)
+    const double* xi; long long xi_s0;               // model origins [nmodels][dim]
+    const double* fi; long long fi_s0;               // model coefficients [nmodels][fi_s0]
+    const signed char* order; int order_uniform;     // per-model order, or uniform
+    int diff;                                        // DOF slot to differentiate to, or -1: all slots
+    double* out; long long out_s0;                   // [nx] (diff >= 0) or [nx][out_s0]
+};
+
+cudaError_t launch_prepare(int dim, const PrepareParams& P, int blocks, int threads, size_t smem, cudaStream_t st);
+cudaError_t launch_solve(int dim, const SolveParams& P, int blocks, int threads, size_t smem, cudaStream_t st);
+cudaError_t launch_scatter_fi(const CaseMeta* meta, const CaseMeta& uni, long long ncases, const double* fi_case,
+                              int fi_case_ld, double* fi_out, long long fi_out_s0, cudaStream_t st);
+cudaError_t launch_interpolate(const InterpParams& P, cudaStream_t st);
+cudaError_t launch_getrf(int n, long long nlhs, double* A, int* ipiv, cudaStream_t st);
+cudaError_t launch_getrs(int n, long long nlhs, const double* LU, const int* ipiv, double* b, cudaStream_t st);
+cudaError_t launch_cond(int n_max, long long ncases, const CaseMeta* meta, const CaseMeta& uni, const double* As,
+                        int as_stride, double* cond, cudaStream_t st);
+
+}  // namespace wlsqm

@@ -1,0 +1,98 @@
+"""Batched general dense drivers on the GPU: ``mgeneral[p]``, ``mgeneralfactor[p]``, ``mgeneralfactored[p]``.
+
+Host-side mirror of the batched *general* family of ``wlsqm/utils/lapackdrivers.pyx:1551-1723`` (the
+pieces on the fitter's path; the symmetric / tridiagonal / scaling utilities of that module are a
+generic LAPACK convenience layer outside the hot path -- keep importing the reference for those).
+Layout is the reference's: ``A`` (n, n, nlhs) Fortran-contiguous, ``b`` (n, nlhs) Fortran,
+``ipiv`` (n, nlhs) int32 Fortran, 1-based pivots; everything is overwritten in place; LAPACK's ``info``
+is not reported (the reference drops it too: a singular system silently yields inf/NaN).
+The ``*p`` variants take ``ntasks`` for signature compatibility; on the GPU every variant is one launch.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from .. import _lib
+
+__all__ = ["mgeneral", "mgeneralp", "mgeneralfactor", "mgeneralfactorp", "mgeneralfactored", "mgeneralfactoredp"]
+
+
+def _f3(a, name, dtype, ndim):
+    a_ = _lib.as_arr(a, dtype, ndim, name, writable=True, last_contig=False) if not _lib._is_torch_tensor(a) else None
+    if a_ is None:
+        t = a
+        if not t.is_cuda:
+            raise ValueError(f"{name}: torch tensors must live on a CUDA device (pass numpy arrays for host data)")
+        st = tuple(int(s) for s in t.stride())
+        exp, acc = [], 1
+        for d in t.shape:
+            exp.append(acc)
+            acc *= int(d)
+        if tuple(exp) != st:
+            raise ValueError(f"{name}: tensor must be Fortran-contiguous")
+        return int(t.data_ptr()), tuple(t.shape), t.device.index
+    if not a_.np.flags.f_contiguous:
+        raise ValueError(f"{name}: ndarray is not Fortran contiguous")
+    return a_.ptr, a_.shape, None
+
+
+def _dev(*devs):
+    for d in devs:
+        if d is not None:
+            return d
+    return _lib.default_device()
+
+
+def mgeneralfactor(A, ipiv, device=None):
+    """LU-factor nlhs independent n x n systems in place (dgetrf each; ``lapackdrivers.pyx:1612-1635``)."""
+    pa, sa, da = _f3(A, "A", np.float64, 3)
+    pp, sp, dp = _f3(ipiv, "ipiv", np.int32, 2)
+    n, n2, nlhs = sa
+    if n != n2 or sp != (n, nlhs):
+        raise ValueError("shape mismatch: A (n,n,nlhs), ipiv (n,nlhs)")
+    _lib.check(_lib.lib().wlsqm_mgetrf(n, nlhs, pa, pp, int(_dev(device, da, dp))))
+
+
+def mgeneralfactored(LU, ipiv, b, device=None):
+    """Solve with factors from :func:`mgeneralfactor`; b is overwritten by x (dgetrs each;
+    ``lapackdrivers.pyx:1638-1665``)."""
+    pa, sa, da = _f3(LU, "LU", np.float64, 3)
+    pp, sp, dp = _f3(ipiv, "ipiv", np.int32, 2)
+    pb, sb, db = _f3(b, "b", np.float64, 2)
+    n, n2, nlhs = sa
+    if n != n2 or sp != (n, nlhs) or sb != (n, nlhs):
+        raise ValueError("shape mismatch: LU (n,n,nlhs), ipiv (n,nlhs), b (n,nlhs)")
+    _lib.check(_lib.lib().wlsqm_mgetrs(n, nlhs, pa, pp, pb, int(_dev(device, da, dp, db))))
+
+
+def mgeneral(A, b, device=None):
+    """Solve nlhs independent systems (dgesv each; ``lapackdrivers.pyx:1551-1578``): A is overwritten by
+    its LU factors, b by the solution."""
+    pa, sa, da = _f3(A, "A", np.float64, 3)
+    pb, sb, db = _f3(b, "b", np.float64, 2)
+    n, n2, nlhs = sa
+    if n != n2 or sb != (n, nlhs):
+        raise ValueError("shape mismatch: A (n,n,nlhs), b (n,nlhs)")
+    ipiv = np.empty((n, nlhs), dtype=np.int32, order='F')
+    if da is not None:
+        import torch
+        ipiv_t = torch.empty((nlhs, n), dtype=torch.int32, device=A.device).t()
+        pp = int(ipiv_t.data_ptr())
+    else:
+        pp = ipiv.ctypes.data
+    _lib.check(_lib.lib().wlsqm_mgesv(n, nlhs, pa, pp, pb, int(_dev(device, da, db))))
+
+
+def mgeneralp(A, b, ntasks=1, device=None):
+    """``lapackdrivers.pyx:1581-1609``"""
+    return mgeneral(A, b, device)
+
+
+def mgeneralfactorp(A, ipiv, ntasks=1, device=None):
+    """``lapackdrivers.pyx:1666-1692``"""
+    return mgeneralfactor(A, ipiv, device)
+
+
+def mgeneralfactoredp(LU, ipiv, b, ntasks=1, device=None):
+    """``lapackdrivers.pyx:1695-1723``"""
+    return mgeneralfactored(LU, ipiv, b, device)

@@ -1,0 +1,273 @@
+"""GPU parity tests: the CUDA path, through the C ABI (wlsqm_b200 -> libwlsqm_b200.so), vs the oracle.
+
+Tolerances: known-answer tests use the reference's own test tolerances (tests/test_simple.py:24
+ATOL_EXACT = 1e-10, tests/test_expert.py 1e-12/1e-14 equivalences are replaced by oracle comparisons);
+differential tests use the per-derivative-order noise-floor criterion of tests/parity.py
+(SURVEY.md 8c): <= 4x the oracle's own neighbour-permutation self-difference, p99 <= 1e-10 for d <= 1.
+"""
+import numpy as np
+import pytest
+
+import parity
+import oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+wlsqm = pytest.importorskip("wlsqm_b200")
+
+
+def _uniform_meta(n, k, order, knowns, wm):
+    return (np.full(n, k, np.int32), np.full(n, order, np.int32), np.full(n, knowns, np.int64),
+            np.full(n, wm, np.int32))
+
+
+def _run_gpu(dim, nk, od, kn, wm, x, xk, fk, fi0, algorithm=1, do_sens=False, max_iter=10, debug=False):
+    s = wlsqm.ExpertSolver(dim, nk, od, kn, wm, algorithm=algorithm, do_sens=do_sens, max_iter=max_iter,
+                           ntasks=1, debug=debug)
+    s.prepare(x, xk)
+    fi = fi0.copy()
+    sens = np.zeros((len(nk), xk.shape[1], fi.shape[1])) if do_sens else None
+    it = s.solve(fk, fi, sens)
+    return fi, sens, it, s
+
+
+CONFIGS = [
+    # dim, order, k, knowns, wm, algorithm, n, do_sens
+    pytest.param(2, 2, 12, 1, 2, 1, 4000, False, id="cfg1-2D-o2-k12-bF-center"),
+    pytest.param(2, 4, 30, 0, 1, 1, 4000, False, id="cfg2-2D-o4-k30-uniform"),
+    pytest.param(2, 4, 30, 0, 2, 1, 4000, False, id="cfg2-2D-o4-k30-center"),
+    pytest.param(2, 4, 30, 1, 1, 1, 4000, True, id="cfg2v-2D-o4-k30-bF-sens"),
+    pytest.param(2, 4, 30, 1, 1, 2, 3000, False, id="cfg2-2D-o4-k30-bF-iterative"),
+    pytest.param(3, 4, 60, 1, 2, 2, 800, True, id="cfg3-3D-o4-k60-bF-iter-sens"),
+    pytest.param(3, 4, 60, 0, 1, 1, 600, False, id="3D-o4-k60-nr35"),
+    pytest.param(3, 2, 20, 1, 2, 1, 2000, False, id="3D-o2-k20"),
+    pytest.param(3, 3, 40, 0, 1, 1, 1000, False, id="3D-o3-k40"),
+    pytest.param(1, 3, 8, 1, 1, 1, 4000, False, id="cfg4-1D-o3-k8"),
+    pytest.param(2, 3, 24, 1, 1, 1, 4000, False, id="cfg4-2D-o3-k24"),
+    pytest.param(1, 4, 9, 0, 2, 2, 2000, True, id="1D-o4-k9-iter-sens"),
+    pytest.param(2, 1, 6, 0, 2, 1, 2000, False, id="2D-o1-k6"),
+    pytest.param(2, 0, 5, 0, 1, 1, 1000, False, id="2D-o0-k5"),
+]
+
+
+@pytest.mark.parametrize("dim,order,k,knowns,wm,algo,n,do_sens", CONFIGS)
+def test_differential_vs_oracle(dim, order, k, knowns, wm, algo, n, do_sens):
+    x, hoods, f = parity.make_case(n, dim, k)
+    xk, fk = parity.gathered(x, f, hoods)
+    no = wlsqm.number_of_dofs(dim, order)
+    nk, od, kn, w = _uniform_meta(n, k, order, knowns, wm)
+    fi0 = np.zeros((n, no))
+    fi0[:, 0] = f
+    max_iter = 3
+    fi_g, sens_g, it_g, s = _run_gpu(dim, nk, od, kn, w, x, xk, fk, fi0, algo, do_sens, max_iter)
+    fi_o, sens_o, it_o, _ = parity.oracle_solve(dim, nk, od, kn, w, x, xk, fk, fi0, algo, do_sens, max_iter)
+    a, b = parity.permuted_self_noise(dim, nk, od, kn, w, x, xk, fk, fi0, algo, max_iter)
+    print(parity.check_against_floor(fi_g, fi_o, b + (fi_o - a), dim, order, "gpu-vs-oracle"))
+    assert it_g == it_o
+    # knowns are left untouched, bit for bit
+    for o in range(no):
+        if knowns >> o & 1:
+            assert np.array_equal(fi_g[:, o], fi0[:, o])
+    if do_sens:
+        assert np.array_equal(np.isnan(sens_g), np.isnan(sens_o))
+        sc = np.nanmax(np.abs(np.where(np.isnan(sens_o), 0.0, sens_o)), axis=(0, 1))
+        sc[sc == 0] = 1.0
+        err = np.abs(np.nan_to_num(sens_g) - np.nan_to_num(sens_o)) / sc
+        # sens entries are solves of the same scaled LU: cond * eps relative to the largest entry of the column
+        assert err.max() < 1e-8, err.max()
+        assert np.median(err) < 1e-12
+
+
+def test_heterogeneous_batch():
+    """per-case nk / order / knowns / weighting in one batch (expert.pyx:92-104)"""
+    n, dim, kmax = 3000, 2, 30
+    x, hoods, f = parity.make_case(n, dim, kmax)
+    rng = np.random.default_rng(3)
+    od = rng.integers(0, 5, n).astype(np.int32)
+    nk = np.array([rng.integers(wlsqm.number_of_dofs(2, int(o)) + 2, kmax + 1) for o in od], np.int32)
+    kn = np.where(rng.random(n) < 0.5, 1, 0).astype(np.int64)
+    kn[od >= 2] |= np.where(rng.random((od >= 2).sum()) < 0.3, wlsqm.b2_XY, 0)
+    wm = rng.integers(1, 3, n).astype(np.int32)
+    xk, fk = parity.gathered(x, f, hoods)
+    fi0 = rng.standard_normal((n, 15))
+    fi0[:, 0] = f
+    fi_g, sens_g, _, _ = _run_gpu(dim, nk, od, kn, wm, x, xk, fk, fi0, 1, True)
+    fi_o, sens_o, _, _ = parity.oracle_solve(dim, nk, od, kn, wm, x, xk, fk, fi0, 1, True)
+    # untouched: columns >= no_j, and known slots
+    for j in range(n):
+        no = wlsqm.number_of_dofs(2, int(od[j]))
+        assert np.array_equal(fi_g[j, no:], fi0[j, no:])
+        for o in range(no):
+            if kn[j] >> o & 1:
+                assert fi_g[j, o] == fi0[j, o]
+    for order in range(5):
+        m = od == order
+        no = wlsqm.number_of_dofs(2, order)
+        sc = np.abs(fi_o[m][:, :no]).max(axis=0)
+        sc[sc == 0] = 1
+        e = np.abs(fi_g[m][:, :no] - fi_o[m][:, :no]) / sc
+        assert np.median(e) < 1e-9 and np.quantile(e, 0.99) < 1e-6, (order, np.median(e), e.max())
+    assert np.array_equal(np.isnan(sens_g), np.isnan(sens_o))
+    # sens rows k >= nk_j and columns o >= no_j stay untouched (zeros here)
+    for j in range(0, n, 97):
+        assert (sens_g[j, nk[j]:, :] == 0).all()
+
+
+def test_fk_alias_of_fi_on_device():
+    """fk given as a view into fi (expert.pyx:548-557): every case must see the old data"""
+    torch = pytest.importorskip("torch")
+    n, k = 2000, 12
+    x, hoods, f = parity.make_case(n, 2, k)
+    nk, od, kn, w = _uniform_meta(n, k, 2, 0, 2)
+    xk, fk = parity.gathered(x, f, hoods)
+    fi_o = np.zeros((n, 6))
+    parity_fi, _, _, _ = parity.oracle_solve(2, nk, od, kn, w, x, xk, fk, fi_o)
+    # device buffer holding [fk | fi] side by side so that fk is a strided view of the same allocation
+    buf = torch.zeros((n, k + 6), dtype=torch.float64, device="cuda")
+    buf[:, :k] = torch.from_numpy(fk).cuda()
+    s = wlsqm.ExpertSolver(2, nk, od, kn, w)
+    s.prepare(torch.from_numpy(x).cuda(), torch.from_numpy(xk).cuda())
+    s.solve(buf[:, :k], buf[:, k:])
+    torch.cuda.synchronize()
+    got = buf[:, k:].cpu().numpy()
+    sc = np.abs(parity_fi).max(axis=0)
+    assert (np.abs(got - parity_fi) / sc).max() < 1e-9
+
+
+def test_torch_tensors_zero_copy_matches_numpy_path():
+    torch = pytest.importorskip("torch")
+    n, k = 3000, 30
+    x, hoods, f = parity.make_case(n, 2, k)
+    nk, od, kn, w = _uniform_meta(n, k, 4, 1, 1)
+    xk, fk = parity.gathered(x, f, hoods)
+    fi0 = np.zeros((n, 15))
+    fi0[:, 0] = f
+    fi_np, _, _, _ = _run_gpu(2, nk, od, kn, w, x, xk, fk, fi0)
+    s = wlsqm.ExpertSolver(2, nk, od, kn, w)
+    s.prepare(torch.from_numpy(x).cuda(), torch.from_numpy(xk).cuda())
+    fi_t = torch.from_numpy(fi0).cuda()
+    s.solve(torch.from_numpy(fk).cuda(), fi_t)
+    torch.cuda.synchronize()
+    assert np.array_equal(fi_t.cpu().numpy(), fi_np)
+
+
+def test_conds_match_svd_of_oracle_scaled_matrix():
+    n, k = 500, 30
+    x, hoods, f = parity.make_case(n, 2, k)
+    nk, od, kn, w = _uniform_meta(n, k, 4, 0, 1)
+    xk, fk = parity.gathered(x, f, hoods)
+    fi0 = np.zeros((n, 15))
+    _, _, _, s = _run_gpu(2, nk, od, kn, w, x, xk, fk, fi0, debug=True)
+    _, _, _, so = parity.oracle_solve(2, nk, od, kn, w, x, xk, fk, fi0)
+    cg, co = s.conds(), so.conds()
+    assert np.allclose(cg, co, rtol=1e-6), np.abs(cg / co - 1).max()
+
+
+def test_interpolate_nearest_all_diffs_vs_oracle():
+    n, k, dim, order = 3000, 30, 2, 4
+    x, hoods, f = parity.make_case(n, dim, k)
+    nk, od, kn, w = _uniform_meta(n, k, order, 0, 2)
+    xk, fk = parity.gathered(x, f, hoods)
+    fi0 = np.zeros((n, 15))
+    fi_g, _, _, s = _run_gpu(dim, nk, od, kn, w, x, xk, fk, fi0)
+    rng = np.random.default_rng(5)
+    xq = np.repeat(x, 4, axis=0) + 0.3e-2 * rng.uniform(-1, 1, (4 * n, 2))
+    s.prep_interpolate()
+    out0, I = s.interpolate(xq, mode='nearest', diff=0)
+    from scipy.spatial import cKDTree
+    assert np.array_equal(I, cKDTree(x).query(xq)[1])
+    assert I.dtype == np.int_
+    so = orc.OracleSolver(dim, nk, od, kn, w)
+    so.xi = x
+    so.fi = fi_g.copy()      # same coefficients: isolates the evaluator
+    allg, _ = s.interpolate(xq, diff='all', I=I)
+    for d in range(15):
+        og, I2 = s.interpolate(xq, mode='nearest', diff=d, I=I)
+        oo = so.interpolate(xq, I, d)
+        scale = max(np.abs(oo).max(), 1e-300)
+        assert np.abs(og - oo).max() / scale < 1e-12, (d, np.abs(og - oo).max() / scale)
+        assert np.array_equal(allg[:, d], og)
+    # NaN query: everything NaN (expert.pyx:862-870)
+    xq2 = xq[:10].copy()
+    xq2[3, 0] = np.nan
+    o, _ = s.interpolate(xq2, diff=0)
+    assert np.isnan(o).all()
+
+
+def test_interpolate_continuous_vs_reference_formula():
+    n, k = 1500, 20
+    x, hoods, f = parity.make_case(n, 2, k)
+    nk, od, kn, w = _uniform_meta(n, k, 3, 0, 2)
+    xk, fk = parity.gathered(x, f, hoods)
+    fi_g, _, _, s = _run_gpu(2, nk, od, kn, w, x, xk, fk, np.zeros((n, 10)))
+    s.prep_interpolate()
+    rng = np.random.default_rng(11)
+    xq = x[:200] + 1e-3 * rng.uniform(-1, 1, (200, 2))
+    r = 0.03
+    out, Iout = s.interpolate(xq, mode='continuous', r=r, diff=wlsqm.i2_X)
+    from scipy.spatial import cKDTree
+    L = cKDTree(xq).query_ball_tree(cKDTree(x), r=r)
+    exp = np.empty(200)
+    for m in range(200):
+        acc = sw = 0.0
+        for li in L[m]:
+            v = orc.interpolate_fit(x[li], fi_g[li], 2, 3, xq[m:m + 1], wlsqm.i2_X)[0]
+            d2 = ((xq[m] - x[li]) ** 2).sum()
+            ww = (1 - np.sqrt(d2 / r ** 2)) ** 2
+            acc += ww * v
+            sw += ww
+        exp[m] = acc / sw
+    assert np.allclose(out, exp, rtol=1e-10, atol=1e-12)
+
+
+def test_simple_api_many_equals_expert_and_single():
+    """fit_2D_many_parallel == ExpertSolver == loop of fit_2D (tests/test_simple.py:132-168, test_parallel.py:35-66)"""
+    n, k = 64, 12
+    x, hoods, f = parity.make_case(n, 2, k, unit_box=True)
+    nk, od, kn, w = _uniform_meta(n, k, 2, wlsqm.b2_F, wlsqm.WEIGHT_CENTER)
+    xk, fk = parity.gathered(x, f, hoods)
+    fi0 = np.zeros((n, 6))
+    fi0[:, 0] = f
+    fi_many = fi0.copy()
+    sens = np.zeros((n, k, 6))
+    assert wlsqm.fit_2D_many_parallel(xk, fk, nk, x, fi_many, sens, 1, od, kn, w, ntasks=4) == 0
+    fi_e, sens_e, _, _ = _run_gpu(2, nk, od, kn, w, x, xk, fk, fi0, do_sens=True)
+    assert np.array_equal(fi_many, fi_e)
+    assert np.array_equal(np.nan_to_num(sens), np.nan_to_num(sens_e))
+    for j in range(0, n, 9):
+        fi1 = fi0[j].copy()
+        s1 = np.zeros((k, 6))
+        wlsqm.fit_2D(xk[j], fk[j], x[j], fi1, s1, do_sens=1, order=2, knowns=wlsqm.b2_F,
+                     weighting_method=wlsqm.WEIGHT_CENTER)
+        assert np.array_equal(fi1, fi_many[j])
+    fi_it = fi0.copy()
+    it = wlsqm.fit_2D_iterative_many_parallel(xk, fk, nk, x, fi_it, None, 0, od, kn, w, max_iter=5)
+    fi_o, _, it_o, _ = parity.oracle_solve(2, nk, od, kn, w, x, xk, fk, fi0, 2, False, 5)
+    assert it == it_o
+    assert np.abs(fi_it - fi_o).max() < 1e-9
+
+
+def test_mgeneral_drivers_vs_numpy():
+    from wlsqm_b200.utils import lapackdrivers as ld
+    rng = np.random.default_rng(0)
+    for n in (1, 3, 15, 36, 70):
+        nlhs = 300
+        A = np.asfortranarray(rng.standard_normal((n, n, nlhs)))
+        b = np.asfortranarray(rng.standard_normal((n, nlhs)))
+        x_ref = np.stack([np.linalg.solve(A[:, :, l], b[:, l]) for l in range(nlhs)], axis=1)
+        LU = A.copy(order='F')
+        ipiv = np.zeros((n, nlhs), dtype=np.int32, order='F')
+        ld.mgeneralfactor(LU, ipiv)
+        assert ipiv.min() >= 1 and ipiv.max() <= n
+        # the factorisation matches the oracle's dgetf2 restatement pivot for pivot
+        LUo = A.copy(order='F')
+        ipo = np.zeros_like(ipiv)
+        orc.mgetrf(LUo, ipo)
+        assert np.array_equal(ipiv, ipo)
+        assert np.allclose(LU, LUo, rtol=1e-9, atol=1e-11)
+        x = b.copy(order='F')
+        ld.mgeneralfactoredp(LU, ipiv, x, 4)
+        assert np.allclose(x, x_ref, rtol=1e-8, atol=1e-9)
+        A2, b2 = A.copy(order='F'), b.copy(order='F')
+        ld.mgeneralp(A2, b2, 8)
+        assert np.array_equal(b2, x)

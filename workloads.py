@@ -22,7 +22,7 @@ def cloud(n: int, dim: int, seed: int = 42, unit_box: bool = False) -> np.ndarra
 def hoods_knn(x: np.ndarray, k: int) -> np.ndarray:
     from scipy.spatial import cKDTree
     x2 = x.reshape(len(x), -1)
-    return cKDTree(x2).query(x2, k + 1)[1][:, 1:].astype(np.int32)
+    return cKDTree(x2).query(x2, k + 1, workers=-1)[1][:, 1:].astype(np.int32)
 
 
 def field(x: np.ndarray) -> np.ndarray:
