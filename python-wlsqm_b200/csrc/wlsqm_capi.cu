@@ -167,20 +167,22 @@ int config_prepare(const wlsqm_solver* s, PrepareParams& P, LaunchCfg& L) {
 
 int config_solve(const wlsqm_solver* s, SolveParams& P, LaunchCfg& L) {
     const bool iter = s->algorithm == WLSQM_ALGO_ITERATIVE;
-    const int stage_doubles = std::max(2, even(s->maxnq * s->maxnr));
+    // one stage of the per-warp ring: [operator block | fext = fk + known fi | xk (ALGO_ITERATIVE)]
+    const int op_doubles = std::max(2, even(s->maxnq * s->maxnr));
+    const int f_doubles = std::max(2, even(s->maxnq));
+    const int x_doubles = iter ? std::max(2, even(s->maxnk * s->dim)) : 0;
+    const int stage_doubles = op_doubles + f_doubles + x_doubles;
     const size_t stage_bytes = (size_t)stage_doubles * 8;
     int S = env_int("WLSQM_SOLVE_STAGES", stage_bytes <= 8192 ? 3 : 2);
     S = std::max(1, std::min(S, 8));
     int warps = env_int("WLSQM_SOLVE_WARPS", 8);
     warps = std::max(1, std::min(warps, SOLVE_MAX_THREADS / 32));
     size_t per_warp = 0;
-    int off_f, off_fi, off_r, off_xk, wd;
+    int off_fi, off_r, wd;
     for (;;) {
-        off_f = S * stage_doubles;
-        off_fi = off_f + std::max(2, even(s->maxnq));
+        off_fi = S * stage_doubles;
         off_r = off_fi + 36;
-        off_xk = off_r + (iter ? std::max(2, even(s->maxnk)) : 0);
-        wd = off_xk + (iter ? std::max(2, even(s->maxnk * s->dim)) : 0);
+        wd = off_r + (iter ? std::max(2, even(s->maxnk)) : 0);
         wd = (wd + 15) & ~15;                      // 128 B granularity per warp slice
         per_warp = (size_t)wd * 8 + (size_t)S * 8;
         if (warps * per_warp <= SMEM_PER_CTA) break;
@@ -192,8 +194,13 @@ int config_solve(const wlsqm_solver* s, SolveParams& P, LaunchCfg& L) {
     }
     P.stages = S;
     P.stage_doubles = stage_doubles;
-    P.off_f = off_f; P.off_fi = off_fi; P.off_r = off_r; P.off_xk = off_xk;
+    P.off_f = op_doubles; P.off_xk = op_doubles + f_doubles;
+    P.off_fi = off_fi; P.off_r = off_r;
     P.warp_doubles = wd;
+    // bulk-copy eligibility of the data arrays (16 B alignment of every row start, unit stride)
+    P.f_tma = (P.fk_s1 == 1 && ((uintptr_t)P.fk % 16 == 0) && (P.fk_s0 % 2 == 0)) ? 1 : 0;
+    P.xk_tma = (iter && P.xk_s1 == s->dim && ((uintptr_t)P.xk % 16 == 0) && (P.xk_s0 % 2 == 0)) ? 1 : 0;
+    if (env_int("WLSQM_SOLVE_NO_FTMA", 0)) P.f_tma = P.xk_tma = 0;
     P.bar_off_bytes = warps * wd * 8;
     L.threads = warps * 32;
     L.smem = (size_t)P.bar_off_bytes + (size_t)warps * S * 8;

@@ -37,9 +37,11 @@ struct SolveParams {
     const double* xk; long long xk_s0, xk_s1;
     int* iters_max;                                  // max refinement iterations over all cases
     int* iters_case;                                 // optional per-case iteration counts
-    int stages, stage_doubles;                       // TMA ring per warp
-    int warp_doubles, off_f, off_fi, off_r, off_xk;  // per-warp smem carve-up (doubles)
+    int stages, stage_doubles;                       // TMA ring per warp; a stage is [operator | fext | xk]
+    int off_f, off_xk;                               // offsets of fext / xk inside a stage (doubles)
+    int warp_doubles, off_fi, off_r;                 // per-warp smem carve-up (doubles)
     int bar_off_bytes;                               // start of the mbarrier array
+    int f_tma, xk_tma;                               // fk / xk rows qualify for bulk copies (alignment, unit stride)
 };
 
 struct InterpParams {

@@ -23,6 +23,59 @@
 
 namespace wlsqm {
 
+// out[j] = sum_q op[q*nr + j] * v[q], q < n, for one warp.  The 32 lanes form G = 32/W groups of W lanes
+// (W = smallest power of two >= nr); group g takes the rows q = g, g+G, ... so that one shared-memory
+// wavefront reads G consecutive operator rows; a xor-butterfly over the groups leaves the total for
+// reduced DOF j in every lane with (lane & (W-1)) == j.  nr > 32 (3D order 4 with < 3 knowns): lanes
+// also own row j + 32, returned in `hi`.
+__device__ __forceinline__ void warp_matvec(const double* __restrict__ op, const double* __restrict__ v, int n, int nr,
+                                            int lane, double& lo, double& hi) {
+    const int W = nr <= 1 ? 1 : nr <= 2 ? 2 : nr <= 4 ? 4 : nr <= 8 ? 8 : nr <= 16 ? 16 : 32;
+    const int G = 32 / W;
+    const int g = lane / W, j = lane & (W - 1);
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    hi = 0.0;
+    if (j < nr) {
+        const double* p = op + g * nr + j;
+        const double* vq = v + g;
+        const int sp = G * nr;
+        int q = g;
+        for (; q + 3 * G < n; q += 4 * G) {
+            a0 = fma(p[0], vq[0], a0);
+            a1 = fma(p[sp], vq[G], a1);
+            a2 = fma(p[2 * sp], vq[2 * G], a2);
+            a3 = fma(p[3 * sp], vq[3 * G], a3);
+            p += 4 * sp;
+            vq += 4 * G;
+        }
+        for (; q < n; q += G) {
+            a0 = fma(p[0], vq[0], a0);
+            p += sp;
+            vq += G;
+        }
+        if (j + 32 < nr) {   // only when W == 32, G == 1
+            const double* p2 = op + j + 32;
+            double b0 = 0.0, b1 = 0.0;
+            int q2 = 0;
+            for (; q2 + 1 < n; q2 += 2) {
+                b0 = fma(p2[q2 * nr], v[q2], b0);
+                b1 = fma(p2[(q2 + 1) * nr], v[q2 + 1], b1);
+            }
+            if (q2 < n) b0 = fma(p2[q2 * nr], v[q2], b0);
+            hi = b0 + b1;
+        }
+    }
+    lo = (a0 + a1) + (a2 + a3);
+    for (int off = W; off < 32; off <<= 1) lo += __shfl_xor_sync(0xffffffffu, lo, off);
+}
+
+// value of reduced DOF j for original slot o held by this lane (every lane must call it)
+__device__ __forceinline__ double fetch_reduced(double lo, double hi, int j) {
+    const double vlo = __shfl_sync(0xffffffffu, lo, j & 31);
+    const double vhi = __shfl_sync(0xffffffffu, hi, j & 31);
+    return j < 32 ? vlo : vhi;
+}
+
 template <int DIM, bool ITER, bool SENS>
 __global__ void __launch_bounds__(SOLVE_MAX_THREADS) solve_kernel(SolveParams P) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -31,11 +84,9 @@ __global__ void __launch_bounds__(SOLVE_MAX_THREADS) solve_kernel(SolveParams P)
     const int nwarps = blockDim.x >> 5;
     const int S = P.stages;
     double* wb = reinterpret_cast<double*>(smem_raw) + (size_t)warp * P.warp_doubles;
-    double* ring = wb;                      // S * stage_doubles
-    double* fext = wb + P.off_f;            // nk + nkn data values
+    double* ring = wb;                      // S stages of [operator block | fext = (fk, known fi) | xk (ITER)]
     double* fis = wb + P.off_fi;            // current solution of the case (no values)
     double* rs = wb + P.off_r;              // ITER: residual at the neighbours
-    double* xks = wb + P.off_xk;            // ITER: neighbour coordinates
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + P.bar_off_bytes) + warp * S;
 
     const long long gw = (long long)blockIdx.x * nwarps + warp;
@@ -52,11 +103,26 @@ __global__ void __launch_bounds__(SOLVE_MAX_THREADS) solve_kernel(SolveParams P)
         }
         return m;
     };
-    auto issue = [&](int s, long long c) {   // lane 0 only
+    // bulk copies need 16 B alignment and sizes: the host says whether the arrays qualify (f_tma, xk_tma),
+    // the per-case element count has to be even on top of that; otherwise the lanes gather with plain loads
+    auto f_by_tma = [&](const CaseMeta& m) { return P.f_tma && !(m.nk & 1); };
+    auto xk_by_tma = [&](const CaseMeta& m) { return ITER && P.xk_tma && !((m.nk * DIM) & 1); };
+    auto issue = [&](int s, long long c) {   // lane 0 only: arm the stage's barrier and start its copies
         const CaseMeta m = get_meta(c);
-        const uint32_t bytes = ((uint32_t)((m.nk + m.nkn) * (int)m.nr) * 8u + 15u) & ~15u;
-        mbar_expect_tx(&bars[s], bytes);
-        if (bytes) tma_load_1d(ring + (size_t)s * P.stage_doubles, P.op + m.op_off, bytes, &bars[s]);
+        double* st = ring + (size_t)s * P.stage_doubles;
+        const uint32_t b_op = ((uint32_t)((m.nk + m.nkn) * (int)m.nr) * 8u + 15u) & ~15u;
+        const uint32_t b_f = f_by_tma(m) ? (uint32_t)m.nk * 8u : 0u;
+        const uint32_t b_x = xk_by_tma(m) ? (uint32_t)(m.nk * DIM) * 8u : 0u;
+        mbar_expect_tx(&bars[s], b_op + b_f + b_x);
+        if (b_op) tma_load_1d(st, P.op + m.op_off, b_op, &bars[s]);
+        if (b_f) tma_load_1d(st + P.off_f, P.fk + c * P.fk_s0, b_f, &bars[s]);
+        if (b_x) tma_load_1d(st + P.off_xk, P.xk + c * P.xk_s0, b_x, &bars[s]);
+    };
+    // known fi values of a case, one register per lane and 32-slot group (prefetched one case ahead)
+    auto load_g = [&](long long c, const CaseMeta& m, double& g0, double& g1) {
+        g0 = g1 = 0.0;
+        if (lane < m.no && ((m.knowns >> lane) & 1LL)) g0 = P.fi_in[c * P.fi_in_s0 + lane];
+        if (lane + 32 < m.no && ((m.knowns >> (lane + 32)) & 1LL)) g1 = P.fi_in[c * P.fi_in_s0 + lane + 32];
     };
 
     if (lane == 0) {
@@ -68,6 +134,12 @@ __global__ void __launch_bounds__(SOLVE_MAX_THREADS) solve_kernel(SolveParams P)
 
     int stage = 0, itmax = 0;
     uint32_t phase = 0;
+    double g0 = 0.0, g1 = 0.0;
+    CaseMeta mt{};
+    if (n_my > 0) {
+        mt = get_meta(gw);
+        load_g(gw, mt, g0, g1);
+    }
     for (long long i = 0; i < n_my; ++i) {
         const long long c = gw + i * GW;
         if (lane == 0 && i + S - 1 < n_my) {
@@ -75,54 +147,63 @@ __global__ void __launch_bounds__(SOLVE_MAX_THREADS) solve_kernel(SolveParams P)
             if (sn >= S) sn -= S;
             issue(sn, gw + (i + S - 1) * GW);
         }
-        const CaseMeta mt = get_meta(c);
         const int nk = mt.nk, no = mt.no, nr = mt.nr, nkn = mt.nkn, nq = nk + nkn;
         const long long knowns = mt.knowns;
+        double* st = ring + (size_t)stage * P.stage_doubles;
+        const double* op = st;
+        double* fext = st + P.off_f;
+        const double* xks = st + P.off_xk;
 
-        // ---- gather the data of this case while its operator block is in flight ---------------
-        {
+        // ---- data that did not come by TMA, and the known values ---------------------------------
+        if (!f_by_tma(mt)) {
             const double* f = P.fk + c * P.fk_s0;
             for (int k = lane; k < nk; k += 32) fext[k] = ld_stream(f + (long long)k * P.fk_s1);
         }
-        for (int o = lane; o < no; o += 32) {
-            if ((knowns >> o) & 1LL) {
-                const double g = P.fi_in[c * P.fi_in_s0 + o];
-                fext[nk + __popcll(knowns & ((1LL << o) - 1))] = g;
-                fis[o] = g;
-            }
-        }
-        if (ITER) {
+        if (ITER && !xk_by_tma(mt)) {
             const double* xp = P.xk + c * P.xk_s0;
-            if (P.xk_s1 == DIM) {
-                for (int t = lane; t < nk * DIM; t += 32) xks[t] = xp[t];
-            } else {
-                for (int t = lane; t < nk * DIM; t += 32) xks[t] = xp[(long long)(t / DIM) * P.xk_s1 + (t % DIM)];
-            }
+            double* xw = st + P.off_xk;
+            for (int t = lane; t < nk * DIM; t += 32) xw[t] = xp[(long long)(t / DIM) * P.xk_s1 + (t % DIM)];
+        }
+        if (nkn) {
+            if (lane < no && ((knowns >> lane) & 1LL)) fext[nk + __popcll(knowns & ((1LL << lane) - 1))] = g0;
+            if (lane + 32 < no && ((knowns >> (lane + 32)) & 1LL))
+                fext[nk + __popcll(knowns & ((1LL << (lane + 32)) - 1))] = g1;
+        }
+        // prefetch the next case's record and known values while this one is being worked on
+        CaseMeta mt_next = mt;
+        double gn0 = 0.0, gn1 = 0.0;
+        if (i + 1 < n_my) {
+            mt_next = get_meta(c + GW);
+            if (mt_next.nkn) load_g(c + GW, mt_next, gn0, gn1);
         }
         __syncwarp();
         mbar_wait(&bars[stage], phase);
-        const double* op = ring + (size_t)stage * P.stage_doubles;
 
-        // ---- fi[unknown] = Op^T fext (lane = DOF slot) ------------------------------------------
-        for (int o = lane; o < no; o += 32) {
-            if (!((knowns >> o) & 1LL)) {
-                const int j = o - __popcll(knowns & ((1LL << o) - 1));
-                const double* col = op + j;
-                double a0 = 0.0, a1 = 0.0;
-                int q = 0;
-                for (; q + 1 < nq; q += 2) {
-                    const double2 f2 = *reinterpret_cast<const double2*>(fext + q);
-                    a0 = fma(col[q * nr], f2.x, a0);
-                    a1 = fma(col[(q + 1) * nr], f2.y, a1);
-                }
-                if (q < nq) a0 = fma(col[q * nr], fext[q], a0);
-                fis[o] = a0 + a1;
+        // ---- fi[unknown] = Op^T fext ----------------------------------------------------------------
+        // reduced index of the slots this lane writes back: o = lane and o = lane + 32
+        const bool unk0 = lane < no && !((knowns >> lane) & 1LL);
+        const bool unk1 = lane + 32 < no && !((knowns >> (lane + 32)) & 1LL);
+        const int j0 = unk0 ? lane - __popcll(knowns & ((1LL << lane) - 1)) : 0;
+        const int j1 = unk1 ? lane + 32 - __popcll(knowns & ((1LL << (lane + 32)) - 1)) : 0;
+        double v0 = g0, v1 = g1;     // known slots keep the caller's value
+        if (nr > 0) {
+            double lo, hi;
+            warp_matvec(op, fext, nq, nr, lane, lo, hi);
+            const double t0 = fetch_reduced(lo, hi, j0);
+            if (unk0) v0 = t0;
+            if (no > 32) {
+                const double t1 = fetch_reduced(lo, hi, j1);
+                if (unk1) v1 = t1;
             }
         }
-        __syncwarp();
+        if (ITER) {
+            if (lane < no) fis[lane] = v0;
+            if (lane + 32 < no) fis[lane + 32] = v1;
+            __syncwarp();
+        }
 
         // ---- sensitivities: the operator itself, re-indexed by DOF slot (impl.pyx:838-846) ------
-        if (SENS) {
+        if (SENS && nr > 0) {   // nr == 0: silent no-op, sens untouched (impl.pyx:742)
             double* sn = P.sens + c * P.sens_s0;
             const double qnan = __longlong_as_double(0x7ff8000000000000LL);
             for (int t = lane; t < nk * no; t += 32) {
@@ -156,18 +237,13 @@ __global__ void __launch_bounds__(SOLVE_MAX_THREADS) solve_kernel(SolveParams P)
                 prev = nrm;
                 __syncwarp();
                 if (nr > 0) {
-                    for (int o = lane; o < no; o += 32) {
-                        if (!((knowns >> o) & 1LL)) {
-                            const double* col = op + (o - __popcll(knowns & ((1LL << o) - 1)));
-                            double a0 = 0.0, a1 = 0.0;
-                            int q = 0;
-                            for (; q + 1 < nk; q += 2) {
-                                a0 = fma(col[q * nr], rs[q], a0);
-                                a1 = fma(col[(q + 1) * nr], rs[q + 1], a1);
-                            }
-                            if (q < nk) a0 = fma(col[q * nr], rs[q], a0);
-                            fis[o] += a0 + a1;
-                        }
+                    double lo, hi;
+                    warp_matvec(op, rs, nk, nr, lane, lo, hi);
+                    const double t0 = fetch_reduced(lo, hi, j0);
+                    if (unk0) { v0 += t0; fis[lane] = v0; }
+                    if (no > 32) {
+                        const double t1 = fetch_reduced(lo, hi, j1);
+                        if (unk1) { v1 += t1; fis[lane + 32] = v1; }
                     }
                 }
                 __syncwarp();
@@ -180,13 +256,17 @@ __global__ void __launch_bounds__(SOLVE_MAX_THREADS) solve_kernel(SolveParams P)
         }
 
         // ---- write-back: solver-owned copy (all `no` entries) and, if allowed, the caller's fi ---
-        for (int o = lane; o < no; o += 32) {
-            const double v = fis[o];
-            P.fi_case[c * P.fi_case_ld + o] = v;
-            if (P.fi_out && !((knowns >> o) & 1LL)) P.fi_out[c * P.fi_out_s0 + o] = v;
+        if (lane < no) {
+            P.fi_case[c * P.fi_case_ld + lane] = v0;
+            if (P.fi_out && unk0) P.fi_out[c * P.fi_out_s0 + lane] = v0;
+        }
+        if (lane + 32 < no) {
+            P.fi_case[c * P.fi_case_ld + lane + 32] = v1;
+            if (P.fi_out && unk1) P.fi_out[c * P.fi_out_s0 + lane + 32] = v1;
         }
         __syncwarp();   // every lane is done with this stage before lane 0 re-arms it
         if (++stage == S) { stage = 0; phase ^= 1u; }
+        mt = mt_next; g0 = gn0; g1 = gn1;
     }
     if (ITER && lane == 0 && itmax > 0) atomicMax(P.iters_max, itmax);
 }

@@ -18,22 +18,34 @@ __all__ = ["mgeneral", "mgeneralp", "mgeneralfactor", "mgeneralfactorp", "mgener
 
 
 def _f3(a, name, dtype, ndim):
-    a_ = _lib.as_arr(a, dtype, ndim, name, writable=True, last_contig=False) if not _lib._is_torch_tensor(a) else None
-    if a_ is None:
+    """Fortran-contiguous array argument (``double[::1,:,:]`` etc.) -> (pointer, shape, cuda device or None)"""
+    dtype = np.dtype(dtype)
+    if _lib._is_torch_tensor(a):
         t = a
         if not t.is_cuda:
             raise ValueError(f"{name}: torch tensors must live on a CUDA device (pass numpy arrays for host data)")
-        st = tuple(int(s) for s in t.stride())
+        if t.dim() != ndim:
+            raise ValueError(f"{name}: Buffer has wrong number of dimensions (expected {ndim}, got {t.dim()})")
+        if str(t.dtype).replace("torch.", "") != dtype.name:
+            raise ValueError(f"{name}: Buffer dtype mismatch, expected '{dtype.name}' but got '{t.dtype}'")
         exp, acc = [], 1
         for d in t.shape:
             exp.append(acc)
             acc *= int(d)
-        if tuple(exp) != st:
+        if tuple(exp) != tuple(int(s) for s in t.stride()) and t.numel() > 1:
             raise ValueError(f"{name}: tensor must be Fortran-contiguous")
-        return int(t.data_ptr()), tuple(t.shape), t.device.index
-    if not a_.np.flags.f_contiguous:
+        return int(t.data_ptr()), tuple(int(d) for d in t.shape), t.device.index
+    if not isinstance(a, np.ndarray):
+        raise TypeError(f"{name}: expected a numpy array or a CUDA torch.Tensor")
+    if a.dtype != dtype:
+        raise ValueError(f"{name}: Buffer dtype mismatch, expected '{dtype.name}' but got '{a.dtype.name}'")
+    if a.ndim != ndim:
+        raise ValueError(f"{name}: Buffer has wrong number of dimensions (expected {ndim}, got {a.ndim})")
+    if not a.flags.f_contiguous:
         raise ValueError(f"{name}: ndarray is not Fortran contiguous")
-    return a_.ptr, a_.shape, None
+    if not a.flags.writeable:
+        raise ValueError(f"{name}: buffer source array is read-only")
+    return a.ctypes.data, a.shape, None
 
 
 def _dev(*devs):

@@ -68,3 +68,46 @@ def check_against_floor(got, ref, ref_perm, dim, order, label=""):
     report = "\n".join(lines)
     assert ok, "parity outside the reference's own noise floor:\n" + report
     return report
+
+
+# ---- golden vectors (tests/golden/, generated from the unmodified reference by make_golden.py) ----------
+from pathlib import Path as _Path
+
+GOLDEN_DIR = _Path(__file__).resolve().parent / "golden"
+_golden = None
+
+
+def golden():
+    global _golden
+    if _golden is None:
+        _golden = np.load(GOLDEN_DIR / "golden_cases.npz")
+    return _golden
+
+
+def golden_names():
+    return [str(s) for s in golden()["names"]]
+
+
+def golden_case(name):
+    g = golden()
+    c = {k.split("/", 1)[1]: g[k] for k in g.files if k.startswith(name + "/")}
+    dim, order, k, knowns, wm, algo, max_iter, n = (int(v) for v in c["meta"])
+    c.update(dim=dim, order=order, k=k, knowns=knowns, wm=wm, algo=algo, max_iter=max_iter, n=n)
+    c["nk"] = np.full(n, k, np.int32)
+    c["od"] = np.full(n, order, np.int32)
+    c["kn"] = np.full(n, knowns, np.int64)
+    c["w"] = np.full(n, wm, np.int32)
+    c["xk"] = np.ascontiguousarray(c["x"][c["hoods"]])
+    c["fk"] = np.ascontiguousarray(c["f"][c["hoods"]])
+    return c
+
+
+def check_sens(sens_got, sens_ref, label=""):
+    """sens parity: identical NaN pattern; entries within cond*eps of the column's largest entry"""
+    assert np.array_equal(np.isnan(sens_got), np.isnan(sens_ref)), label + ": NaN pattern of sens differs"
+    r = np.nan_to_num(sens_ref)
+    sc = np.abs(r).max(axis=(0, 1))
+    sc[sc == 0] = 1.0
+    err = np.abs(np.nan_to_num(sens_got) - r) / sc
+    assert err.max() < 1e-7 and np.median(err) < 1e-11, (label, err.max(), np.median(err))
+    return err.max()

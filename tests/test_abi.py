@@ -1,0 +1,121 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads and exports every symbol that
+include/wlsqm_b200.h declares; the ctypes table covers them; the product never touches the oracle;
+without a CUDA device the compute entry points fail loudly instead of falling back."""
+import ctypes
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def _declared_symbols():
+    hdr = (ROOT / "include" / "wlsqm_b200.h").read_text()
+    return sorted(set(re.findall(r"WLSQM_API\s+[\w\s\*]+?\b(wlsqm_\w+)\s*\(", hdr)))
+
+
+def test_library_exports_every_declared_symbol():
+    from wlsqm_b200 import _lib
+    syms = _declared_symbols()
+    assert len(syms) >= 20
+    L = ctypes.CDLL(str(_lib.LIB_PATH))
+    for s in syms:
+        assert hasattr(L, s), f"{s} declared in include/wlsqm_b200.h but not exported"
+    assert sorted(_lib.SIGNATURES) == syms, "ctypes signature table and header are out of sync"
+    assert _lib.lib().wlsqm_b200_abi_version() == 1
+
+
+def test_number_of_dofs_tables():
+    # reference tests/test_package.py:47-53
+    import wlsqm_b200 as w
+    from wlsqm_b200 import _lib
+    for dim, exp in ((1, [1, 2, 3, 4, 5]), (2, [1, 3, 6, 10, 15]), (3, [1, 4, 10, 20, 35])):
+        assert [w.number_of_dofs(dim, o) for o in range(5)] == exp
+        assert [_lib.lib().wlsqm_number_of_dofs(dim, o) for o in range(5)] == exp
+    assert w.number_of_dofs(0, 1) == -1 and w.number_of_dofs(2, 7) == -2
+    assert _lib.lib().wlsqm_number_of_dofs(5, 1) == -1 and _lib.lib().wlsqm_number_of_dofs(2, -1) == -2
+
+
+def test_package_surface_matches_reference():
+    # reference tests/test_package.py:24-32: the flat namespace re-exports
+    import wlsqm_b200 as w
+    for name in ["ALGO_BASIC", "ALGO_ITERATIVE", "WEIGHT_UNIFORM", "WEIGHT_CENTER", "ExpertSolver", "number_of_dofs",
+                 "interpolate_fit", "lambdify_fit", "b2_F", "i3_XYZ2", "SIZE3", "i3_0th_end"] + \
+                [f"fit_{d}D{it}{m}" for d in (1, 2, 3) for it in ("", "_iterative") for m in ("", "_many", "_many_parallel")]:
+        assert hasattr(w, name), name
+    assert not hasattr(w, "i1_0th_end") and not hasattr(w, "i2_0th_end")     # defs.pyx:316,346
+    assert w.b3_XYZ2 == 1 << w.i3_XYZ2 == 1 << 34
+    import wlsqm_b200.utils.lapackdrivers as ld
+    for name in ("mgeneral", "mgeneralp", "mgeneralfactor", "mgeneralfactorp", "mgeneralfactored", "mgeneralfactoredp"):
+        assert hasattr(ld, name)
+
+
+def test_argument_validation_needs_no_device():
+    import wlsqm_b200 as w
+    nk = np.array([5, 5], np.int32)
+    od = np.array([1, 1], np.int32)
+    kn = np.zeros(2, np.int64)
+    wm = np.ones(2, np.int32)
+    with pytest.raises(ValueError, match="same length"):
+        w.ExpertSolver(2, nk, od[:1], kn, wm)
+    with pytest.raises(ValueError, match="Dimension"):
+        w.ExpertSolver(5, nk, od, kn, wm)
+    with pytest.raises(ValueError, match="algorithm"):
+        w.ExpertSolver(2, nk, od, kn, wm, algorithm=None)
+    with pytest.raises(ValueError, match="Unknown algorithm"):
+        w.ExpertSolver(2, nk, od, kn, wm, algorithm=3)
+    with pytest.raises(ValueError, match="ntasks"):
+        w.ExpertSolver(2, nk, od, kn, wm, ntasks=0)
+    with pytest.raises(ValueError, match="dtype"):
+        w.ExpertSolver(2, nk.astype(np.int64), od, kn, wm)
+    with pytest.raises(ValueError):
+        w.interpolate_fit(np.zeros(2), np.zeros(6), 4, 2, np.zeros((3, 2)))
+    with pytest.raises(ValueError):
+        w.lambdify_fit(np.zeros(2), np.zeros(6), 2, 9)
+
+
+def test_no_cpu_fallback_without_device():
+    from wlsqm_b200 import _lib
+    import wlsqm_b200 as w
+    if _lib.lib().wlsqm_device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    nk = np.array([5], np.int32)
+    with pytest.raises(RuntimeError, match="no CUDA device"):
+        w.ExpertSolver(2, nk, np.array([1], np.int32), np.zeros(1, np.int64), np.ones(1, np.int32))
+    with pytest.raises(RuntimeError, match="no CUDA device"):
+        w.fit_2D(np.zeros((5, 2)), np.zeros(5), np.zeros(2), np.zeros(3), None, order=1, knowns=0)
+    with pytest.raises(RuntimeError, match="no CUDA device"):
+        w.interpolate_fit(np.zeros(2), np.zeros(3), 2, 1, np.zeros((4, 2)))
+
+
+def test_product_never_touches_the_oracle():
+    """only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may use oracle/"""
+    bad = []
+    for p in (ROOT / "python-wlsqm_b200").rglob("*"):
+        if p.suffix in (".py", ".cu", ".cuh", ".h", ".pyx") and p.is_file():
+            txt = p.read_text(errors="replace")
+            if re.search(r"^\s*(import|from)\s+oracle\b|oracle/|wlsqm_oracle|libwlsqm_oracle|_ref/", txt, re.M):
+                bad.append(str(p))
+    hdr = (ROOT / "include" / "wlsqm_b200.h").read_text()
+    assert "oracle" not in hdr
+    assert not bad, bad
+
+
+def test_as_arr_mirrors_memoryview_checks():
+    from wlsqm_b200 import _lib
+    a = np.zeros((4, 6))
+    assert _lib.as_arr(a, np.float64, 2, "a").strides == (6, 1)
+    assert _lib.as_arr(a[:, ::2], np.float64, 2, "a", last_contig=False, allow_copy=True).strides == (3, 1)
+    with pytest.raises(ValueError, match="contiguous"):
+        _lib.as_arr(a[:, ::2], np.float64, 2, "a")
+    with pytest.raises(ValueError, match="dtype"):
+        _lib.as_arr(a.astype(np.float32), np.float64, 2, "a")
+    with pytest.raises(ValueError, match="dimensions"):
+        _lib.as_arr(a, np.float64, 3, "a")
+    ro = a.copy()
+    ro.setflags(write=False)
+    with pytest.raises(ValueError, match="read-only"):
+        _lib.as_arr(ro, np.float64, 2, "a", writable=True)
+    assert _lib.as_arr(a[::2], np.float64, 2, "a").strides == (12, 1)      # pitched rows are fine
