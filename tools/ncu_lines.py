@@ -30,7 +30,7 @@ for r in rows:
 tot = sum(l[0] for l in lines) or 1
 tots = sum(l[1] for l in lines) or 1
 print(f"total warp instructions {tot:,}; samples {tots:,}")
-for inst, smp, f, ln, src, d in sorted(lines, reverse=True)[:top]:
+for inst, smp, f, ln, src, d in sorted(lines, key=lambda l: -l[0])[:top]:
     stalls = {k[6:]: int(v) for k, v in d.items() if k.startswith("stall_") and "Not Issued" not in k and v not in ("", "0")}
     ts = sorted(stalls.items(), key=lambda kv: -kv[1])[:3]
     print(f"{100*inst/tot:5.1f}% inst {100*smp/tots:5.1f}% smp  {f}:{ln:>4}  {src[:90]:90s} {ts}")
