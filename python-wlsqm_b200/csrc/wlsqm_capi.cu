@@ -118,6 +118,8 @@ struct wlsqm_solver {
     bool ready = false;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
+    cudaStream_t s_in = nullptr, s_out = nullptr;   // H2D / D2H streams of the staged (host-pointer) pipeline
+    std::vector<cudaEvent_t> events;
     int sm_count = 148;
     DevBuf xk_keep;             // dense copy of xk (ALGO_ITERATIVE needs the geometry at solve time)
     DevBuf st_xk, st_fk, st_fi, st_sens, st_x, st_I, st_out;
@@ -165,7 +167,7 @@ int config_prepare(const wlsqm_solver* s, PrepareParams& P, LaunchCfg& L) {
     return WLSQM_OK;
 }
 
-int config_solve(const wlsqm_solver* s, SolveParams& P, LaunchCfg& L) {
+int config_solve(const wlsqm_solver* s, SolveParams& P, LaunchCfg& L, long long ncases_launch) {
     const bool iter = s->algorithm == WLSQM_ALGO_ITERATIVE;
     // one stage of the per-warp ring: [operator block | fext = fk + known fi | xk (ALGO_ITERATIVE)]
     const int op_doubles = std::max(2, even(s->maxnq * s->maxnr));
@@ -206,7 +208,7 @@ int config_solve(const wlsqm_solver* s, SolveParams& P, LaunchCfg& L) {
     L.smem = (size_t)P.bar_off_bytes + (size_t)warps * S * 8;
     int ctas = (int)(SMEM_PER_SM / (L.smem + 1024));
     ctas = std::max(1, std::min(ctas, std::max(1, env_int("WLSQM_SOLVE_MAXWARPS_SM", 48) / warps)));
-    long long need = (s->ncases + warps - 1) / warps;
+    long long need = (ncases_launch + warps - 1) / warps;
     L.blocks = (int)std::max<long long>(1, std::min<long long>((long long)s->sm_count * ctas, need));
     return WLSQM_OK;
 }
@@ -388,6 +390,9 @@ int wlsqm_solver_destroy(wlsqm_solver_t* s) {
     s->xk_keep.release(); s->st_xk.release(); s->st_fk.release(); s->st_fi.release(); s->st_sens.release();
     s->st_x.release(); s->st_I.release(); s->st_out.release();
     if (s->own_stream && s->stream) cudaStreamDestroy(s->stream);
+    if (s->s_in) cudaStreamDestroy(s->s_in);
+    if (s->s_out) cudaStreamDestroy(s->s_out);
+    for (cudaEvent_t e : s->events) cudaEventDestroy(e);
     cudaGetLastError();
     delete s;
     return WLSQM_OK;
@@ -497,18 +502,16 @@ int wlsqm_solver_solve(wlsqm_solver_t* s, const double* fk, int64_t fk_s0, int64
         P.iters_case = s->iters_dev + 1;
     }
 
-    // fk
+    // ---- device-side views of the arguments (host arrays get dense device mirrors) -------------------
+    const bool staged = !fk_dev || !fi_dev || !sens_dev;
     if (fk_dev) {
         P.fk = fk; P.fk_s0 = fk_s0; P.fk_s1 = fk_s1;
     } else {
         if (fk_s1 != 1 && s->maxnk > 1) return fail(WLSQM_E_VALUE, "host fk must have unit stride on its last axis");
         rc = s->st_fk.reserve((size_t)n * s->maxnk * 8);
         if (rc) return rc;
-        rc = to_dense((double*)s->st_fk.p, fk, n, s->maxnk, fk_s0, st);
-        if (rc) return rc;
         P.fk = (const double*)s->st_fk.p; P.fk_s0 = s->maxnk; P.fk_s1 = 1;
     }
-    // fi (known values in; unknowns out)
     bool deferred = false;
     if (fi_dev) {
         P.fi_in = fi; P.fi_in_s0 = fi_s0;
@@ -522,64 +525,104 @@ int wlsqm_solver_solve(wlsqm_solver_t* s, const double* fk, int64_t fk_s0, int64
         }
         if (alias) deferred = true;
         else { P.fi_out = fi; P.fi_out_s0 = fi_s0; }
-    } else {
-        if (s->any_knowns) {
-            rc = s->st_fi.reserve((size_t)n * s->maxno * 8);
-            if (rc) return rc;
-            rc = to_dense((double*)s->st_fi.p, fi, n, s->maxno, fi_s0, st);
-            if (rc) return rc;
-            P.fi_in = (const double*)s->st_fi.p; P.fi_in_s0 = s->maxno;
-        }
+    } else if (s->any_knowns) {
+        rc = s->st_fi.reserve((size_t)n * s->maxno * 8);
+        if (rc) return rc;
+        P.fi_in = (const double*)s->st_fi.p; P.fi_in_s0 = s->maxno;
     }
-    // sens
+    const long long plane = (long long)s->maxnk * s->maxno;
     if (s->do_sens) {
         if (sens_dev) {
             P.sens = sens; P.sens_s0 = sens_s0; P.sens_s1 = sens_s1;
         } else {
-            rc = s->st_sens.reserve((size_t)n * s->maxnk * s->maxno * 8);
+            rc = s->st_sens.reserve((size_t)n * plane * 8);
             if (rc) return rc;
-            P.sens = (double*)s->st_sens.p; P.sens_s0 = (long long)s->maxnk * s->maxno; P.sens_s1 = s->maxno;
+            P.sens = (double*)s->st_sens.p; P.sens_s0 = plane; P.sens_s1 = s->maxno;
         }
     }
+    const bool sens_direct = s->do_sens && !sens_dev && s->uniform && s->uni.nk == s->maxnk &&
+                             sens_s1 == s->maxno && sens_s0 == plane;
 
+    // ---- chunked pipeline: H2D of chunk i+1, kernel of chunk i and D2H of chunk i-1 overlap ------------
+    // (device-resident arguments: one chunk, everything on the solver's stream, no synchronisation)
+    long long chunk = n;
+    cudaStream_t s_in = st, s_out = st;
+    if (staged) {
+        chunk = std::max<long long>(1024, env_int("WLSQM_SOLVE_CHUNK", 65536));
+        if (!s->s_in) CU(cudaStreamCreateWithFlags(&s->s_in, cudaStreamNonBlocking));
+        if (!s->s_out) CU(cudaStreamCreateWithFlags(&s->s_out, cudaStreamNonBlocking));
+        s_in = s->s_in; s_out = s->s_out;
+        const size_t nev = 2 * (size_t)((n + chunk - 1) / chunk) + 1;
+        while (s->events.size() < nev) {
+            cudaEvent_t e;
+            CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            s->events.push_back(e);
+        }
+        // the copy streams must not run ahead of work already queued on the solver's stream
+        CU(cudaEventRecord(s->events[nev - 1], st));
+        CU(cudaStreamWaitEvent(s_in, s->events[nev - 1], 0));
+    }
     LaunchCfg L;
-    rc = config_solve(s, P, L);
-    if (rc) return rc;
-    CU(launch_solve(s->dim, P, L.blocks, L.threads, L.smem, st));
+    size_t ev = 0;
+    for (long long c0 = 0; c0 < n; c0 += chunk) {
+        const long long c1 = std::min(n, c0 + chunk), rows = c1 - c0;
+        if (!fk_dev) {
+            rc = to_dense((double*)s->st_fk.p + c0 * s->maxnk, fk + c0 * fk_s0, rows, s->maxnk, fk_s0, s_in);
+            if (rc) return rc;
+        }
+        if (!fi_dev && s->any_knowns) {
+            rc = to_dense((double*)s->st_fi.p + c0 * s->maxno, fi + c0 * fi_s0, rows, s->maxno, fi_s0, s_in);
+            if (rc) return rc;
+        }
+        if (staged) {
+            CU(cudaEventRecord(s->events[ev], s_in));
+            CU(cudaStreamWaitEvent(st, s->events[ev], 0));
+            ++ev;
+        }
+        P.case_lo = c0;
+        P.ncases = c1;
+        rc = config_solve(s, P, L, rows);
+        if (rc) return rc;
+        CU(launch_solve(s->dim, P, L.blocks, L.threads, L.smem, st));
+        if (staged) {
+            CU(cudaEventRecord(s->events[ev], st));
+            CU(cudaStreamWaitEvent(s_out, s->events[ev], 0));
+            ++ev;
+        }
+        if (!fi_dev && s->uniform_no) {
+            rc = from_dense(fi + c0 * fi_s0, fi_s0, s->fi_case + c0 * s->maxno, s->maxno, rows, s->uni.no, s_out);
+            if (rc) return rc;
+        }
+        if (sens_direct)
+            CU(cudaMemcpyAsync(sens + c0 * plane, (const double*)s->st_sens.p + c0 * plane, (size_t)rows * plane * 8,
+                               cudaMemcpyDeviceToHost, s_out));
+    }
     if (deferred) CU(launch_scatter_fi(s->dmeta, s->uni, n, s->fi_case, s->maxno, fi, fi_s0, st));
 
-    // results to host
-    if (!fi_dev) {
-        if (s->uniform_no) {
-            rc = from_dense(fi, fi_s0, s->fi_case, s->maxno, n, s->uni.no, st);
-            if (rc) return rc;
-        } else {
-            std::vector<double> tmp((size_t)n * s->maxno);
-            CU(cudaMemcpyAsync(tmp.data(), s->fi_case, tmp.size() * 8, cudaMemcpyDeviceToHost, st));
-            CU(cudaStreamSynchronize(st));
-            for (long long i = 0; i < n; ++i)
-                memcpy(fi + i * fi_s0, tmp.data() + (size_t)i * s->maxno, (size_t)s->hmeta[(size_t)i].no * 8);
-        }
+    // ---- results that need a host-side scatter (heterogeneous no / nk, pitched sens) ---------------------
+    if (!fi_dev && !s->uniform_no) {
+        std::vector<double> tmp((size_t)n * s->maxno);
+        CU(cudaMemcpyAsync(tmp.data(), s->fi_case, tmp.size() * 8, cudaMemcpyDeviceToHost, s_out));
+        CU(cudaStreamSynchronize(s_out));
+        for (long long i = 0; i < n; ++i)
+            memcpy(fi + i * fi_s0, tmp.data() + (size_t)i * s->maxno, (size_t)s->hmeta[(size_t)i].no * 8);
     }
-    if (s->do_sens && !sens_dev) {
-        const long long plane = (long long)s->maxnk * s->maxno;
-        if (s->uniform && s->uni.nk == s->maxnk && sens_s1 == s->maxno && sens_s0 == plane) {
-            CU(cudaMemcpyAsync(sens, s->st_sens.p, (size_t)n * plane * 8, cudaMemcpyDeviceToHost, st));
-        } else {
-            std::vector<double> tmp((size_t)n * plane);
-            CU(cudaMemcpyAsync(tmp.data(), s->st_sens.p, tmp.size() * 8, cudaMemcpyDeviceToHost, st));
-            CU(cudaStreamSynchronize(st));
-            for (long long i = 0; i < n; ++i) {
-                const CaseMeta& m = s->hmeta[(size_t)i];
-                for (int k = 0; k < m.nk; ++k)
-                    memcpy(sens + i * sens_s0 + (long long)k * sens_s1, tmp.data() + (size_t)i * plane + (size_t)k * s->maxno,
-                           (size_t)m.no * 8);
-            }
+    if (s->do_sens && !sens_dev && !sens_direct) {
+        std::vector<double> tmp((size_t)n * plane);
+        CU(cudaMemcpyAsync(tmp.data(), s->st_sens.p, tmp.size() * 8, cudaMemcpyDeviceToHost, s_out));
+        CU(cudaStreamSynchronize(s_out));
+        for (long long i = 0; i < n; ++i) {
+            const CaseMeta& m = s->hmeta[(size_t)i];
+            if (m.nr < 1) continue;     // silent no-op case: sens untouched
+            for (int k = 0; k < m.nk; ++k)
+                memcpy(sens + i * sens_s0 + (long long)k * sens_s1, tmp.data() + (size_t)i * plane + (size_t)k * s->maxno,
+                       (size_t)m.no * 8);
         }
     }
     int32_t it = 0;
     if (iter) CU(cudaMemcpyAsync(&it, s->iters_dev, 4, cudaMemcpyDeviceToHost, st));
-    if (iter || !fk_dev || !fi_dev || !sens_dev) CU(cudaStreamSynchronize(st));
+    if (staged) CU(cudaStreamSynchronize(s_out));
+    if (iter || staged) CU(cudaStreamSynchronize(st));
     if (iters_out) *iters_out = it;
     return WLSQM_OK;
 }

@@ -25,7 +25,8 @@ struct SolveParams {
     const CaseMeta* meta;
     CaseMeta uni;
     long long op_stride;
-    long long ncases;
+    long long ncases;                                // cases [case_lo, ncases) are processed by this launch
+    long long case_lo;
     const double* op;
     const double* fk; long long fk_s0, fk_s1;        // [ncases][nk] fully strided (simple.pyx:149-159)
     const double* fi_in; long long fi_in_s0;         // caller's fi (known values are read from it)

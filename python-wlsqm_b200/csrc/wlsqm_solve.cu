@@ -89,7 +89,7 @@ __global__ void __launch_bounds__(SOLVE_MAX_THREADS) solve_kernel(SolveParams P)
     double* rs = wb + P.off_r;              // ITER: residual at the neighbours
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + P.bar_off_bytes) + warp * S;
 
-    const long long gw = (long long)blockIdx.x * nwarps + warp;
+    const long long gw = P.case_lo + (long long)blockIdx.x * nwarps + warp;   // first case of this warp
     const long long GW = (long long)gridDim.x * nwarps;
     const long long n_my = gw < P.ncases ? (P.ncases - gw + GW - 1) / GW : 0;
 
