@@ -23,50 +23,66 @@
 
 namespace wlsqm {
 
-// out[j] = sum_q op[q*nr + j] * v[q], q < n, for one warp.  The 32 lanes form G = 32/W groups of W lanes
-// (W = smallest power of two >= nr); group g takes the rows q = g, g+G, ... so that one shared-memory
-// wavefront reads G consecutive operator rows; a xor-butterfly over the groups leaves the total for
-// reduced DOF j in every lane with (lane & (W-1)) == j.  nr > 32 (3D order 4 with < 3 knowns): lanes
-// also own row j + 32, returned in `hi`.
+// Geometry of the grouped warp GEMV for a case with nr unknowns: the 32 lanes form G = 32/W groups of
+// W lanes (W = smallest power of two >= nr, capped at 32); lane = g*W + j.
+struct Groups {
+    int lw;   // log2(W)
+    int W, G, g, j;
+};
+__device__ __forceinline__ Groups make_groups(int nr, int lane) {
+    Groups r;
+    r.lw = nr <= 1 ? 0 : (nr > 16 ? 5 : 32 - __clz(nr - 1));
+    r.W = 1 << r.lw;
+    r.G = 32 >> r.lw;
+    r.g = lane >> r.lw;
+    r.j = lane & (r.W - 1);
+    return r;
+}
+
+// out[j] = sum_q op[q*nr + j] * v[q], q < n, for one warp.  Group g takes the rows q = g, g+G, ... so that
+// one shared-memory wavefront reads G consecutive operator rows (conflict free); 4 independent FMA chains
+// per lane; a xor-butterfly over the groups leaves the total for reduced DOF j in every lane with
+// (lane & (W-1)) == j.  nr > 32 (3D order 4 with < 3 knowns): lanes also own row j + 32, returned in `hi`.
 __device__ __forceinline__ void warp_matvec(const double* __restrict__ op, const double* __restrict__ v, int n, int nr,
-                                            int lane, double& lo, double& hi) {
-    const int W = nr <= 1 ? 1 : nr <= 2 ? 2 : nr <= 4 ? 4 : nr <= 8 ? 8 : nr <= 16 ? 16 : 32;
-    const int G = 32 / W;
-    const int g = lane / W, j = lane & (W - 1);
+                                            const Groups& gr, double& lo, double& hi) {
     double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
     hi = 0.0;
-    if (j < nr) {
-        const double* p = op + g * nr + j;
-        const double* vq = v + g;
-        const int sp = G * nr;
-        int q = g;
-        for (; q + 3 * G < n; q += 4 * G) {
-            a0 = fma(p[0], vq[0], a0);
-            a1 = fma(p[sp], vq[G], a1);
-            a2 = fma(p[2 * sp], vq[2 * G], a2);
-            a3 = fma(p[3 * sp], vq[3 * G], a3);
-            p += 4 * sp;
-            vq += 4 * G;
+    if (gr.j < nr) {
+        const int G = gr.G, sp = G * nr;
+        const double* p = op + gr.g * nr + gr.j;
+        const double* vq = v + gr.g;
+        const double* p1 = p + sp;
+        const double* p2 = p1 + sp;
+        const double* p3 = p2 + sp;
+        int cnt = (n - gr.g + G - 1) >> (5 - gr.lw);      // rows of this group: ceil((n - g) / G)
+        int o = 0, ov = 0;
+        for (; cnt >= 4; cnt -= 4) {
+            a0 = fma(p[o], vq[ov], a0);
+            a1 = fma(p1[o], vq[ov + G], a1);
+            a2 = fma(p2[o], vq[ov + 2 * G], a2);
+            a3 = fma(p3[o], vq[ov + 3 * G], a3);
+            o += 4 * sp;
+            ov += 4 * G;
         }
-        for (; q < n; q += G) {
-            a0 = fma(p[0], vq[0], a0);
-            p += sp;
-            vq += G;
+        for (; cnt > 0; --cnt) {
+            a0 = fma(p[o], vq[ov], a0);
+            o += sp;
+            ov += G;
         }
-        if (j + 32 < nr) {   // only when W == 32, G == 1
-            const double* p2 = op + j + 32;
+        if (gr.j + 32 < nr) {   // only when W == 32, G == 1
+            const double* q2 = op + gr.j + 32;
             double b0 = 0.0, b1 = 0.0;
-            int q2 = 0;
-            for (; q2 + 1 < n; q2 += 2) {
-                b0 = fma(p2[q2 * nr], v[q2], b0);
-                b1 = fma(p2[(q2 + 1) * nr], v[q2 + 1], b1);
+            int t = 0;
+            for (; t + 1 < n; t += 2) {
+                b0 = fma(q2[t * nr], v[t], b0);
+                b1 = fma(q2[(t + 1) * nr], v[t + 1], b1);
             }
-            if (q2 < n) b0 = fma(p2[q2 * nr], v[q2], b0);
+            if (t < n) b0 = fma(q2[t * nr], v[t], b0);
             hi = b0 + b1;
         }
     }
     lo = (a0 + a1) + (a2 + a3);
-    for (int off = W; off < 32; off <<= 1) lo += __shfl_xor_sync(0xffffffffu, lo, off);
+    for (int off = gr.W; off < 32; off <<= 1) lo += __shfl_xor_sync(0xffffffffu, lo, off);
 }
 
 // value of reduced DOF j for original slot o held by this lane (every lane must call it)
@@ -76,7 +92,9 @@ __device__ __forceinline__ double fetch_reduced(double lo, double hi, int j) {
     return j < 32 ? vlo : vhi;
 }
 
-template <int DIM, bool ITER, bool SENS>
+// UNI = the whole batch shares one CaseMeta (passed by value): everything derived from it is loop
+// invariant and hoisted by the compiler, which is what keeps the per-case instruction count low.
+template <int DIM, bool ITER, bool SENS, bool UNI>
 __global__ void __launch_bounds__(SOLVE_MAX_THREADS) solve_kernel(SolveParams P) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31;
@@ -87,7 +105,9 @@ __global__ void __launch_bounds__(SOLVE_MAX_THREADS) solve_kernel(SolveParams P)
     double* ring = wb;                      // S stages of [operator block | fext = (fk, known fi) | xk (ITER)]
     double* fis = wb + P.off_fi;            // current solution of the case (no values)
     double* rs = wb + P.off_r;              // ITER: residual at the neighbours
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + P.bar_off_bytes) + warp * S;
+    const uint32_t ring_u32 = smem_u32(ring);
+    const uint32_t bars_u32 = smem_u32(smem_raw + P.bar_off_bytes) + (uint32_t)(warp * S) * 8u;
+    const uint32_t stage_bytes = (uint32_t)P.stage_doubles * 8u;
 
     const long long gw = P.case_lo + (long long)blockIdx.x * nwarps + warp;   // first case of this warp
     const long long GW = (long long)gridDim.x * nwarps;
@@ -95,11 +115,11 @@ __global__ void __launch_bounds__(SOLVE_MAX_THREADS) solve_kernel(SolveParams P)
 
     auto get_meta = [&](long long c) {
         CaseMeta m;
-        if (P.meta) {
-            m = P.meta[c];
-        } else {
+        if (UNI) {
             m = P.uni;
             m.op_off = c * P.op_stride;
+        } else {
+            m = P.meta[c];
         }
         return m;
     };
@@ -109,14 +129,14 @@ __global__ void __launch_bounds__(SOLVE_MAX_THREADS) solve_kernel(SolveParams P)
     auto xk_by_tma = [&](const CaseMeta& m) { return ITER && P.xk_tma && !((m.nk * DIM) & 1); };
     auto issue = [&](int s, long long c) {   // lane 0 only: arm the stage's barrier and start its copies
         const CaseMeta m = get_meta(c);
-        double* st = ring + (size_t)s * P.stage_doubles;
+        const uint32_t st = ring_u32 + (uint32_t)s * stage_bytes, bar = bars_u32 + (uint32_t)s * 8u;
         const uint32_t b_op = ((uint32_t)((m.nk + m.nkn) * (int)m.nr) * 8u + 15u) & ~15u;
         const uint32_t b_f = f_by_tma(m) ? (uint32_t)m.nk * 8u : 0u;
         const uint32_t b_x = xk_by_tma(m) ? (uint32_t)(m.nk * DIM) * 8u : 0u;
-        mbar_expect_tx(&bars[s], b_op + b_f + b_x);
-        if (b_op) tma_load_1d(st, P.op + m.op_off, b_op, &bars[s]);
-        if (b_f) tma_load_1d(st + P.off_f, P.fk + c * P.fk_s0, b_f, &bars[s]);
-        if (b_x) tma_load_1d(st + P.off_xk, P.xk + c * P.xk_s0, b_x, &bars[s]);
+        mbar_expect_tx_u32(bar, b_op + b_f + b_x);
+        if (b_op) tma_load_1d_u32(st, P.op + m.op_off, b_op, bar);
+        if (b_f) tma_load_1d_u32(st + (uint32_t)P.off_f * 8u, P.fk + c * P.fk_s0, b_f, bar);
+        if (b_x) tma_load_1d_u32(st + (uint32_t)P.off_xk * 8u, P.xk + c * P.xk_s0, b_x, bar);
     };
     // known fi values of a case, one register per lane and 32-slot group (prefetched one case ahead)
     auto load_g = [&](long long c, const CaseMeta& m, double& g0, double& g1) {
@@ -126,7 +146,7 @@ __global__ void __launch_bounds__(SOLVE_MAX_THREADS) solve_kernel(SolveParams P)
     };
 
     if (lane == 0) {
-        for (int s = 0; s < S; ++s) mbar_init(&bars[s], 1);
+        for (int s = 0; s < S; ++s) mbar_init_u32(bars_u32 + (uint32_t)s * 8u, 1);
         fence_mbar_init();
         for (int s = 0; s < S - 1 && s < n_my; ++s) issue(s, gw + (long long)s * GW);
     }
@@ -138,21 +158,23 @@ __global__ void __launch_bounds__(SOLVE_MAX_THREADS) solve_kernel(SolveParams P)
     CaseMeta mt{};
     if (n_my > 0) {
         mt = get_meta(gw);
-        load_g(gw, mt, g0, g1);
+        if (mt.nkn) load_g(gw, mt, g0, g1);
     }
-    for (long long i = 0; i < n_my; ++i) {
-        const long long c = gw + i * GW;
+    long long c = gw;
+    for (long long i = 0; i < n_my; ++i, c += GW) {
         if (lane == 0 && i + S - 1 < n_my) {
             int sn = stage + S - 1;
             if (sn >= S) sn -= S;
-            issue(sn, gw + (i + S - 1) * GW);
+            issue(sn, c + (long long)(S - 1) * GW);
         }
+        if (UNI) mt = P.uni;   // loop invariant: lets the compiler hoist everything derived from the record
         const int nk = mt.nk, no = mt.no, nr = mt.nr, nkn = mt.nkn, nq = nk + nkn;
         const long long knowns = mt.knowns;
         double* st = ring + (size_t)stage * P.stage_doubles;
         const double* op = st;
         double* fext = st + P.off_f;
         const double* xks = st + P.off_xk;
+        const Groups gr = make_groups(nr, lane);
 
         // ---- data that did not come by TMA, and the known values ---------------------------------
         if (!f_by_tma(mt)) {
@@ -164,31 +186,33 @@ __global__ void __launch_bounds__(SOLVE_MAX_THREADS) solve_kernel(SolveParams P)
             double* xw = st + P.off_xk;
             for (int t = lane; t < nk * DIM; t += 32) xw[t] = xp[(long long)(t / DIM) * P.xk_s1 + (t % DIM)];
         }
+        // reduced index of the slots this lane writes back: o = lane and o = lane + 32
+        const bool in0 = lane < no, in1 = lane + 32 < no;
+        const bool unk0 = in0 && !((knowns >> lane) & 1LL);
+        const bool unk1 = in1 && !((knowns >> (lane + 32)) & 1LL);
+        const int below0 = __popcll(knowns & ((1LL << lane) - 1));
+        const int below1 = __popcll(knowns & ((1LL << (lane + 32)) - 1));
+        const int j0 = unk0 ? lane - below0 : 0;
+        const int j1 = unk1 ? lane + 32 - below1 : 0;
         if (nkn) {
-            if (lane < no && ((knowns >> lane) & 1LL)) fext[nk + __popcll(knowns & ((1LL << lane) - 1))] = g0;
-            if (lane + 32 < no && ((knowns >> (lane + 32)) & 1LL))
-                fext[nk + __popcll(knowns & ((1LL << (lane + 32)) - 1))] = g1;
+            if (in0 && !unk0) fext[nk + below0] = g0;
+            if (in1 && !unk1) fext[nk + below1] = g1;
         }
         // prefetch the next case's record and known values while this one is being worked on
         CaseMeta mt_next = mt;
         double gn0 = 0.0, gn1 = 0.0;
         if (i + 1 < n_my) {
-            mt_next = get_meta(c + GW);
+            if (!UNI) mt_next = get_meta(c + GW);
             if (mt_next.nkn) load_g(c + GW, mt_next, gn0, gn1);
         }
         __syncwarp();
-        mbar_wait(&bars[stage], phase);
+        mbar_wait_u32(bars_u32 + (uint32_t)stage * 8u, phase);
 
         // ---- fi[unknown] = Op^T fext ----------------------------------------------------------------
-        // reduced index of the slots this lane writes back: o = lane and o = lane + 32
-        const bool unk0 = lane < no && !((knowns >> lane) & 1LL);
-        const bool unk1 = lane + 32 < no && !((knowns >> (lane + 32)) & 1LL);
-        const int j0 = unk0 ? lane - __popcll(knowns & ((1LL << lane) - 1)) : 0;
-        const int j1 = unk1 ? lane + 32 - __popcll(knowns & ((1LL << (lane + 32)) - 1)) : 0;
         double v0 = g0, v1 = g1;     // known slots keep the caller's value
         if (nr > 0) {
             double lo, hi;
-            warp_matvec(op, fext, nq, nr, lane, lo, hi);
+            warp_matvec(op, fext, nq, nr, gr, lo, hi);
             const double t0 = fetch_reduced(lo, hi, j0);
             if (unk0) v0 = t0;
             if (no > 32) {
@@ -197,8 +221,8 @@ __global__ void __launch_bounds__(SOLVE_MAX_THREADS) solve_kernel(SolveParams P)
             }
         }
         if (ITER) {
-            if (lane < no) fis[lane] = v0;
-            if (lane + 32 < no) fis[lane + 32] = v1;
+            if (in0) fis[lane] = v0;
+            if (in1) fis[lane + 32] = v1;
             __syncwarp();
         }
 
@@ -206,11 +230,25 @@ __global__ void __launch_bounds__(SOLVE_MAX_THREADS) solve_kernel(SolveParams P)
         if (SENS && nr > 0) {   // nr == 0: silent no-op, sens untouched (impl.pyx:742)
             double* sn = P.sens + c * P.sens_s0;
             const double qnan = __longlong_as_double(0x7ff8000000000000LL);
-            for (int t = lane; t < nk * no; t += 32) {
-                const int k = t / no, o = t - k * no;
-                double v = qnan;
-                if (!((knowns >> o) & 1LL)) v = op[k * nr + (o - __popcll(knowns & ((1LL << o) - 1)))];
-                st_stream(sn + (long long)k * P.sens_s1 + o, v);
+            if (P.sens_s1 == no) {
+                // rows are back to back: walk the (k, o) plane with lane-contiguous stores
+                int k = lane / no, o = lane - k * no;          // position of element t = lane
+                const int dk = 32 / no, d_o = 32 - dk * no;      // advance of (k, o) per 32 elements
+                for (int t = lane; t < nk * no; t += 32) {
+                    double v = qnan;
+                    if (!((knowns >> o) & 1LL)) v = op[k * nr + (o - __popcll(knowns & ((1LL << o) - 1)))];
+                    st_stream(sn + t, v);
+                    k += dk;
+                    o += d_o;
+                    if (o >= no) { o -= no; ++k; }
+                }
+            } else {
+                for (int t = lane; t < nk * no; t += 32) {
+                    const int k = t / no, o = t - k * no;
+                    double v = qnan;
+                    if (!((knowns >> o) & 1LL)) v = op[k * nr + (o - __popcll(knowns & ((1LL << o) - 1)))];
+                    st_stream(sn + (long long)k * P.sens_s1 + o, v);
+                }
             }
         }
 
@@ -238,7 +276,7 @@ __global__ void __launch_bounds__(SOLVE_MAX_THREADS) solve_kernel(SolveParams P)
                 __syncwarp();
                 if (nr > 0) {
                     double lo, hi;
-                    warp_matvec(op, rs, nk, nr, lane, lo, hi);
+                    warp_matvec(op, rs, nk, nr, gr, lo, hi);
                     const double t0 = fetch_reduced(lo, hi, j0);
                     if (unk0) { v0 += t0; fis[lane] = v0; }
                     if (no > 32) {
@@ -256,11 +294,11 @@ __global__ void __launch_bounds__(SOLVE_MAX_THREADS) solve_kernel(SolveParams P)
         }
 
         // ---- write-back: solver-owned copy (all `no` entries) and, if allowed, the caller's fi ---
-        if (lane < no) {
+        if (in0) {
             P.fi_case[c * P.fi_case_ld + lane] = v0;
             if (P.fi_out && unk0) P.fi_out[c * P.fi_out_s0 + lane] = v0;
         }
-        if (lane + 32 < no) {
+        if (in1) {
             P.fi_case[c * P.fi_case_ld + lane + 32] = v1;
             if (P.fi_out && unk1) P.fi_out[c * P.fi_out_s0 + lane + 32] = v1;
         }
@@ -282,25 +320,29 @@ __global__ void scatter_fi_kernel(const CaseMeta* meta, CaseMeta uni, long long 
     if (o < no) fi_out[c * s0 + o] = fi_case[c * ld + o];
 }
 
-template <int DIM, bool ITER, bool SENS>
+template <int DIM, bool ITER, bool SENS, bool UNI>
 static cudaError_t launch_one(const SolveParams& P, int blocks, int threads, size_t smem, cudaStream_t st) {
-    cudaError_t e =
-        cudaFuncSetAttribute(solve_kernel<DIM, ITER, SENS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(solve_kernel<DIM, ITER, SENS, UNI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)smem);
     if (e != cudaSuccess) return e;
-    solve_kernel<DIM, ITER, SENS><<<blocks, threads, smem, st>>>(P);
+    solve_kernel<DIM, ITER, SENS, UNI><<<blocks, threads, smem, st>>>(P);
     return cudaGetLastError();
 }
 
+template <int DIM, bool ITER>
+static cudaError_t launch_su(const SolveParams& P, int blocks, int threads, size_t smem, cudaStream_t st) {
+    const bool sens = P.sens != nullptr, uni = P.meta == nullptr;
+    if (sens) return uni ? launch_one<DIM, ITER, true, true>(P, blocks, threads, smem, st)
+                         : launch_one<DIM, ITER, true, false>(P, blocks, threads, smem, st);
+    return uni ? launch_one<DIM, ITER, false, true>(P, blocks, threads, smem, st)
+               : launch_one<DIM, ITER, false, false>(P, blocks, threads, smem, st);
+}
+
 cudaError_t launch_solve(int dim, const SolveParams& P, int blocks, int threads, size_t smem, cudaStream_t st) {
-    const bool iter = P.algorithm == WLSQM_ALGO_ITERATIVE, sens = P.sens != nullptr;
-    if (!iter) return sens ? launch_one<1, false, true>(P, blocks, threads, smem, st)
-                           : launch_one<1, false, false>(P, blocks, threads, smem, st);
-    if (dim == 1) return sens ? launch_one<1, true, true>(P, blocks, threads, smem, st)
-                              : launch_one<1, true, false>(P, blocks, threads, smem, st);
-    if (dim == 2) return sens ? launch_one<2, true, true>(P, blocks, threads, smem, st)
-                              : launch_one<2, true, false>(P, blocks, threads, smem, st);
-    return sens ? launch_one<3, true, true>(P, blocks, threads, smem, st)
-                : launch_one<3, true, false>(P, blocks, threads, smem, st);
+    if (P.algorithm != WLSQM_ALGO_ITERATIVE) return launch_su<1, false>(P, blocks, threads, smem, st);
+    if (dim == 1) return launch_su<1, true>(P, blocks, threads, smem, st);
+    if (dim == 2) return launch_su<2, true>(P, blocks, threads, smem, st);
+    return launch_su<3, true>(P, blocks, threads, smem, st);
 }
 
 cudaError_t launch_scatter_fi(const CaseMeta* meta, const CaseMeta& uni, long long ncases, const double* fi_case,
