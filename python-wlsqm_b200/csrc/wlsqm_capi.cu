@@ -175,10 +175,15 @@ int config_solve(const wlsqm_solver* s, SolveParams& P, LaunchCfg& L, long long 
     const int x_doubles = iter ? std::max(2, even(s->maxnk * s->dim)) : 0;
     const int stage_doubles = op_doubles + f_doubles + x_doubles;
     const size_t stage_bytes = (size_t)stage_doubles * 8;
-    int S = env_int("WLSQM_SOLVE_STAGES", stage_bytes <= 8192 ? 3 : 2);
+    // Measured on B200 (profiles/README.md): a ring of 2 stages and ONE CTA per SM with as many warps as
+    // fit (16 for the headline block size) streams best; deeper rings or several CTAs per SM put more
+    // distant operator blocks in flight at once and lose HBM efficiency.  Blocks under 3 KB are bound by
+    // per-case issue overhead instead and want two such CTAs per SM.
+    int S = env_int("WLSQM_SOLVE_STAGES", 2);
     S = std::max(1, std::min(S, 8));
-    int warps = env_int("WLSQM_SOLVE_WARPS", 8);
-    warps = std::max(1, std::min(warps, SOLVE_MAX_THREADS / 32));
+    const int max_warps = (iter ? SOLVE_MAX_THREADS_ITER : SOLVE_MAX_THREADS) / 32;
+    int warps = env_int("WLSQM_SOLVE_WARPS", 16);
+    warps = std::max(1, std::min(warps, max_warps));
     size_t per_warp = 0;
     int off_fi, off_r, wd;
     for (;;) {
@@ -207,7 +212,7 @@ int config_solve(const wlsqm_solver* s, SolveParams& P, LaunchCfg& L, long long 
     L.threads = warps * 32;
     L.smem = (size_t)P.bar_off_bytes + (size_t)warps * S * 8;
     int ctas = (int)(SMEM_PER_SM / (L.smem + 1024));
-    ctas = std::max(1, std::min(ctas, std::max(1, env_int("WLSQM_SOLVE_MAXWARPS_SM", 48) / warps)));
+    ctas = std::max(1, std::min(ctas, std::max(1, env_int("WLSQM_SOLVE_MAXWARPS_SM", stage_bytes >= 3072 ? 16 : 32) / warps)));
     long long need = (ncases_launch + warps - 1) / warps;
     L.blocks = (int)std::max<long long>(1, std::min<long long>((long long)s->sm_count * ctas, need));
     return WLSQM_OK;

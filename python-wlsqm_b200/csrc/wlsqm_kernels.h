@@ -6,7 +6,8 @@
 namespace wlsqm {
 
 constexpr int PREP_MAX_THREADS = 512;
-constexpr int SOLVE_MAX_THREADS = 512;
+constexpr int SOLVE_MAX_THREADS = 1024;       // ALGO_BASIC variants (<= 64 registers per thread)
+constexpr int SOLVE_MAX_THREADS_ITER = 512;   // ALGO_ITERATIVE variants carry the Taylor evaluator
 
 // All strides are in elements (doubles), all offsets into per-warp shared memory in doubles.
 struct PrepareParams {

@@ -39,50 +39,84 @@ __device__ __forceinline__ Groups make_groups(int nr, int lane) {
     return r;
 }
 
+// shared-memory load on a 32-bit shared address (explicit state space: one LDS, no generic addressing)
+__device__ __forceinline__ double lds_f64(uint32_t addr) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr) : "memory");
+    return v;
+}
+
 // out[j] = sum_q op[q*nr + j] * v[q], q < n, for one warp.  Group g takes the rows q = g, g+G, ... so that
-// one shared-memory wavefront reads G consecutive operator rows (conflict free); 4 independent FMA chains
-// per lane; a xor-butterfly over the groups leaves the total for reduced DOF j in every lane with
-// (lane & (W-1)) == j.  nr > 32 (3D order 4 with < 3 knowns): lanes also own row j + 32, returned in `hi`.
-__device__ __forceinline__ void warp_matvec(const double* __restrict__ op, const double* __restrict__ v, int n, int nr,
-                                            const Groups& gr, double& lo, double& hi) {
+// one shared-memory wavefront reads G consecutive operator rows (conflict free).  Batches of four rows:
+// eight loads are issued before the four independent FMA chains consume them.  A xor-butterfly over the
+// groups leaves the total for reduced DOF j in every lane with (lane & (W-1)) == j.
+// nr > 32 (3D order 4 with < 3 knowns): lanes also own row j + 32, returned in `hi`.
+// op_s / v_s are 32-bit shared-memory addresses.
+template <int LW>
+__device__ __forceinline__ void warp_matvec_t(uint32_t op_s, uint32_t v_s, int n, int nr, int lane, double& lo,
+                                              double& hi) {
+    constexpr int W = 1 << LW, G = 32 >> LW;
+    const int g = lane >> LW, j = lane & (W - 1);
     double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
     hi = 0.0;
-    if (gr.j < nr) {
-        const int G = gr.G, sp = G * nr;
-        const double* p = op + gr.g * nr + gr.j;
-        const double* vq = v + gr.g;
-        const double* p1 = p + sp;
-        const double* p2 = p1 + sp;
-        const double* p3 = p2 + sp;
-        int cnt = (n - gr.g + G - 1) >> (5 - gr.lw);      // rows of this group: ceil((n - g) / G)
-        int o = 0, ov = 0;
+    if (j < nr) {
+        const uint32_t sp = (uint32_t)(G * nr) * 8u, sp2 = 2u * sp, sp3 = 3u * sp;
+        uint32_t pa = op_s + (uint32_t)(g * nr + j) * 8u;
+        uint32_t va = v_s + (uint32_t)g * 8u;
+        int cnt = (n - g + G - 1) / G;      // rows of this group
         for (; cnt >= 4; cnt -= 4) {
-            a0 = fma(p[o], vq[ov], a0);
-            a1 = fma(p1[o], vq[ov + G], a1);
-            a2 = fma(p2[o], vq[ov + 2 * G], a2);
-            a3 = fma(p3[o], vq[ov + 3 * G], a3);
-            o += 4 * sp;
-            ov += 4 * G;
+            const double x0 = lds_f64(pa), x1 = lds_f64(pa + sp), x2 = lds_f64(pa + sp2), x3 = lds_f64(pa + sp3);
+            const double y0 = lds_f64(va), y1 = lds_f64(va + G * 8), y2 = lds_f64(va + 2 * G * 8),
+                         y3 = lds_f64(va + 3 * G * 8);
+            a0 = fma(x0, y0, a0);
+            a1 = fma(x1, y1, a1);
+            a2 = fma(x2, y2, a2);
+            a3 = fma(x3, y3, a3);
+            pa += 4u * sp;
+            va += 4 * G * 8;
         }
-        for (; cnt > 0; --cnt) {
-            a0 = fma(p[o], vq[ov], a0);
-            o += sp;
-            ov += G;
+        if (cnt >= 2) {
+            const double x0 = lds_f64(pa), x1 = lds_f64(pa + sp);
+            const double y0 = lds_f64(va), y1 = lds_f64(va + G * 8);
+            a0 = fma(x0, y0, a0);
+            a1 = fma(x1, y1, a1);
+            pa += sp2;
+            va += 2 * G * 8;
+            cnt -= 2;
         }
-        if (gr.j + 32 < nr) {   // only when W == 32, G == 1
-            const double* q2 = op + gr.j + 32;
+        if (cnt > 0) a2 = fma(lds_f64(pa), lds_f64(va), a2);
+        if (LW == 5 && j + 32 < nr) {
+            uint32_t qa = op_s + (uint32_t)(j + 32) * 8u, wa = v_s;
+            const uint32_t rs8 = (uint32_t)nr * 8u;
             double b0 = 0.0, b1 = 0.0;
-            int t = 0;
-            for (; t + 1 < n; t += 2) {
-                b0 = fma(q2[t * nr], v[t], b0);
-                b1 = fma(q2[(t + 1) * nr], v[t + 1], b1);
+            int t = n;
+            for (; t >= 2; t -= 2) {
+                const double x0 = lds_f64(qa), x1 = lds_f64(qa + rs8);
+                const double y0 = lds_f64(wa), y1 = lds_f64(wa + 8);
+                b0 = fma(x0, y0, b0);
+                b1 = fma(x1, y1, b1);
+                qa += 2u * rs8;
+                wa += 16;
             }
-            if (t < n) b0 = fma(q2[t * nr], v[t], b0);
+            if (t > 0) b0 = fma(lds_f64(qa), lds_f64(wa), b0);
             hi = b0 + b1;
         }
     }
     lo = (a0 + a1) + (a2 + a3);
-    for (int off = gr.W; off < 32; off <<= 1) lo += __shfl_xor_sync(0xffffffffu, lo, off);
+#pragma unroll
+    for (int off = W; off < 32; off <<= 1) lo += __shfl_xor_sync(0xffffffffu, lo, off);
+}
+
+__device__ __forceinline__ void warp_matvec(uint32_t op_s, uint32_t v_s, int n, int nr, const Groups& gr, int lane,
+                                            double& lo, double& hi) {
+    switch (gr.lw) {   // warp-uniform
+        case 0: warp_matvec_t<0>(op_s, v_s, n, nr, lane, lo, hi); break;
+        case 1: warp_matvec_t<1>(op_s, v_s, n, nr, lane, lo, hi); break;
+        case 2: warp_matvec_t<2>(op_s, v_s, n, nr, lane, lo, hi); break;
+        case 3: warp_matvec_t<3>(op_s, v_s, n, nr, lane, lo, hi); break;
+        case 4: warp_matvec_t<4>(op_s, v_s, n, nr, lane, lo, hi); break;
+        default: warp_matvec_t<5>(op_s, v_s, n, nr, lane, lo, hi); break;
+    }
 }
 
 // value of reduced DOF j for original slot o held by this lane (every lane must call it)
@@ -95,7 +129,7 @@ __device__ __forceinline__ double fetch_reduced(double lo, double hi, int j) {
 // UNI = the whole batch shares one CaseMeta (passed by value): everything derived from it is loop
 // invariant and hoisted by the compiler, which is what keeps the per-case instruction count low.
 template <int DIM, bool ITER, bool SENS, bool UNI>
-__global__ void __launch_bounds__(SOLVE_MAX_THREADS) solve_kernel(SolveParams P) {
+__global__ void __launch_bounds__(ITER ? SOLVE_MAX_THREADS_ITER : SOLVE_MAX_THREADS) solve_kernel(SolveParams P) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
@@ -106,6 +140,7 @@ __global__ void __launch_bounds__(SOLVE_MAX_THREADS) solve_kernel(SolveParams P)
     double* fis = wb + P.off_fi;            // current solution of the case (no values)
     double* rs = wb + P.off_r;              // ITER: residual at the neighbours
     const uint32_t ring_u32 = smem_u32(ring);
+    const uint32_t rs_u32 = smem_u32(rs);
     const uint32_t bars_u32 = smem_u32(smem_raw + P.bar_off_bytes) + (uint32_t)(warp * S) * 8u;
     const uint32_t stage_bytes = (uint32_t)P.stage_doubles * 8u;
 
@@ -171,6 +206,7 @@ __global__ void __launch_bounds__(SOLVE_MAX_THREADS) solve_kernel(SolveParams P)
         const int nk = mt.nk, no = mt.no, nr = mt.nr, nkn = mt.nkn, nq = nk + nkn;
         const long long knowns = mt.knowns;
         double* st = ring + (size_t)stage * P.stage_doubles;
+        const uint32_t st_u32 = ring_u32 + (uint32_t)stage * stage_bytes;
         const double* op = st;
         double* fext = st + P.off_f;
         const double* xks = st + P.off_xk;
@@ -212,7 +248,7 @@ __global__ void __launch_bounds__(SOLVE_MAX_THREADS) solve_kernel(SolveParams P)
         double v0 = g0, v1 = g1;     // known slots keep the caller's value
         if (nr > 0) {
             double lo, hi;
-            warp_matvec(op, fext, nq, nr, gr, lo, hi);
+            warp_matvec(st_u32, st_u32 + (uint32_t)P.off_f * 8u, nq, nr, gr, lane, lo, hi);
             const double t0 = fetch_reduced(lo, hi, j0);
             if (unk0) v0 = t0;
             if (no > 32) {
@@ -276,7 +312,7 @@ __global__ void __launch_bounds__(SOLVE_MAX_THREADS) solve_kernel(SolveParams P)
                 __syncwarp();
                 if (nr > 0) {
                     double lo, hi;
-                    warp_matvec(op, rs, nk, nr, gr, lo, hi);
+                    warp_matvec(st_u32, rs_u32, nk, nr, gr, lane, lo, hi);
                     const double t0 = fetch_reduced(lo, hi, j0);
                     if (unk0) { v0 += t0; fis[lane] = v0; }
                     if (no > 32) {
