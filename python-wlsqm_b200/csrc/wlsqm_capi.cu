@@ -102,7 +102,7 @@ __global__ void gather3_kernel(double* __restrict__ dst, const double* __restric
 struct wlsqm_solver {
     int dim = 0, device = 0, algorithm = 1, do_sens = 0, max_iter = 0, debug = 0;
     long long ncases = 0;
-    int maxnk = 0, maxno = 1, maxnr = 0, maxnq = 0;
+    int maxnk = 0, maxno = 1, maxnr = 0, maxnq = 0, maxorder = 0;
     bool uniform = true, any_knowns = false, uniform_no = true;
     CaseMeta uni{};
     long long op_stride = 0, op_total = 0;
@@ -165,6 +165,29 @@ int config_prepare(const wlsqm_solver* s, PrepareParams& P, LaunchCfg& L) {
     long long need = (s->ncases + warps - 1) / warps;
     L.blocks = (int)std::max<long long>(1, std::min<long long>((long long)s->sm_count * ctas, need));
     return WLSQM_OK;
+}
+
+// register/DMMA kernel: false if the fit does not fit its shared-memory carve-up (then the smem kernel runs)
+bool config_prepare_reg(const wlsqm_solver* s, PrepRegParams& P, LaunchCfg& L) {
+    const int nkp = (std::max(s->maxnk, 1) + 3) & ~3;
+    P.nb = (std::max(nkp, s->maxnq) + 31) / 32;
+    P.warp_doubles = prep_reg_warp_doubles(s->dim, s->maxorder, P.nb);
+    const size_t per_warp = (size_t)P.warp_doubles * 8;
+    int warps = PREP_REG_THREADS / 32;
+    while (warps > 1 && warps * per_warp > SMEM_PER_CTA) --warps;
+    if (warps * per_warp > SMEM_PER_CTA) return false;
+    L.threads = warps * 32;
+    L.smem = warps * per_warp;
+    int ctas = 1;
+    if (prepare_reg_occupancy(s->dim, s->maxorder, L.threads, L.smem, &ctas) != cudaSuccess || ctas < 1) {
+        cudaGetLastError();
+        return false;
+    }
+    const int cap = env_int("WLSQM_PREP_CTAS", 0);
+    if (cap > 0) ctas = std::min(ctas, cap);
+    long long need = (s->ncases + warps - 1) / warps;
+    L.blocks = (int)std::max<long long>(1, std::min<long long>((long long)s->sm_count * ctas, need));
+    return true;
 }
 
 int config_solve(const wlsqm_solver* s, SolveParams& P, LaunchCfg& L, long long ncases_launch) {
@@ -323,6 +346,7 @@ int wlsqm_solver_create(int dimension, int64_t ncases, const int32_t* nk, const 
         s->maxno = std::max(s->maxno, no);
         s->maxnr = std::max(s->maxnr, (int)m.nr);
         s->maxnq = std::max(s->maxnq, m.nk + m.nkn);
+        s->maxorder = std::max(s->maxorder, (int)m.order);
         if (m.knowns) s->any_knowns = true;
         if (i > 0) {
             const CaseMeta& f = s->hmeta[0];
@@ -461,15 +485,26 @@ int wlsqm_solver_prepare(wlsqm_solver_t* s, const double* xi, int64_t xi_s0, con
         s1 = dim;
     }
 
-    PrepareParams P{};
-    P.meta = s->dmeta; P.uni = s->uni; P.op_stride = s->op_stride; P.ncases = n;
-    P.xi = s->xi_dev; P.xi_s0 = dim;
-    P.xk = xk_use; P.xk_s0 = s0; P.xk_s1 = s1;
-    P.op = s->op; P.As = s->As; P.as_stride = s->as_stride;
     LaunchCfg L;
-    rc = config_prepare(s, P, L);
-    if (rc) return rc;
-    CU(launch_prepare(dim, P, L.blocks, L.threads, L.smem, s->stream));
+    PrepRegParams R{};
+    R.meta = s->dmeta; R.uni = s->uni; R.op_stride = s->op_stride; R.ncases = n;
+    R.xi = s->xi_dev; R.xi_s0 = dim;
+    R.xk = xk_use; R.xk_s0 = s0; R.xk_s1 = s1;
+    R.op = s->op; R.As = s->As; R.as_stride = s->as_stride;
+    const char* ksel = getenv("WLSQM_PREP_KERNEL");
+    const bool want_smem = ksel && !strcmp(ksel, "smem");
+    if (!want_smem && config_prepare_reg(s, R, L)) {
+        CU(launch_prepare_reg(dim, s->maxorder, R, L.blocks, L.threads, L.smem, s->stream));
+    } else {
+        PrepareParams P{};
+        P.meta = s->dmeta; P.uni = s->uni; P.op_stride = s->op_stride; P.ncases = n;
+        P.xi = s->xi_dev; P.xi_s0 = dim;
+        P.xk = xk_use; P.xk_s0 = s0; P.xk_s1 = s1;
+        P.op = s->op; P.As = s->As; P.as_stride = s->as_stride;
+        rc = config_prepare(s, P, L);
+        if (rc) return rc;
+        CU(launch_prepare_smem(dim, P, L.blocks, L.threads, L.smem, s->stream));
+    }
     if (!xk_dev) {
         // the call owns the host array only until it returns
         CU(cudaStreamSynchronize(s->stream));

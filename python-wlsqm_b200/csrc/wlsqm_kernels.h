@@ -5,7 +5,9 @@
 
 namespace wlsqm {
 
-constexpr int PREP_MAX_THREADS = 512;
+constexpr int PREP_MAX_THREADS = 512;        // shared-memory variant (wlsqm_prepare_smem.cu)
+constexpr int PREP_REG_THREADS = 128;        // register/DMMA variant (wlsqm_prepare.cu): 4 fits in flight per CTA
+constexpr int PREP_CB = 36;                  // row stride (doubles) inside a 32-column block of the monomial table
 constexpr int SOLVE_MAX_THREADS = 1024;       // ALGO_BASIC variants (<= 64 registers per thread)
 constexpr int SOLVE_MAX_THREADS_ITER = 512;   // ALGO_ITERATIVE variants carry the Taylor evaluator
 
@@ -20,6 +22,20 @@ struct PrepareParams {
     double* op;                                      // operator blocks (output)
     double* As; int as_stride;                       // debug: scaled matrices [ncases][as_stride] or nullptr
     int warp_doubles, off_w, off_a, off_rs, off_s, off_i;
+};
+
+// register/DMMA prepare kernel (wlsqm_prepare.cu)
+struct PrepRegParams {
+    const CaseMeta* meta;   // per-case records, or nullptr when the batch is uniform
+    CaseMeta uni;
+    long long op_stride;
+    long long ncases;
+    const double* xi; long long xi_s0;               // [ncases][dim]
+    const double* xk; long long xk_s0, xk_s1;        // [ncases][nk][dim], last axis contiguous
+    double* op;                                      // operator blocks (output)
+    double* As; int as_stride;                       // debug: scaled matrices [ncases][as_stride] or nullptr
+    int nb;                                          // 32-column blocks of the monomial table per warp
+    int warp_doubles;                                // shared-memory doubles per warp (prep_reg_warp_doubles)
 };
 
 struct SolveParams {
@@ -58,7 +74,11 @@ struct InterpParams {
     double* out; long long out_s0;                   // [nx] (diff >= 0) or [nx][out_s0]
 };
 
-cudaError_t launch_prepare(int dim, const PrepareParams& P, int blocks, int threads, size_t smem, cudaStream_t st);
+cudaError_t launch_prepare_smem(int dim, const PrepareParams& P, int blocks, int threads, size_t smem, cudaStream_t st);
+int prep_reg_warp_doubles(int dim, int maxorder, int nb);
+cudaError_t prepare_reg_occupancy(int dim, int maxorder, int threads, size_t smem, int* ctas_per_sm);
+cudaError_t launch_prepare_reg(int dim, int maxorder, const PrepRegParams& P, int blocks, int threads, size_t smem,
+                               cudaStream_t st);
 cudaError_t launch_solve(int dim, const SolveParams& P, int blocks, int threads, size_t smem, cudaStream_t st);
 cudaError_t launch_scatter_fi(const CaseMeta* meta, const CaseMeta& uni, long long ncases, const double* fi_case,
                               int fi_case_ld, double* fi_out, long long fi_out_s0, cudaStream_t st);
