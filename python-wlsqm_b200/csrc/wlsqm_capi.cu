@@ -102,7 +102,7 @@ __global__ void gather3_kernel(double* __restrict__ dst, const double* __restric
 struct wlsqm_solver {
     int dim = 0, device = 0, algorithm = 1, do_sens = 0, max_iter = 0, debug = 0;
     long long ncases = 0;
-    int maxnk = 0, maxno = 1, maxnr = 0, maxnq = 0, maxorder = 0;
+    int maxnk = 0, maxno = 1, maxnr = 0, maxnq = 0, maxorder = 0, maxnkn = 0;
     bool uniform = true, any_knowns = false, uniform_no = true;
     CaseMeta uni{};
     long long op_stride = 0, op_total = 0;
@@ -171,7 +171,10 @@ int config_prepare(const wlsqm_solver* s, PrepareParams& P, LaunchCfg& L) {
 bool config_prepare_reg(const wlsqm_solver* s, PrepRegParams& P, LaunchCfg& L) {
     const int nkp = (std::max(s->maxnk, 1) + 3) & ~3;
     P.nb = (std::max(nkp, s->maxnq) + 31) / 32;
-    P.warp_doubles = prep_reg_warp_doubles(s->dim, s->maxorder, P.nb);
+    const int nkn_max = s->maxnq > 0 ? s->maxnkn : 0;
+    P.fit_doubles = prep_reg_fit_doubles(s->dim, s->maxorder, P.nb, nkn_max);
+    P.warp_doubles = prep_reg_warp_doubles(s->dim, s->maxorder, P.nb, nkn_max);
+    const int fpw = prep_reg_fits_per_warp(s->dim, s->maxorder);
     const size_t per_warp = (size_t)P.warp_doubles * 8;
     int warps = PREP_REG_THREADS / 32;
     while (warps > 1 && warps * per_warp > SMEM_PER_CTA) --warps;
@@ -185,7 +188,7 @@ bool config_prepare_reg(const wlsqm_solver* s, PrepRegParams& P, LaunchCfg& L) {
     }
     const int cap = env_int("WLSQM_PREP_CTAS", 0);
     if (cap > 0) ctas = std::min(ctas, cap);
-    long long need = (s->ncases + warps - 1) / warps;
+    long long need = (s->ncases + (long long)warps * fpw - 1) / ((long long)warps * fpw);
     L.blocks = (int)std::max<long long>(1, std::min<long long>((long long)s->sm_count * ctas, need));
     return true;
 }
@@ -347,6 +350,7 @@ int wlsqm_solver_create(int dimension, int64_t ncases, const int32_t* nk, const 
         s->maxnr = std::max(s->maxnr, (int)m.nr);
         s->maxnq = std::max(s->maxnq, m.nk + m.nkn);
         s->maxorder = std::max(s->maxorder, (int)m.order);
+        s->maxnkn = std::max(s->maxnkn, (int)m.nkn);
         if (m.knowns) s->any_knowns = true;
         if (i > 0) {
             const CaseMeta& f = s->hmeta[0];

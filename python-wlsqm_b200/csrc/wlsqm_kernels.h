@@ -34,8 +34,9 @@ struct PrepRegParams {
     const double* xk; long long xk_s0, xk_s1;        // [ncases][nk][dim], last axis contiguous
     double* op;                                      // operator blocks (output)
     double* As; int as_stride;                       // debug: scaled matrices [ncases][as_stride] or nullptr
-    int nb;                                          // 32-column blocks of the monomial table per warp
-    int warp_doubles;                                // shared-memory doubles per warp (prep_reg_warp_doubles)
+    int nb;                                          // 32-column blocks of the monomial table
+    int fit_doubles;                                 // shared-memory doubles per fit region (prep_reg_fit_doubles)
+    int warp_doubles;                                // per warp: monomial table + prep_reg_fits_per_warp() fit regions
 };
 
 struct SolveParams {
@@ -75,7 +76,9 @@ struct InterpParams {
 };
 
 cudaError_t launch_prepare_smem(int dim, const PrepareParams& P, int blocks, int threads, size_t smem, cudaStream_t st);
-int prep_reg_warp_doubles(int dim, int maxorder, int nb);
+int prep_reg_fit_doubles(int dim, int maxorder, int nb, int nkn_max);
+int prep_reg_warp_doubles(int dim, int maxorder, int nb, int nkn_max);
+int prep_reg_fits_per_warp(int dim, int maxorder);
 cudaError_t prepare_reg_occupancy(int dim, int maxorder, int threads, size_t smem, int* ctas_per_sm);
 cudaError_t launch_prepare_reg(int dim, int maxorder, const PrepRegParams& P, int blocks, int threads, size_t smem,
                                cudaStream_t st);

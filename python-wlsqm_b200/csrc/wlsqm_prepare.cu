@@ -42,6 +42,8 @@ struct PK {
     static constexpr int NOP = (NO + 7) & ~7;       // Gram tiles of 8 slots
     static constexpr int NRP = (NO + 3) & ~3;       // padded row length held in registers
     static constexpr int RPL = NRP > 32 ? 2 : 1;    // matrix rows per lane
+    static constexpr int LPF = NRP <= 8 ? 8 : (NRP <= 16 ? 16 : 32);   // lanes per fit in the row phases (P3, P4)
+    static constexpr int FPW = 32 / LPF;            // fits a warp carries through the row phases together
     static constexpr int T = NOP / 8;
     static constexpr int LDA = NOP + 2;             // row stride of G / LU: LDS.128 by lane = row is conflict free
     static constexpr int BLK = NOP * PREP_CB;       // doubles per 32-column block of CT
@@ -51,9 +53,23 @@ __host__ __device__ constexpr int prep_no(int dim, int ord) {
     return dim == 1 ? ord + 1 : (dim == 2 ? (ord + 1) * (ord + 2) / 2 : (ord + 1) * (ord + 2) * (ord + 3) / 6);
 }
 
-int prep_reg_warp_doubles(int dim, int maxorder, int nb) {
+int prep_reg_fits_per_warp(int dim, int maxorder) {
+    const int nrp = (prep_no(dim, maxorder) + 3) & ~3;
+    return nrp <= 8 ? 4 : (nrp <= 16 ? 2 : 1);
+}
+
+// shared-memory doubles that stay with ONE fit from the Gram phase to the operator store:
+//   G [NOP][NOP+2] | W [nb*32] | RS [NRP] | DINV [NRP] | REC [NRP x 2] | R2O [NOP ints] | KN [nkn_max][NOP]
+int prep_reg_fit_doubles(int dim, int maxorder, int nb, int nkn_max) {
+    const int no = prep_no(dim, maxorder), nop = (no + 7) & ~7, nrp = (no + 3) & ~3;
+    const int d = nop * (nop + 2) + nb * 32 + 4 * nrp + nop / 2 + nkn_max * nop;
+    return (d + 1) & ~1;
+}
+// per warp: the monomial table CT [nb][NOP][PREP_CB] (transient: Gram phase, then right-hand-side gather and
+// operator staging) followed by prep_reg_fits_per_warp() fit regions
+int prep_reg_warp_doubles(int dim, int maxorder, int nb, int nkn_max) {
     const int nop = (prep_no(dim, maxorder) + 7) & ~7;
-    const int d = nb * nop * PREP_CB + nop * (nop + 2) + nb * 32 + 40 + 40 + 80 + 20;
+    const int d = nb * nop * PREP_CB + prep_reg_fits_per_warp(dim, maxorder) * prep_reg_fit_doubles(dim, maxorder, nb, nkn_max);
     return (d + 15) & ~15;
 }
 
@@ -63,161 +79,236 @@ __device__ __forceinline__ void dmma884(double (&d)[2], double a, double b) {
         : "d"(a), "d"(b));
 }
 
+// max of two non-negative, non-NaN doubles: one DSETP + two selects (fmax() costs ~8 instructions for its NaN rules)
+__device__ __forceinline__ double max_nn(double a, double b) { return b > a ? b : a; }
+
 __device__ __forceinline__ double2 ld2(const double* p) { return *reinterpret_cast<const double2*>(p); }
 __device__ __forceinline__ void st2(double* p, double x, double y) { *reinterpret_cast<double2*>(p) = make_double2(x, y); }
+
+// max / min over the LPF consecutive lanes of this lane's group (grp = lane / LPF): one warp-wide REDUX per
+// group (they are independent, so their latencies overlap) instead of a dependent shuffle butterfly
+template <int LPF>
+__device__ __forceinline__ unsigned group_max(unsigned v, int grp) {
+    if constexpr (LPF == 32) return __reduce_max_sync(0xffffffffu, v);
+    unsigned r = 0u;
+#pragma unroll
+    for (int g = 0; g < 32 / LPF; ++g) {
+        const unsigned m = __reduce_max_sync(0xffffffffu, grp == g ? v : 0u);
+        if (grp == g) r = m;
+    }
+    return r;
+}
+template <int LPF>
+__device__ __forceinline__ unsigned group_min(unsigned v, int grp) {
+    if constexpr (LPF == 32) return __reduce_min_sync(0xffffffffu, v);
+    unsigned r = 0u;
+#pragma unroll
+    for (int g = 0; g < 32 / LPF; ++g) {
+        const unsigned m = __reduce_min_sync(0xffffffffu, grp == g ? v : 0xffffffffu);
+        if (grp == g) r = m;
+    }
+    return r;
+}
 
 template <int DIM, int ORD>
 __global__ void __launch_bounds__(PREP_REG_THREADS) prepare_reg_kernel(PrepRegParams P) {
     using K = PK<DIM, ORD>;
     constexpr int NOP = K::NOP, NRP = K::NRP, RPL = K::RPL, T = K::T, LDA = K::LDA, CB = PREP_CB, BLK = K::BLK;
+    constexpr int LPF = K::LPF, FPW = K::FPW;
     constexpr unsigned FULL = 0xffffffffu;
+    constexpr unsigned GMASK = LPF == 32 ? 0xffffffffu : ((1u << (LPF & 31)) - 1u);
     extern __shared__ __align__(128) double smem[];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int nwarps = blockDim.x >> 5;
-    double* wb = smem + (size_t)warp * P.warp_doubles;
-    double* CT = wb;                                  // [nb][NOP][CB]  monomials (transposed), later the staged operator
-    double* G = CT + P.nb * BLK;                      // [NOP][LDA]     Gram matrix, later the LU factors (pivot order)
-    double* W = G + NOP * LDA;                        // [nb*32]        weights of the right-hand-side columns
-    double* RS = W + P.nb * 32;                       // [40]           row (= column) scale, natural order
-    double* DINV = RS + 40;                           // [40]           reciprocal pivots
-    double2* REC = reinterpret_cast<double2*>(DINV + 40);   // [40]     pivot order: {row scale, CT row offset}
-    int* R2O = reinterpret_cast<int*>(DINV + 40 + 80);      // [40]     reduced -> original slot, then the known slots
+    double* CT = smem + (size_t)warp * P.warp_doubles;   // [nb][NOP][CB] monomials (transposed); P5: gather + staging
+    double* fits = CT + P.nb * BLK;
+    // carve-up of one fit's region (offsets in doubles)
+    constexpr int oG = 0;                      // [NOP][LDA]  Gram matrix, later the LU factors (pivot order)
+    constexpr int oW = oG + NOP * LDA;         // [nb*32]     weights of the right-hand-side columns
+    const int oRS = oW + P.nb * 32;            // [NRP]       row (= column) scale, natural order
+    const int oDINV = oRS + NRP;               // [NRP]       reciprocal pivots (Ruiz: second scale buffer)
+    const int oREC = oDINV + NRP;              // [NRP] x 16 B pivot order: {row scale, CT row offset}
+    const int oR2O = oREC + 2 * NRP;           // [NOP] ints  reduced -> original slot, then the known slots
+    const int oKN = oR2O + NOP / 2;            // [nkn_max][NOP] knowns right-hand sides -A[:, known]
+    // row phases: this lane's fit (group) and row inside it
+    const int grp = lane / LPF, jl = lane % LPF;
+    double* gb = fits + grp * P.fit_doubles;
+    double* gG = gb + oG;
+    double* gRS = gb + oRS;
+    double* gDINV = gb + oDINV;
+    double2* gREC = reinterpret_cast<double2*>(gb + oREC);
+    const int* gR2O = reinterpret_cast<const int*>(gb + oR2O);
 
-    const long long gw = (long long)blockIdx.x * nwarps + warp;
-    const long long GW = (long long)gridDim.x * nwarps;
-
-    for (long long c = gw; c < P.ncases; c += GW) {
-        CaseMeta mt;
+    auto get_meta = [&](long long c) {
+        CaseMeta m;
         if (P.meta) {
-            mt = P.meta[c];
+            m = P.meta[c];
         } else {
-            mt = P.uni;
-            mt.op_off = c * P.op_stride;
+            m = P.uni;
+            m.op_off = c * P.op_stride;
         }
-        const int nk = mt.nk, no = mt.no, nr = mt.nr, nkn = mt.nkn, nq = nk + nkn;
-        const long long knowns = mt.knowns;
-        if (nr < 1) continue;   // everything known: silent no-op (impl.pyx:574,636,742)
-        const int nkp = (nk + 3) & ~3;
-        const int nblk = (max(nkp, nq) + 31) >> 5;
-
-        // the previous fit's bulk stores read this warp's CT blocks
-        if (lane == 0) tma_store_wait_read();
-        __syncwarp();
-
-        // ---- P1. monomials and squared distances (lane = neighbour) ----------------------------
-        double xi0 = P.xi[c * P.xi_s0], xi1 = 0.0, xi2 = 0.0;
-        if (DIM >= 2) xi1 = P.xi[c * P.xi_s0 + 1];
-        if (DIM >= 3) xi2 = P.xi[c * P.xi_s0 + 2];
-        double max_d2 = 0.0;
-        for (int b = 0; b < nblk; ++b) {
-            const int k = b * 32 + lane;
-            const bool in = k < nk;
-            double dx = 0.0, dy = 0.0, dz = 0.0;
-            if (in) {
-                const double* xp = P.xk + c * P.xk_s0 + (long long)k * P.xk_s1;
-                dx = xp[0] - xi0;
-                if (DIM >= 2) dy = xp[1] - xi1;
-                if (DIM >= 3) dz = xp[2] - xi2;
+        return m;
+    };
+    // monomials of neighbour k of case c into column `lane` of one CT block; returns d^2 (0 outside the hood)
+    auto monomial_column = [&](long long c, int k, int nk, int no, double* ctb) -> double {
+        const bool in = k < nk;
+        double dx = 0.0, dy = 0.0, dz = 0.0;
+        if (in) {
+            const double* xp = P.xk + c * P.xk_s0 + (long long)k * P.xk_s1;
+            const double* xo = P.xi + c * P.xi_s0;
+            dx = xp[0] - xo[0];
+            if (DIM >= 2) dy = xp[DIM >= 2 ? 1 : 0] - xo[DIM >= 2 ? 1 : 0];
+            if (DIM >= 3) dz = xp[DIM >= 3 ? 2 : 0] - xo[DIM >= 3 ? 2 : 0];
+        }
+        double d2 = dx * dx;
+        if (DIM >= 2) d2 += dy * dy;
+        if (DIM >= 3) d2 += dz * dz;
+        const Pow5 px = scaled_powers(dx), py = scaled_powers(dy), pz = scaled_powers(dz);
+        static_for<0, NOP>([&](auto I) {
+            constexpr int s = decltype(I)::value;
+            double v = 0.0;
+            if constexpr (s < K::NO) {
+                if (in && s < no) v = monomial<DIM, s>(px, py, pz);
             }
-            double d2 = dx * dx;
-            if (DIM >= 2) d2 += dy * dy;
-            if (DIM >= 3) d2 += dz * dz;
-            max_d2 = fmax(max_d2, d2);
-            W[k] = d2;
-            const Pow5 px = scaled_powers(dx), py = scaled_powers(dy), pz = scaled_powers(dz);
-            double* ctb = CT + b * BLK + lane;
-            static_for<0, NOP>([&](auto I) {
-                constexpr int s = decltype(I)::value;
-                double v = 0.0;
-                if constexpr (s < K::NO) {
-                    if (in && s < no) v = monomial<DIM, s>(px, py, pz);
-                }
-                ctb[s * CB] = v;
-            });
+            ctb[s * CB] = v;
+        });
+        return d2;
+    };
+
+    const long long w0 = ((long long)blockIdx.x * nwarps + warp) * FPW;
+    const long long WS = (long long)gridDim.x * nwarps * FPW;
+    bool pending = false;    // a bulk store may still be reading CT
+
+    for (long long c0 = w0; c0 < P.ncases; c0 += WS) {
+        if (pending) {
+            if (lane == 0) tma_store_wait_read();
+            __syncwarp();
+            pending = false;
         }
-        max_d2 = warp_max(max_d2);
-        // ---- weights (infra.pyx:679-702); columns >= nk carry weight 0 through the Gram phase ----
-        for (int b = 0; b < nblk; ++b) {
-            const int k = b * 32 + lane;
-            double w = 0.0;
-            if (k < nk) {
-                w = 1.0;
-                if (mt.wm == WLSQM_WEIGHT_CENTER) {
-                    const double t = 1.0 - sqrt(W[k] / max_d2);
-                    w = 1e-4 + (1.0 - 1e-4) * (t * t);
+
+        // ================= per fit, whole warp: P1 monomials + weights, P2 Gram matrix =================
+#pragma unroll 1
+        for (int f = 0; f < FPW; ++f) {
+            const long long c = c0 + f;
+            if (c >= P.ncases) break;
+            const CaseMeta mt = get_meta(c);
+            const int nk = mt.nk, no = mt.no, nr = mt.nr, nkn = mt.nkn, nq = nk + nkn;
+            const long long knowns = mt.knowns;
+            if (nr < 1) continue;   // everything known: silent no-op (impl.pyx:574,636,742)
+            const int nkp = (nk + 3) & ~3;
+            const int nblk = (max(nkp, nq) + 31) >> 5;
+            double* fb = fits + f * P.fit_doubles;
+            double* G = fb + oG;
+            double* W = fb + oW;
+            int* R2O = reinterpret_cast<int*>(fb + oR2O);
+
+            // ---- P1. monomials and squared distances (lane = neighbour) ----------------------------
+            double max_d2 = 0.0;
+            for (int b = 0; b < nblk; ++b) {
+                const int k = b * 32 + lane;
+                const double d2 = monomial_column(c, k, nk, no, CT + b * BLK + lane);
+                max_d2 = max_nn(max_d2, d2);
+                W[k] = d2;
+            }
+            // ---- weights (infra.pyx:679-702); columns >= nk carry weight 0 through the Gram phase ----
+            if (mt.wm == WLSQM_WEIGHT_CENTER) {
+                max_d2 = warp_max(max_d2);
+                for (int b = 0; b < nblk; ++b) {
+                    const int k = b * 32 + lane;
+                    double w = 0.0;
+                    if (k < nk) {
+                        const double t = 1.0 - sqrt(W[k] / max_d2);
+                        w = 1e-4 + (1.0 - 1e-4) * (t * t);
+                    }
+                    W[k] = w;
+                }
+            } else {
+                for (int b = 0; b < nblk; ++b) {
+                    const int k = b * 32 + lane;
+                    W[k] = k < nk ? 1.0 : 0.0;
                 }
             }
-            W[k] = w;
-        }
-        for (int o = lane; o < no; o += 32) {
-            const long long below = knowns & ((1LL << o) - 1);
-            if (!((knowns >> o) & 1LL)) R2O[o - __popcll(below)] = o;        // unknown: reduced index
-            else R2O[nr + __popcll(below)] = o;                              // known slots, ascending, after the unknowns
-        }
-        __syncwarp();
+            for (int o = lane; o < no; o += 32) {
+                const long long below = knowns & ((1LL << o) - 1);
+                if (!((knowns >> o) & 1LL)) R2O[o - __popcll(below)] = o;        // unknown: reduced index
+                else R2O[nr + __popcll(below)] = o;                              // known slots, ascending, after the unknowns
+            }
+            __syncwarp();
 
-        // ---- P2. G = C^T W C on the FP64 tensor cores --------------------------------------------
-        {
-            double acc[T * (T + 1) / 2][2];
+            // ---- P2. G = C^T W C on the FP64 tensor cores ----------------------------------------
+            {
+                double acc[T * (T + 1) / 2][2];
 #pragma unroll
-            for (int t = 0; t < T * (T + 1) / 2; ++t) acc[t][0] = acc[t][1] = 0.0;
-            const int kk = lane & 3, jj = lane >> 2;
-            for (int k0 = 0; k0 < nkp; k0 += 4) {
-                const int k = k0 + kk;
-                const double* ctk = CT + (k >> 5) * BLK + (k & 31) + jj * CB;
-                const double w = W[k];
-                double cf[T], wf[T];
+                for (int t = 0; t < T * (T + 1) / 2; ++t) acc[t][0] = acc[t][1] = 0.0;
+                const int kk = lane & 3, jj = lane >> 2;
+                for (int k0 = 0; k0 < nkp; k0 += 4) {
+                    const int k = k0 + kk;
+                    const double* ctk = CT + (k >> 5) * BLK + (k & 31) + jj * CB;
+                    const double w = W[k];
+                    double cf[T], wf[T];
 #pragma unroll
-                for (int t = 0; t < T; ++t) {
-                    cf[t] = ctk[8 * t * CB];
-                    wf[t] = w * cf[t];
+                    for (int t = 0; t < T; ++t) {
+                        cf[t] = ctk[8 * t * CB];
+                        wf[t] = w * cf[t];
+                    }
+#pragma unroll
+                    for (int tj = 0; tj < T; ++tj)
+#pragma unroll
+                        for (int tm = 0; tm <= tj; ++tm) dmma884(acc[tj * (tj + 1) / 2 + tm], cf[tj], wf[tm]);
                 }
+                // lower triangle, mirrored (make_A computes (w c_m) c_j for the full square; the mirror makes
+                // the matrix exactly symmetric, which the single-pass Ruiz sweep below relies on)
 #pragma unroll
                 for (int tj = 0; tj < T; ++tj)
 #pragma unroll
-                    for (int tm = 0; tm <= tj; ++tm) dmma884(acc[tj * (tj + 1) / 2 + tm], cf[tj], wf[tm]);
-            }
-            // lower triangle, mirrored (make_A computes (w c_m) c_j for the full square; the mirror makes
-            // the matrix exactly symmetric, which the single-pass Ruiz sweep below relies on)
+                    for (int tm = 0; tm <= tj; ++tm)
 #pragma unroll
-            for (int tj = 0; tj < T; ++tj)
-#pragma unroll
-                for (int tm = 0; tm <= tj; ++tm)
-#pragma unroll
-                    for (int e = 0; e < 2; ++e) {
-                        const int row = 8 * tj + jj, col = 8 * tm + 2 * kk + e;
-                        const double v = acc[tj * (tj + 1) / 2 + tm][e];
-                        if (row >= col) {
-                            G[row * LDA + col] = v;
-                            G[col * LDA + row] = v;
+                        for (int e = 0; e < 2; ++e) {
+                            const int row = 8 * tj + jj, col = 8 * tm + 2 * kk + e;
+                            const double v = acc[tj * (tj + 1) / 2 + tm][e];
+                            if (row >= col) {
+                                G[row * LDA + col] = v;
+                                G[col * LDA + row] = v;
+                            }
                         }
-                    }
-        }
-        __syncwarp();
-        // knowns elimination columns: right-hand sides -A[oj, known om] (impl.pyx:792-818), weight 1
-        if (nkn) {
-            for (int t = lane; t < no * nkn; t += 32) {
-                const int s = t % no, mk = t / no;
-                const int q = nk + mk;
-                CT[(q >> 5) * BLK + s * CB + (q & 31)] = -G[s * LDA + R2O[nr + mk]];
             }
-            if (lane < nkn) W[nk + lane] = 1.0;
             __syncwarp();
+            // knowns elimination: right-hand sides -A[oj, known om] (impl.pyx:792-818), weight 1
+            if (nkn) {
+                double* KN = fb + oKN;
+                for (int t = lane; t < no * nkn; t += 32) {
+                    const int s = t % no, mk = t / no;
+                    KN[mk * NOP + s] = -G[s * LDA + R2O[nr + mk]];
+                }
+                if (lane < nkn) W[nk + lane] = 1.0;
+                __syncwarp();
+            }
         }
 
+        // ================= row phases: LPF lanes per fit, FPW fits side by side ========================
         // ---- P3. reduced matrix rows -> registers; Ruiz equilibration ------------------------------
+        const long long cg = c0 + grp;
+        int nr = 0;
+        long long knowns = 0;
+        if (cg < P.ncases) {
+            const CaseMeta mg = get_meta(cg);
+            nr = mg.nr;
+            knowns = mg.knowns;
+        }
+        const int nrmax = FPW == 1 ? nr : (int)__reduce_max_sync(FULL, (unsigned)nr);
+        if (nrmax < 1) continue;
         double a[RPL][NRP];
         double rj[RPL];
         int roff[RPL];
 #pragma unroll
         for (int t = 0; t < RPL; ++t) {
-            const int j = lane + 32 * t;
+            const int j = jl + 32 * t;
             const bool valid = j < nr;
-            const int oj = valid ? R2O[j] : 0;
+            const int oj = valid ? gR2O[j] : 0;
             roff[t] = oj * CB;
             rj[t] = 1.0;
-            const double* g = G + oj * LDA;
+            const double* g = gG + oj * LDA;
             if (knowns == 0) {
 #pragma unroll
                 for (int m = 0; m < NRP; m += 2) {
@@ -228,59 +319,78 @@ __global__ void __launch_bounds__(PREP_REG_THREADS) prepare_reg_kernel(PrepRegPa
             } else {
 #pragma unroll
                 for (int m = 0; m < NRP; ++m) {
-                    const int om = m < nr ? R2O[m] : 0;
+                    const int om = m < nr ? gR2O[m] : 0;
                     const double v = g[om];
                     a[t][m] = (valid && m < nr) ? v : 0.0;
                 }
             }
         }
-        for (int i = lane; i < 40; i += 32) RS[i] = 1.0;
-        __syncwarp();
         // A is exactly symmetric, so the reference's row and column passes coincide (DR == DC); the running
-        // reciprocal products row_j = 1/DRp_j are kept instead of dividing every entry.
-        for (int it = 0; it < 100; ++it) {
-            double mx[RPL];
+        // reciprocal products row_j = 1/DRp_j are kept instead of dividing every entry.  The scale vector is
+        // double buffered (RS / DINV, which is free until the LU) so that a sweep needs one warp barrier.
+        // A fit that has converged stops updating while its warp-mates finish.
+        for (int i = jl; i < NRP; i += LPF) gRS[i] = gDINV[i] = 1.0;
+        __syncwarp();
+        {
+            bool done = nr < 1;
+            double* rs_cur = gRS;
+            double* rs_nxt = gDINV;
+            for (int it = 0; it < 100; ++it) {
+                double mx[RPL][4];
 #pragma unroll
-            for (int t = 0; t < RPL; ++t) mx[t] = 0.0;
+                for (int t = 0; t < RPL; ++t) mx[t][0] = mx[t][1] = mx[t][2] = mx[t][3] = 0.0;
 #pragma unroll
-            for (int m = 0; m < NRP; m += 2) {
-                const double2 r2 = ld2(RS + m);
+                for (int m = 0; m < NRP; m += 4) {
+                    const double2 r2 = ld2(rs_cur + m), r3 = ld2(rs_cur + m + 2);
+#pragma unroll
+                    for (int t = 0; t < RPL; ++t) {
+                        mx[t][0] = max_nn(mx[t][0], fabs(a[t][m]) * r2.x);
+                        mx[t][1] = max_nn(mx[t][1], fabs(a[t][m + 1]) * r2.y);
+                        mx[t][2] = max_nn(mx[t][2], fabs(a[t][m + 2]) * r3.x);
+                        mx[t][3] = max_nn(mx[t][3], fabs(a[t][m + 3]) * r3.y);
+                    }
+                }
+                bool conv = true;
 #pragma unroll
                 for (int t = 0; t < RPL; ++t) {
-                    mx[t] = fmax(mx[t], fabs(a[t][m]) * r2.x);
-                    mx[t] = fmax(mx[t], fabs(a[t][m + 1]) * r2.y);
+                    const int j = jl + 32 * t;
+                    if (j < nr) {
+                        if (!done) {
+                            // = DR_j^2, the scaled inf-norm of row j
+                            const double m2 = max_nn(max_nn(mx[t][0], mx[t][1]), max_nn(mx[t][2], mx[t][3])) * rj[t];
+                            conv = conv && (fabs(1.0 - m2) < 1e-15);
+                            rj[t] *= rsqrt(m2);
+                        }
+                        rs_nxt[j] = rj[t];
+                    }
                 }
+                const unsigned cb = __ballot_sync(FULL, conv);
+                done = done || (((cb >> (grp * LPF)) & GMASK) == GMASK);
+                __syncwarp();
+                double* tmp = rs_cur; rs_cur = rs_nxt; rs_nxt = tmp;
+                if (__all_sync(FULL, done)) break;
             }
-            __syncwarp();
-            bool conv = true;
+            // the final scale vector lives in RS (P5 reads it there)
 #pragma unroll
-            for (int t = 0; t < RPL; ++t) {
-                const int j = lane + 32 * t;
-                if (j < nr) {
-                    const double m2 = mx[t] * rj[t];            // = DR_j^2, the scaled inf-norm of row j
-                    conv = conv && (fabs(1.0 - m2) < 1e-15);
-                    rj[t] *= rsqrt(m2);
-                    RS[j] = rj[t];
-                }
-            }
+            for (int t = 0; t < RPL; ++t)
+                if (jl + 32 * t < nr) gRS[jl + 32 * t] = rj[t];
             __syncwarp();
-            if (__all_sync(FULL, conv)) break;
         }
         // ---- A <- diag(row) A diag(col)  (lapackdrivers.pyx:293-299) -----------------------------
 #pragma unroll
         for (int m = 0; m < NRP; m += 2) {
-            const double2 r2 = ld2(RS + m);
+            const double2 r2 = ld2(gRS + m);
 #pragma unroll
             for (int t = 0; t < RPL; ++t) {
                 a[t][m] *= rj[t] * r2.x;
                 a[t][m + 1] *= rj[t] * r2.y;
             }
         }
-        if (P.As) {   // debug=True: keep the scaled matrix for conds() (impl.pyx:662-682)
-            double* as = P.As + c * (long long)P.as_stride;
+        if (P.As && nr > 0) {   // debug=True: keep the scaled matrix for conds() (impl.pyx:662-682)
+            double* as = P.As + cg * (long long)P.as_stride;
 #pragma unroll
             for (int t = 0; t < RPL; ++t) {
-                const int j = lane + 32 * t;
+                const int j = jl + 32 * t;
 #pragma unroll
                 for (int m = 0; m < NRP; ++m)
                     if (j < nr && m < nr) as[j + nr * m] = a[t][m];
@@ -292,122 +402,200 @@ __global__ void __launch_bounds__(PREP_REG_THREADS) prepare_reg_kernel(PrepRegPa
         int pos[RPL];
 #pragma unroll
         for (int t = 0; t < RPL; ++t) {
-            pos[t] = lane + 32 * t;
+            pos[t] = jl + 32 * t;
             act[t] = pos[t] < nr;
         }
 #pragma unroll
         for (int p = 0; p < NRP; ++p) {
-            if (p < nr) {
-                // this lane's candidate: largest |a[.][p]| among its active rows, first in row order on ties
-                unsigned khi = 0u, klo = 0u;
-                int kpos = 0xffff, kt = 0;
-                bool any = false;
+            if (p < nrmax) {
+                // pivot = largest |a[.][p]| among the active rows, first in current row order on ties (idamax)
+                bool piv[RPL];
+                bool has_piv;
+                unsigned ppos;
+                if constexpr (RPL == 1) {
+                    const unsigned long long bits = (unsigned long long)__double_as_longlong(fabs(a[0][p]));
+                    const unsigned khi = (unsigned)(bits >> 32), klo = (unsigned)bits;
+                    const unsigned hi = group_max<LPF>(act[0] ? khi : 0u, grp);
+                    const bool c1 = act[0] && khi == hi;
+                    unsigned cand = (__ballot_sync(FULL, c1) >> (grp * LPF)) & GMASK;
+                    if (__any_sync(FULL, __popc(cand) > 1)) {   // rare: rows share the leading 32 bits -> exact comparison
+                        const unsigned lo = group_max<LPF>(c1 ? klo : 0u, grp);
+                        const bool c2 = c1 && klo == lo;
+                        const unsigned best = group_min<LPF>(c2 ? (unsigned)pos[0] : 0xffffu, grp);
+                        cand = (__ballot_sync(FULL, c2 && (unsigned)pos[0] == best) >> (grp * LPF)) & GMASK;
+                    }
+                    has_piv = cand != 0u;
+                    const int pl = grp * LPF + (has_piv ? __ffs(cand) - 1 : 0);
+                    ppos = (unsigned)__shfl_sync(FULL, pos[0], pl);
+                    piv[0] = has_piv && lane == pl;
+                } else {
+                    unsigned khi = 0u, klo = 0u;
+                    int kpos = 0xffff, kt = 0;
+                    bool any = false;
 #pragma unroll
-                for (int t = 0; t < RPL; ++t) {
-                    const unsigned long long bits = (unsigned long long)__double_as_longlong(fabs(a[t][p]));
-                    const unsigned hi_t = (unsigned)(bits >> 32), lo_t = (unsigned)bits;
-                    const bool better = act[t] && (!any || hi_t > khi || (hi_t == khi && (lo_t > klo || (lo_t == klo && pos[t] < kpos))));
-                    if (better) { khi = hi_t; klo = lo_t; kpos = pos[t]; kt = t; any = true; }
+                    for (int t = 0; t < RPL; ++t) {
+                        const unsigned long long bits = (unsigned long long)__double_as_longlong(fabs(a[t][p]));
+                        const unsigned hi_t = (unsigned)(bits >> 32), lo_t = (unsigned)bits;
+                        const bool better = act[t] && (!any || hi_t > khi || (hi_t == khi && (lo_t > klo || (lo_t == klo && pos[t] < kpos))));
+                        if (better) { khi = hi_t; klo = lo_t; kpos = pos[t]; kt = t; any = true; }
+                    }
+                    const unsigned hi = __reduce_max_sync(FULL, any ? khi : 0u);
+                    const bool c1 = any && khi == hi;
+                    const unsigned lo = __reduce_max_sync(FULL, c1 ? klo : 0u);
+                    const bool c2 = c1 && klo == lo;
+                    ppos = __reduce_min_sync(FULL, c2 ? (unsigned)kpos : 0xffffu);
+                    has_piv = true;
+#pragma unroll
+                    for (int t = 0; t < RPL; ++t) piv[t] = c2 && kt == t && (unsigned)pos[t] == ppos && act[t];
                 }
-                const unsigned hi = __reduce_max_sync(FULL, any ? khi : 0u);
-                const bool c1 = any && khi == hi;
-                const unsigned lo = __reduce_max_sync(FULL, c1 ? klo : 0u);
-                const bool c2 = c1 && klo == lo;
-                const unsigned ppos = __reduce_min_sync(FULL, c2 ? (unsigned)kpos : 0xffffu);
 #pragma unroll
                 for (int t = 0; t < RPL; ++t) {
-                    const bool piv = c2 && kt == t && (unsigned)pos[t] == ppos && act[t];
-                    if (piv) {
-                        double* row = G + p * LDA;
+                    if (piv[t]) {
+                        double* row = gG + p * LDA;
 #pragma unroll
                         for (int m = 0; m < NRP; m += 2) st2(row + m, a[t][m], a[t][m + 1]);
-                        REC[p] = make_double2(rj[t], __hiloint2double(0, roff[t]));
+                        gREC[p] = make_double2(rj[t], __hiloint2double(0, roff[t]));
                         pos[t] = p;
                         act[t] = false;
-                    } else if (pos[t] == p) {
+                    } else if (has_piv && pos[t] == p) {
                         pos[t] = (int)ppos;     // the row that sat at position p takes the pivot row's old place
                     }
                 }
                 __syncwarp();
-                double u[NRP];
-#pragma unroll
-                for (int m = (p & ~1); m < NRP; m += 2) {
-                    const double2 v = ld2(G + p * LDA + m);
-                    u[m] = v.x;
-                    u[m + 1] = v.y;
-                }
-                const double rp = 1.0 / u[p];
-                if (lane == 0) DINV[p] = rp;
+                const double rp = 1.0 / gG[p * LDA + p];
+                double l[RPL];
 #pragma unroll
                 for (int t = 0; t < RPL; ++t) {
-                    if (act[t]) {
-                        const double l = a[t][p] * rp;
-                        a[t][p] = l;
+                    if (piv[t]) gDINV[p] = rp;
+                    l[t] = a[t][p] * rp;
+                    if (act[t]) a[t][p] = l[t];
+                }
 #pragma unroll
-                        for (int m = p + 1; m < NRP; ++m) a[t][m] = fma(-l, u[m], a[t][m]);
+                for (int m = ((p + 1) & ~1); m < NRP; m += 2) {
+                    const double2 u2 = ld2(gG + p * LDA + m);
+#pragma unroll
+                    for (int t = 0; t < RPL; ++t) {
+                        if (act[t]) {
+                            if (m > p) a[t][m] = fma(-l[t], u2.x, a[t][m]);
+                            a[t][m + 1] = fma(-l[t], u2.y, a[t][m + 1]);
+                        }
                     }
                 }
             }
         }
         __syncwarp();
 
-        // ---- P5. operator columns: dgetrs per right-hand side (lane = column) ----------------------
-        double* opg = P.op + mt.op_off;
-        const int qblk = (nq + 31) >> 5;
-        for (int b = 0; b < qblk; ++b) {
-            const int q = b * 32 + lane;
-            const double wq = W[q];
-            const double* ctq = CT + b * BLK + lane;
-            double y[NRP];
-            // y = P (row o (w_q c_q)): right-hand side row_j w_q c[q,oj] (impl.pyx:769-779), in pivot order
+        // ================= whole warp: P5 operator columns (dgetrs per right-hand side) =================
+        // The FPW fits go through the substitution side by side (independent dependency chains).
+        int f_nr[FPW], f_nk[FPW], f_nq[FPW], f_no[FPW];
+        long long f_off[FPW];
+        int qblk = 0;
 #pragma unroll
-            for (int i = 0; i < NRP; ++i) {
-                y[i] = 0.0;
-                if (i < nr) {
-                    const double2 rec = REC[i];
-                    y[i] = rec.x * (wq * ctq[__double2loint(rec.y)]);
+        for (int f = 0; f < FPW; ++f) {
+            f_nr[f] = f_nk[f] = f_nq[f] = f_no[f] = 0;
+            f_off[f] = 0;
+            if (c0 + f < P.ncases) {
+                const CaseMeta mt = get_meta(c0 + f);
+                if (mt.nr > 0) {
+                    f_nr[f] = mt.nr; f_nk[f] = mt.nk; f_nq[f] = mt.nk + mt.nkn; f_no[f] = mt.no;
+                    f_off[f] = mt.op_off;
+                    qblk = max(qblk, (f_nq[f] + 31) >> 5);
                 }
             }
-            __syncwarp();   // every lane has consumed this CT block: it becomes the staging buffer
+        }
+        for (int b = 0; b < qblk; ++b) {
+            const int q = b * 32 + lane;
+            double y[FPW][NRP];
+            // y = P (row o (w_q c_q)): right-hand side row_j w_q c[q,oj] (impl.pyx:769-779), in pivot order.
+            // The lane recomputes its column of monomials into its own CT column and reads it back through
+            // the pivot-order row offsets (no other lane touches that column: no barrier needed).
+            double* ctq = CT + lane;
+#pragma unroll
+            for (int f = 0; f < FPW; ++f) {
+#pragma unroll
+                for (int i = 0; i < NRP; ++i) y[f][i] = 0.0;
+                if (b * 32 < f_nq[f]) {
+                    const double* fb = fits + f * P.fit_doubles;
+                    const double2* REC = reinterpret_cast<const double2*>(fb + oREC);
+                    if (pending) {
+                        if (lane == 0) tma_store_wait_read();
+                        __syncwarp();
+                        pending = false;
+                    }
+                    monomial_column(c0 + f, q, f_nk[f], f_no[f], ctq);
+                    if (q >= f_nk[f] && q < f_nq[f]) {
+                        const double* kn = fb + oKN + (q - f_nk[f]) * NOP;
+                        for (int s2 = 0; s2 < f_no[f]; ++s2) ctq[s2 * CB] = kn[s2];
+                    }
+                    const double wq = q < f_nq[f] ? fb[oW + q] : 0.0;
+#pragma unroll
+                    for (int i = 0; i < NRP; ++i) {
+                        if (i < f_nr[f]) {
+                            const double2 rec = REC[i];
+                            y[f][i] = rec.x * (wq * ctq[__double2loint(rec.y)]);
+                        }
+                    }
+                }
+            }
             // unit-lower forward substitution
 #pragma unroll
             for (int i = 1; i < NRP; ++i) {
-                if (i < nr) {
 #pragma unroll
-                    for (int p = 0; p < i; p += 2) {
-                        const double2 l2 = ld2(G + i * LDA + p);
-                        y[i] = fma(-l2.x, y[p], y[i]);
-                        if (p + 1 < i) y[i] = fma(-l2.y, y[p + 1], y[i]);
+                for (int f = 0; f < FPW; ++f) {
+                    if (i < f_nr[f]) {
+                        const double* G = fits + f * P.fit_doubles + oG;
+#pragma unroll
+                        for (int p = 0; p < i; p += 2) {
+                            const double2 l2 = ld2(G + i * LDA + p);
+                            y[f][i] = fma(-l2.x, y[f][p], y[f][i]);
+                            if (p + 1 < i) y[f][i] = fma(-l2.y, y[f][p + 1], y[f][i]);
+                        }
                     }
                 }
             }
             // upper backward substitution (padded columns hold zeros)
 #pragma unroll
             for (int i = NRP - 1; i >= 0; --i) {
-                if (i < nr) {
 #pragma unroll
-                    for (int m = ((i + 1) & ~1); m < NRP; m += 2) {
-                        const double2 u2 = ld2(G + i * LDA + m);
-                        if (m > i) y[i] = fma(-u2.x, y[m], y[i]);
-                        y[i] = fma(-u2.y, y[m + 1], y[i]);
+                for (int f = 0; f < FPW; ++f) {
+                    if (i < f_nr[f]) {
+                        const double* G = fits + f * P.fit_doubles + oG;
+#pragma unroll
+                        for (int m = ((i + 1) & ~1); m < NRP; m += 2) {
+                            const double2 u2 = ld2(G + i * LDA + m);
+                            if (m > i) y[f][i] = fma(-u2.x, y[f][m], y[f][i]);
+                            y[f][i] = fma(-u2.y, y[f][m + 1], y[f][i]);
+                        }
+                        y[f][i] *= fits[f * P.fit_doubles + oDINV + i];
                     }
-                    y[i] *= DINV[i];
                 }
             }
-            // Op[q][j] = x_j * col_j, staged as 32 consecutive operator rows and stored in one bulk copy
-            double* ops = CT + b * BLK;
-            if (q < nq) {
+            // Op[q][j] = x_j * col_j: 32 consecutive operator rows staged in CT, one bulk store per fit
 #pragma unroll
-                for (int i = 0; i < NRP; ++i)
-                    if (i < nr) ops[lane * nr + i] = y[i] * RS[i];
-            }
-            const int rows = min(32, nq - b * 32);
-            if (lane == 0 && ((rows * nr) & 1)) ops[rows * nr] = 0.0;
-            fence_proxy_async();
-            __syncwarp();
-            if (lane == 0) {
-                tma_store_1d(opg + (long long)b * 32 * nr, ops, (uint32_t)(((rows * nr + 1) & ~1) * 8));
-                tma_store_commit();
+            for (int f = 0; f < FPW; ++f) {
+                const int nrf = f_nr[f];
+                const int rows = min(32, f_nq[f] - b * 32);
+                if (rows > 0) {
+                    if (pending) {
+                        if (lane == 0) tma_store_wait_read();
+                        pending = false;
+                    }
+                    __syncwarp();    // gathers done / previous store has finished reading
+                    const double* RS = fits + f * P.fit_doubles + oRS;
+                    if (lane < rows) {
+#pragma unroll
+                        for (int i = 0; i < NRP; ++i)
+                            if (i < nrf) CT[lane * nrf + i] = y[f][i] * RS[i];
+                    }
+                    if (lane == 0 && ((rows * nrf) & 1)) CT[rows * nrf] = 0.0;
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) {
+                        tma_store_1d(P.op + f_off[f] + (long long)b * 32 * nrf, CT, (uint32_t)(((rows * nrf + 1) & ~1) * 8));
+                        tma_store_commit();
+                    }
+                    pending = true;
+                }
             }
         }
     }
