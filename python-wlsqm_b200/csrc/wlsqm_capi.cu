@@ -176,16 +176,25 @@ bool config_prepare_reg(const wlsqm_solver* s, PrepRegParams& P, LaunchCfg& L) {
     P.warp_doubles = prep_reg_warp_doubles(s->dim, s->maxorder, P.nb, nkn_max);
     const int fpw = prep_reg_fits_per_warp(s->dim, s->maxorder);
     const size_t per_warp = (size_t)P.warp_doubles * 8;
-    int warps = PREP_REG_THREADS / 32;
-    while (warps > 1 && warps * per_warp > SMEM_PER_CTA) --warps;
-    if (warps * per_warp > SMEM_PER_CTA) return false;
+    if (per_warp > SMEM_PER_CTA) return false;
+    // CTA size: the one that keeps most warps resident (shared memory and registers both limit it)
+    int best_w = 0, best_ctas = 0;
+    const int force_w = env_int("WLSQM_PREP_WARPS", 0);
+    for (int w = 1; w <= PREP_REG_THREADS / 32; ++w) {
+        if (force_w > 0 && w != force_w) continue;
+        if (w * per_warp > SMEM_PER_CTA) break;
+        int c = 0;
+        if (prepare_reg_occupancy(s->dim, s->maxorder, w * 32, w * per_warp, &c) != cudaSuccess) {
+            cudaGetLastError();
+            continue;
+        }
+        if (w * c > best_w * best_ctas || (w * c == best_w * best_ctas && w <= 4)) { best_w = w; best_ctas = c; }
+    }
+    if (best_w < 1 || best_ctas < 1) return false;
+    const int warps = best_w;
+    int ctas = best_ctas;
     L.threads = warps * 32;
     L.smem = warps * per_warp;
-    int ctas = 1;
-    if (prepare_reg_occupancy(s->dim, s->maxorder, L.threads, L.smem, &ctas) != cudaSuccess || ctas < 1) {
-        cudaGetLastError();
-        return false;
-    }
     const int cap = env_int("WLSQM_PREP_CTAS", 0);
     if (cap > 0) ctas = std::min(ctas, cap);
     long long need = (s->ncases + (long long)warps * fpw - 1) / ((long long)warps * fpw);

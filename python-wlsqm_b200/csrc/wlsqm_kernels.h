@@ -6,7 +6,7 @@
 namespace wlsqm {
 
 constexpr int PREP_MAX_THREADS = 512;        // shared-memory variant (wlsqm_prepare_smem.cu)
-constexpr int PREP_REG_THREADS = 128;        // register/DMMA variant (wlsqm_prepare.cu): 4 fits in flight per CTA
+constexpr int PREP_REG_THREADS = 256;        // register/DMMA variant (wlsqm_prepare.cu): launch bound; the host picks the CTA size
 constexpr int PREP_CB = 36;                  // row stride (doubles) inside a 32-column block of the monomial table
 constexpr int SOLVE_MAX_THREADS = 1024;       // ALGO_BASIC variants (<= 64 registers per thread)
 constexpr int SOLVE_MAX_THREADS_ITER = 512;   // ALGO_ITERATIVE variants carry the Taylor evaluator

@@ -47,6 +47,7 @@ struct PK {
     static constexpr int T = NOP / 8;
     static constexpr int LDA = NOP + 2;             // row stride of G / LU: LDS.128 by lane = row is conflict free
     static constexpr int BLK = NOP * PREP_CB;       // doubles per 32-column block of CT
+    static constexpr int MINB = RPL == 2 ? 1 : 2;   // CTAs of PREP_REG_THREADS per SM the register budget must allow
 };
 
 __host__ __device__ constexpr int prep_no(int dim, int ord) {
@@ -111,7 +112,7 @@ __device__ __forceinline__ unsigned group_min(unsigned v, int grp) {
 }
 
 template <int DIM, int ORD>
-__global__ void __launch_bounds__(PREP_REG_THREADS) prepare_reg_kernel(PrepRegParams P) {
+__global__ void __launch_bounds__(PREP_REG_THREADS, PK<DIM, ORD>::MINB) prepare_reg_kernel(PrepRegParams P) {
     using K = PK<DIM, ORD>;
     constexpr int NOP = K::NOP, NRP = K::NRP, RPL = K::RPL, T = K::T, LDA = K::LDA, CB = PREP_CB, BLK = K::BLK;
     constexpr int LPF = K::LPF, FPW = K::FPW;
