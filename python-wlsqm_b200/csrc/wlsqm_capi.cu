@@ -732,6 +732,7 @@ int wlsqm_solver_interpolate(wlsqm_solver_t* s, const double* x, int64_t x_s0, c
         if (diff == WLSQM_DIFF_ALL && !s->uniform_no) CU(cudaMemsetAsync(s->st_out.p, 0, (size_t)nx * ow * 8, st));
         P.out = (double*)s->st_out.p; P.out_s0 = ow;
     }
+    P.stage_no = (diff == WLSQM_DIFF_ALL && s->uniform_no && P.out_s0 == s->uni.no) ? s->uni.no : 0;
     CU(launch_interpolate(P, st));
     if (!out_dev) {
         if (diff == WLSQM_DIFF_ALL) rc = from_dense(out, out_s0, (const double*)s->st_out.p, ow, nx, ow, st);
@@ -829,6 +830,7 @@ int wlsqm_interpolate_fit(int dimension, int order, const double* xi, const doub
         P.x = (const double*)bx.p; P.x_s0 = dimension;
     } else { P.x = x; P.x_s0 = x_s0; }
     P.out = bo.p ? (double*)bo.p : out; P.out_s0 = ow;
+    P.stage_no = diff == WLSQM_DIFF_ALL ? no : 0;
     e = launch_interpolate(P, st);
     if (e == cudaSuccess && bo.p) e = cudaMemcpyAsync(out, bo.p, (size_t)nx * ow * 8, cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);

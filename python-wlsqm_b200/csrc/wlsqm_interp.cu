@@ -10,88 +10,158 @@
 // scratch polynomial `fi2` and evaluates that with a nested Horner form.  Here the derivative
 // d^(p,q,r) of  sum_s fi[s] x^a y^b z^c/(a! b! c!)  is evaluated directly as
 //   sum_{a>=p, b>=q, c>=r} fi[s] x^(a-p) y^(b-q) z^(c-r) / ((a-p)! (b-q)! (c-r)!)
-// by shifting the per-axis scaled-power tables; slots whose exponents fall below (p,q,r) multiply
-// a zero.  A derivative slot >= no gives 0, as interp.pyx:690-694.
-// One thread per query; queries that share a model hit the same coefficient row in L1/L2.
+// from the slot exponent tables, which are compile-time: the list of (slot, shifted monomial) terms of
+// every derivative is unrolled, the shifted monomials are shared between derivatives (they are the
+// model's own monomials of lower order), and a term costs one FMA.  A derivative slot >= no gives 0,
+// as interp.pyx:690-694.
+//
+// One thread per query.  The model row fi[I[m]] (no doubles) and its origin are loaded once into
+// registers; queries that share a model hit the same lines in L1.  diff = WLSQM_DIFF_ALL (extension)
+// writes every slot: the warp's 32 x no results are transposed through shared memory so that the
+// global stores are contiguous.
 #include <type_traits>
 #include "wlsqm_common.cuh"
 #include "wlsqm_kernels.h"
 
 namespace wlsqm {
 
-__device__ __forceinline__ Pow5 shifted_powers(double d, int p) {
-    const Pow5 b = scaled_powers(d);
-    Pow5 r;
-#pragma unroll
-    for (int a = 0; a < 5; ++a) {
-        double v = 0.0;
-#pragma unroll
-        for (int pp = 0; pp <= a; ++pp)
-            if (p == pp) v = b.p[a - pp];
-        r.p[a] = v;
+constexpr int INTERP_THREADS = 256;
+constexpr int INTERP_Q = 4;        // queries per thread
+
+// index of the slot with exponents (a,b,c), or -1 (compile-time search through the slot table)
+template <int DIM>
+__host__ __device__ constexpr int slot_of(int a, int b, int c) {
+    for (int s = 0; s < max_no<DIM>(); ++s) {
+        const SlotExp e = slot_exp<DIM>(s);
+        if (e.a == a && e.b == b && e.c == c) return s;
     }
-    return r;
+    return -1;
 }
 
-template <int DIM>
-__device__ __forceinline__ double eval_diff(int no, const double* __restrict__ fi, double dx, double dy, double dz,
-                                            int p, int q, int r) {
-    const Pow5 px = shifted_powers(dx, p);
-    const Pow5 py = shifted_powers(DIM >= 2 ? dy : 0.0, DIM >= 2 ? q : 0);
-    const Pow5 pz = shifted_powers(DIM >= 3 ? dz : 0.0, DIM >= 3 ? r : 0);
+// value of derivative slot D of the model (fi[0..no), monomials mono[s] = dx^a dy^b dz^c/(a! b! c!))
+template <int DIM, int D>
+__device__ __forceinline__ double eval_slot(int no, const double (&fi)[max_no<DIM>()], const double (&mono)[max_no<DIM>()]) {
     double acc = 0.0;
+    // highest slots first (small terms first), like eval_taylor
     static_for<0, max_no<DIM>()>([&](auto I) {
         constexpr int S = max_no<DIM>() - 1 - decltype(I)::value;
-        if (S < no) acc = fma(__ldg(fi + S), monomial<DIM, S, false>(px, py, pz), acc);
+        constexpr SlotExp e = slot_exp<DIM>(S);
+        constexpr SlotExp d = slot_exp<DIM>(D);
+        if constexpr (S >= D && e.a >= d.a && e.b >= d.b && e.c >= d.c) {
+            constexpr int M = slot_of<DIM>(e.a - d.a, e.b - d.b, e.c - d.c);   // the shifted monomial is a lower slot
+            if (S < no) acc = fma(fi[S], mono[M], acc);
+        }
     });
     return acc;
 }
 
-template <int DIM>
-__device__ __forceinline__ void slot_exponents(int s, int& p, int& q, int& r) {
-    p = q = r = 0;
-    static_for<0, max_no<DIM>()>([&](auto I) {
-        constexpr int S = decltype(I)::value;
-        constexpr SlotExp e = slot_exp<DIM>(S);
-        if (s == S) { p = e.a; q = e.b; r = e.c; }
-    });
-}
-
-template <int DIM>
-__global__ void __launch_bounds__(256) interpolate_kernel(InterpParams P) {
-    const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (m >= P.nx) return;
-    const long long i = P.I ? P.I[m] : 0;
-    const int order = P.order ? (int)P.order[i] : P.order_uniform;
-    const int no = number_of_dofs(DIM, order);
-    const double* xq = P.x + m * P.x_s0;
-    const double* xo = P.xi + i * P.xi_s0;
-    const double dx = xq[0] - xo[0];
-    const double dy = DIM >= 2 ? xq[DIM >= 2 ? 1 : 0] - xo[DIM >= 2 ? 1 : 0] : 0.0;
-    const double dz = DIM >= 3 ? xq[DIM >= 3 ? 2 : 0] - xo[DIM >= 3 ? 2 : 0] : 0.0;
-    const double* fi = P.fi + i * P.fi_s0;
-    if (P.diff >= 0) {
-        int p, q, r;
-        slot_exponents<DIM>(P.diff, p, q, r);
-        st_stream(P.out + m, eval_diff<DIM>(no, fi, dx, dy, dz, p, q, r));
-    } else {   // extension: every derivative slot of the model in one pass, out[m][0..no)
-        double* o = P.out + m * P.out_s0;
-        for (int d = 0; d < no; ++d) {
-            int p, q, r;
-            slot_exponents<DIM>(d, p, q, r);
-            st_stream(o + d, eval_diff<DIM>(no, fi, dx, dy, dz, p, q, r));
+// ALL = every derivative slot (WLSQM_DIFF_ALL); STAGE = transpose the warp's results through shared memory.
+// Each thread owns INTERP_Q queries, blockDim apart (coalesced), and issues their index and coordinate loads
+// together before the dependent model-row loads: the kernel is bound by load latency, not by arithmetic.
+template <int DIM, bool ALL, bool STAGE>
+__global__ void __launch_bounds__(INTERP_THREADS) interpolate_kernel(InterpParams P) {
+    constexpr int NO = max_no<DIM>();
+    constexpr int Q = INTERP_Q;
+    extern __shared__ __align__(16) double stage[];     // STAGE: [warps][32 * no]
+    const long long base = (long long)blockIdx.x * (blockDim.x * Q) + threadIdx.x;
+    long long idx[Q];
+    double xq[Q][DIM];
+#pragma unroll
+    for (int j = 0; j < Q; ++j) {
+        const long long m = base + (long long)j * blockDim.x;
+        const long long mm = m < P.nx ? m : P.nx - 1;
+        idx[j] = P.I ? P.I[mm] : 0;
+#pragma unroll
+        for (int d = 0; d < DIM; ++d) xq[j][d] = P.x[mm * P.x_s0 + d];
+    }
+#pragma unroll
+    for (int j = 0; j < Q; ++j) {
+        const long long m = base + (long long)j * blockDim.x;
+        const bool live = m < P.nx;
+        const long long i = idx[j];
+        const int order = P.order ? (int)P.order[i] : P.order_uniform;
+        const int no = number_of_dofs(DIM, order);
+        const double* xo = P.xi + i * P.xi_s0;
+        const double dx = xq[j][0] - xo[0];
+        const double dy = DIM >= 2 ? xq[j][DIM >= 2 ? 1 : 0] - xo[DIM >= 2 ? 1 : 0] : 0.0;
+        const double dz = DIM >= 3 ? xq[j][DIM >= 3 ? 2 : 0] - xo[DIM >= 3 ? 2 : 0] : 0.0;
+        const double* fg = P.fi + i * P.fi_s0;
+        double fi[NO], mono[NO];
+#pragma unroll
+        for (int s = 0; s < NO; ++s) fi[s] = s < no ? __ldg(fg + s) : 0.0;
+        {
+            const Pow5 px = scaled_powers(dx), py = scaled_powers(dy), pz = scaled_powers(dz);
+            static_for<0, NO>([&](auto I) {
+                constexpr int S = decltype(I)::value;
+                mono[S] = monomial<DIM, S>(px, py, pz);
+            });
+        }
+        if constexpr (!ALL) {
+            double v = 0.0;
+            static_for<0, NO>([&](auto I) {
+                constexpr int D = decltype(I)::value;
+                if (P.diff == D) v = eval_slot<DIM, D>(no, fi, mono);     // grid-uniform branch
+            });
+            if (live) st_stream(P.out + m, v);
+        } else {
+            // extension: every derivative slot of the model in one pass, out[m][0..no)
+            double val[NO];
+            static_for<0, NO>([&](auto I) {
+                constexpr int D = decltype(I)::value;
+                val[D] = eval_slot<DIM, D>(no, fi, mono);
+            });
+            if constexpr (STAGE) {
+                // uniform model size and dense rows: transpose through shared memory, then contiguous stores
+                const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+                const int nno = P.stage_no;
+                double* st = stage + (size_t)warp * 32 * nno;
+                __syncwarp();
+#pragma unroll
+                for (int d = 0; d < NO; ++d)
+                    if (d < nno) st[lane * nno + d] = val[d];
+                __syncwarp();
+                const long long m0 = m - lane;                       // first query of this warp
+                const long long left = (P.nx - m0) * nno;            // doubles this warp may still write
+                double* o = P.out + m0 * nno;
+                for (int t = lane; t < 32 * nno && t < left; t += 32) st_stream(o + t, st[t]);
+            } else if (live) {
+                double* o = P.out + m * P.out_s0;
+#pragma unroll
+                for (int d = 0; d < NO; ++d)
+                    if (d < no) st_stream(o + d, val[d]);
+            }
         }
     }
 }
 
-cudaError_t launch_interpolate(const InterpParams& P, cudaStream_t st) {
-    if (P.nx == 0) return cudaSuccess;
-    const int threads = 256;
-    const unsigned blocks = (unsigned)((P.nx + threads - 1) / threads);
-    if (P.dim == 1) interpolate_kernel<1><<<blocks, threads, 0, st>>>(P);
-    else if (P.dim == 2) interpolate_kernel<2><<<blocks, threads, 0, st>>>(P);
-    else interpolate_kernel<3><<<blocks, threads, 0, st>>>(P);
+template <int DIM, bool ALL, bool STAGE>
+static cudaError_t launch_interp_t(const InterpParams& P, unsigned blocks, size_t smem, cudaStream_t st) {
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(interpolate_kernel<DIM, ALL, STAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    interpolate_kernel<DIM, ALL, STAGE><<<blocks, INTERP_THREADS, smem, st>>>(P);
     return cudaGetLastError();
+}
+
+template <int DIM>
+static cudaError_t launch_interp_d(const InterpParams& P, unsigned blocks, size_t smem, cudaStream_t st) {
+    if (P.diff >= 0) return launch_interp_t<DIM, false, false>(P, blocks, 0, st);
+    if (P.stage_no > 0) return launch_interp_t<DIM, true, true>(P, blocks, smem, st);
+    return launch_interp_t<DIM, true, false>(P, blocks, 0, st);
+}
+
+cudaError_t launch_interpolate(const InterpParams& Pin, cudaStream_t st) {
+    if (Pin.nx == 0) return cudaSuccess;
+    InterpParams P = Pin;
+    const long long per_block = (long long)INTERP_THREADS * INTERP_Q;
+    const unsigned blocks = (unsigned)((P.nx + per_block - 1) / per_block);
+    size_t smem = 0;
+    if (P.diff < 0 && P.stage_no > 0) smem = (size_t)(INTERP_THREADS / 32) * 32 * P.stage_no * sizeof(double);
+    else P.stage_no = 0;
+    if (P.dim == 1) return launch_interp_d<1>(P, blocks, smem, st);
+    if (P.dim == 2) return launch_interp_d<2>(P, blocks, smem, st);
+    return launch_interp_d<3>(P, blocks, smem, st);
 }
 
 }  // namespace wlsqm

@@ -73,6 +73,8 @@ struct InterpParams {
     const signed char* order; int order_uniform;     // per-model order, or uniform
     int diff;                                        // DOF slot to differentiate to, or -1: all slots
     double* out; long long out_s0;                   // [nx] (diff >= 0) or [nx][out_s0]
+    int stage_no;                                    // all slots, every model has stage_no DOFs and out_s0 == stage_no:
+                                                     // results are transposed through shared memory (else 0)
 };
 
 cudaError_t launch_prepare_smem(int dim, const PrepareParams& P, int blocks, int threads, size_t smem, cudaStream_t st);
