@@ -214,7 +214,9 @@ int config_solve(const wlsqm_solver* s, SolveParams& P, LaunchCfg& L, long long 
     // fit (16 for the headline block size) streams best; deeper rings or several CTAs per SM put more
     // distant operator blocks in flight at once and lose HBM efficiency.  Blocks under 3 KB are bound by
     // per-case issue overhead instead and want two such CTAs per SM.
-    int S = env_int("WLSQM_SOLVE_STAGES", 2);
+    // ALGO_ITERATIVE keeps a warp busy on one block for thousands of cycles: more resident warps (one stage
+    // each) beat prefetch depth there (measured: 3D order 4 k=60 with sens, 16.7 -> 9.6 ms per 1M points).
+    int S = env_int("WLSQM_SOLVE_STAGES", (iter && stage_bytes >= 8192) ? 1 : 2);
     S = std::max(1, std::min(S, 8));
     const int max_warps = (iter ? SOLVE_MAX_THREADS_ITER : SOLVE_MAX_THREADS) / 32;
     int warps = env_int("WLSQM_SOLVE_WARPS", 16);

@@ -126,6 +126,15 @@ __device__ __forceinline__ double warp_max(double v) {
     return v;
 }
 
+// max over the warp of a non-negative, non-NaN double: its bit pattern orders like an unsigned integer, so
+// two REDUX (high word, then low word among the lanes that tie on the high word) replace five shuffle rounds
+__device__ __forceinline__ double warp_max_nonneg(double v) {
+    const unsigned hi = (unsigned)__double2hiint(v), lo = (unsigned)__double2loint(v);
+    const unsigned mh = __reduce_max_sync(0xffffffffu, hi);
+    const unsigned ml = __reduce_max_sync(0xffffffffu, hi == mh ? lo : 0u);
+    return __hiloint2double((int)mh, (int)ml);
+}
+
 // ---- mbarrier + 1D bulk-TMA wrappers (cp.async.bulk, SASS: UBLKCP) ---------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return (uint32_t)__cvta_generic_to_shared(p);

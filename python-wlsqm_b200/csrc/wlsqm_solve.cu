@@ -85,22 +85,28 @@ __device__ __forceinline__ void warp_matvec_t(uint32_t op_s, uint32_t v_s, int n
             cnt -= 2;
         }
         if (cnt > 0) a2 = fma(lds_f64(pa), lds_f64(va), a2);
-        if (LW == 5 && j + 32 < nr) {
-            uint32_t qa = op_s + (uint32_t)(j + 32) * 8u, wa = v_s;
-            const uint32_t rs8 = (uint32_t)nr * 8u;
-            double b0 = 0.0, b1 = 0.0;
-            int t = n;
-            for (; t >= 2; t -= 2) {
-                const double x0 = lds_f64(qa), x1 = lds_f64(qa + rs8);
-                const double y0 = lds_f64(wa), y1 = lds_f64(wa + 8);
-                b0 = fma(x0, y0, b0);
-                b1 = fma(x1, y1, b1);
-                qa += 2u * rs8;
-                wa += 16;
-            }
-            if (t > 0) b0 = fma(lds_f64(qa), lds_f64(wa), b0);
-            hi = b0 + b1;
+    }
+    if (LW == 5 && nr > 32) {
+        // columns 32 .. nr-1 (at most three): every lane takes the rows q = lane, lane + 32, ... of those
+        // columns; the partial sums are reduced across the warp and column 32 + t ends up in lane t
+        double h0 = 0.0, h1 = 0.0, h2 = 0.0;
+        const uint32_t rs8 = (uint32_t)nr * 8u;
+        uint32_t qa = op_s + (uint32_t)lane * rs8 + 256u, wa = v_s + (uint32_t)lane * 8u;
+        for (int q = lane; q < n; q += 32) {
+            const double y = lds_f64(wa);
+            h0 = fma(lds_f64(qa), y, h0);
+            if (nr > 33) h1 = fma(lds_f64(qa + 8u), y, h1);
+            if (nr > 34) h2 = fma(lds_f64(qa + 16u), y, h2);
+            qa += 32u * rs8;
+            wa += 256u;
         }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            h0 += __shfl_xor_sync(0xffffffffu, h0, off);
+            if (nr > 33) h1 += __shfl_xor_sync(0xffffffffu, h1, off);
+            if (nr > 34) h2 += __shfl_xor_sync(0xffffffffu, h2, off);
+        }
+        hi = lane == 0 ? h0 : (lane == 1 ? h1 : h2);
     }
     lo = (a0 + a1) + (a2 + a3);
 #pragma unroll
@@ -266,24 +272,32 @@ __global__ void __launch_bounds__(ITER ? SOLVE_MAX_THREADS_ITER : SOLVE_MAX_THRE
         if (SENS && nr > 0) {   // nr == 0: silent no-op, sens untouched (impl.pyx:742)
             double* sn = P.sens + c * P.sens_s0;
             const double qnan = __longlong_as_double(0x7ff8000000000000LL);
-            if (P.sens_s1 == no) {
-                // rows are back to back: walk the (k, o) plane with lane-contiguous stores
-                int k = lane / no, o = lane - k * no;          // position of element t = lane
-                const int dk = 32 / no, d_o = 32 - dk * no;      // advance of (k, o) per 32 elements
-                for (int t = lane; t < nk * no; t += 32) {
-                    double v = qnan;
-                    if (!((knowns >> o) & 1LL)) v = op[k * nr + (o - __popcll(knowns & ((1LL << o) - 1)))];
-                    st_stream(sn + t, v);
-                    k += dk;
-                    o += d_o;
-                    if (o >= no) { o -= no; ++k; }
+            if (no <= 32) {
+                // the 32 lanes cover G2 = 32 / W2 operator rows per pass (W2 = smallest power of two >= no);
+                // a lane's DOF slot, its reduced index and its NaN flag do not change from pass to pass
+                const int lw2 = no <= 1 ? 0 : 32 - __clz(no - 1);
+                const int G2 = 32 >> lw2, rg = lane >> lw2, o = lane & ((1 << lw2) - 1);
+                const bool kn = (knowns >> o) & 1LL;
+                const int jo = o - __popcll(knowns & ((1LL << o) - 1));
+                if (o < no) {
+                    double* sp = sn + (long long)rg * P.sens_s1 + o;
+                    const double* opp = op + rg * nr + jo;
+                    const long long dsn = (long long)G2 * P.sens_s1;
+                    const int dop = G2 * nr;
+                    for (int k = rg; k < nk; k += G2) {
+                        st_stream(sp, kn ? qnan : *opp);
+                        sp += dsn;
+                        opp += dop;
+                    }
                 }
             } else {
-                for (int t = lane; t < nk * no; t += 32) {
-                    const int k = t / no, o = t - k * no;
-                    double v = qnan;
-                    if (!((knowns >> o) & 1LL)) v = op[k * nr + (o - __popcll(knowns & ((1LL << o) - 1)))];
-                    st_stream(sn + (long long)k * P.sens_s1 + o, v);
+                double* sp = sn + lane;
+                const double* opp = op;
+                for (int k = 0; k < nk; ++k) {
+                    st_stream(sp, unk0 ? opp[j0] : qnan);
+                    if (in1) st_stream(sp + 32, unk1 ? opp[j1] : qnan);
+                    sp += P.sens_s1;
+                    opp += nr;
                 }
             }
         }
@@ -304,9 +318,10 @@ __global__ void __launch_bounds__(ITER ? SOLVE_MAX_THREADS_ITER : SOLVE_MAX_THRE
                     const double dz = DIM >= 3 ? xks[k * DIM + (DIM >= 3 ? 2 : 0)] - xi2 : 0.0;
                     const double r = fext[k] - eval_taylor<DIM>(no, fis, dx, dy, dz);
                     rs[k] = r;
-                    nrm = fmax(nrm, fabs(r));
+                    const double ar = fabs(r);
+                    nrm = ar > nrm ? ar : nrm;          // `if tmp > norm` (impl.pyx:1037-1041)
                 }
-                nrm = warp_max(nrm);
+                nrm = warp_max_nonneg(nrm);
                 if (nrm == prev) { broke = true; break; }
                 prev = nrm;
                 __syncwarp();
