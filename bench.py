@@ -50,6 +50,16 @@ METRIC = "ExpertSolver.solve points/s (2D order-4, 15 DOF, k=30, 1M-point cloud)
 UNIT = "points/s"
 
 
+def _fp64_peak():
+    """Measured FP64 vector-FMA peak of this pool's B200 (benchmarks/fp64_peak.cu; MEASURED_PEAKS.json has no FP64 figure)."""
+    p = ROOT / "profiles" / "fp64_peak.json"
+    try:
+        j = json.loads(p.read_text())
+        return float(j["dfma_tflops"]), float(j["dmma_m8n8k4_tflops"]), "measured (profiles/fp64_peak.json, benchmarks/fp64_peak.cu)"
+    except Exception:
+        return 37.0, 37.0, "nominal (B200 datasheet FP64)"
+
+
 def _peaks():
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
@@ -325,13 +335,19 @@ def run_b200(args, rank, world, local_rank):
                        "bytes_per_point": BYTES_PER_POINT},
             "e2e": {"value": world * n * e2e_steps / (e2e_ms * 1e-3), "unit": UNIT,
                     "h2d_bytes_per_step": int(n * K * 8), "d2h_bytes_per_step": int(n * NO * 8),
-                    "steps": e2e_steps, "host_buffers": "pinned"},
+                    "steps": e2e_steps, "host_buffers": "pinned",
+                    "pcie_h2d_GBps": n * K * 8 / (e2e_ms * 1e-3 / e2e_steps) / 1e9,
+                    "note": "bound by the host->device copy of fk (240 MB per step), which the reference API makes part of every step"},
             "gpu_launches": args.steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "kernel": "wlsqm::solve_kernel<1,false,false>", "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": BYTES_PER_POINT * n, "launch_ms": kern_ms},
-            "prepare": {"fits_per_s": n / (prep_ms * 1e-3), "ms": prep_ms,
-                        "fp64_gflops_algorithmic": FLOPS_PREP * n / (prep_ms * 1e-3) / 1e9},
+            "prepare": {"fits_per_s": world * n / (prep_ms * 1e-3), "ms": prep_ms, "flops_per_fit": FLOPS_PREP,
+                        "roofline": {"bound": "fp64", "achieved": FLOPS_PREP * n / (prep_ms * 1e-3) / 1e12,
+                                     "peak": _fp64_peak()[0], "unit": "TFLOP/s",
+                                     "frac": FLOPS_PREP * n / (prep_ms * 1e-3) / 1e12 / _fp64_peak()[0],
+                                     "peak_dmma": _fp64_peak()[1], "peak_source": _fp64_peak()[2],
+                                     "kernel": "wlsqm::prepare_reg_kernel<2,4>"}},
             "clocks": clocks,
         }
         traffic_file = ROOT / "profiles" / "solve_kernel_traffic.json"

@@ -104,6 +104,7 @@ struct wlsqm_solver {
     long long ncases = 0;
     int maxnk = 0, maxno = 1, maxnr = 0, maxnq = 0, maxorder = 0, maxnkn = 0;
     bool uniform = true, any_knowns = false, uniform_no = true;
+    bool geom_uniform = true;   // same nk / order / weighting / number of knowns everywhere (the knowns pattern may vary)
     CaseMeta uni{};
     long long op_stride = 0, op_total = 0;
     std::vector<CaseMeta> hmeta;
@@ -255,6 +256,54 @@ int config_solve(const wlsqm_solver* s, SolveParams& P, LaunchCfg& L, long long 
     return WLSQM_OK;
 }
 
+// packed solve (several small cases per warp pass): launch configuration; the stage holds
+// [CPW operator blocks | CPW fk rows | CPW x nkn known values]
+bool pack_eligible(const wlsqm_solver* s) {
+    // blocks of 3 KB and more already stream at the HBM roofline with one case per warp (measured)
+    return s->geom_uniform && s->algorithm != WLSQM_ALGO_ITERATIVE && s->maxno <= 16 && s->uni.nr > 0 &&
+           s->op_stride * 8 < env_int("WLSQM_SOLVE_PACK_BELOW", 3072) && !env_int("WLSQM_SOLVE_NOPACK", 0);
+}
+int config_solve_pack(const wlsqm_solver* s, SolveParams& P, LaunchCfg& L, long long ncases_launch) {
+    const int no = s->uni.no, nk = s->uni.nk, nkn = s->uni.nkn;
+    int lw = 0;
+    while ((1 << lw) < no) ++lw;
+    P.pack_lw = lw;
+    const int cpw = 32 >> lw;
+    const int op_doubles = cpw * (int)s->op_stride;
+    const int f_doubles = std::max(2, even(cpw * nk));
+    const int k_doubles = std::max(2, even(cpw * nkn));
+    const int stage_doubles = op_doubles + f_doubles + k_doubles;
+    const size_t stage_bytes = (size_t)stage_doubles * 8;
+    int S = env_int("WLSQM_SOLVE_STAGES", 2);
+    S = std::max(2, std::min(S, 8));
+    int warps = env_int("WLSQM_SOLVE_WARPS", 16);
+    warps = std::max(1, std::min(warps, SOLVE_MAX_THREADS / 32));
+    int wd = 0;
+    for (;;) {
+        wd = (S * stage_doubles + 15) & ~15;
+        if ((size_t)warps * (wd * 8 + S * 8) <= SMEM_PER_CTA) break;
+        if (warps > 1) --warps;
+        else return fail(WLSQM_E_VALUE, "operator pack too large for shared memory (%zu bytes)", stage_bytes);
+    }
+    P.stages = S;
+    P.stage_doubles = stage_doubles;
+    P.off_f = op_doubles; P.off_xk = op_doubles + f_doubles;
+    P.warp_doubles = wd;
+    // one bulk copy for the CPW fk rows of a pack: dense rows, 16 B aligned pack starts
+    P.f_tma = (P.fk_s1 == 1 && P.fk_s0 == nk && ((uintptr_t)P.fk % 16 == 0) && ((cpw * nk) % 2 == 0)) ? 1 : 0;
+    if (env_int("WLSQM_SOLVE_NO_FTMA", 0)) P.f_tma = 0;
+    P.xk_tma = 0;
+    P.bar_off_bytes = warps * wd * 8;
+    L.threads = warps * 32;
+    L.smem = (size_t)P.bar_off_bytes + (size_t)warps * S * 8;
+    int ctas = (int)(SMEM_PER_SM / (L.smem + 1024));
+    ctas = std::max(1, std::min(ctas, std::max(1, env_int("WLSQM_SOLVE_MAXWARPS_SM", stage_bytes >= 3072 ? 16 : 32) / warps)));
+    const long long packs = (ncases_launch + cpw - 1) / cpw;
+    long long need = (packs + warps - 1) / warps;
+    L.blocks = (int)std::max<long long>(1, std::min<long long>((long long)s->sm_count * ctas, need));
+    return WLSQM_OK;
+}
+
 // copy a pitched host/device 2-D array of doubles into a dense device buffer (rows x width)
 int to_dense(double* dst, const double* src, long long rows, long long width, long long pitch, cudaStream_t st) {
     if (rows == 0 || width == 0) return WLSQM_OK;
@@ -367,6 +416,7 @@ int wlsqm_solver_create(int dimension, int64_t ncases, const int32_t* nk, const 
             const CaseMeta& f = s->hmeta[0];
             if (m.nk != f.nk || m.order != f.order || m.knowns != f.knowns || m.wm != f.wm) s->uniform = false;
             if (m.no != f.no) s->uniform_no = false;
+            if (m.nk != f.nk || m.order != f.order || m.nkn != f.nkn || m.wm != f.wm) s->geom_uniform = false;
         }
     }
     s->op_total = off;
@@ -378,8 +428,11 @@ int wlsqm_solver_create(int dimension, int64_t ncases, const int32_t* nk, const 
 
     int rc = use_device(s);
     if (rc) { delete s; return rc; }
-    cudaDeviceProp prop;
-    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) s->sm_count = prop.multiProcessorCount;
+    {
+        int smc = 0;   // (cudaGetDeviceProperties costs milliseconds; the one attribute is all that is needed)
+        if (cudaDeviceGetAttribute(&smc, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && smc > 0) s->sm_count = smc;
+        else cudaGetLastError();
+    }
     cudaError_t e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) { delete s; return fail(WLSQM_E_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
     s->own_stream = true;
@@ -503,6 +556,7 @@ int wlsqm_solver_prepare(wlsqm_solver_t* s, const double* xi, int64_t xi_s0, con
     LaunchCfg L;
     PrepRegParams R{};
     R.meta = s->dmeta; R.uni = s->uni; R.op_stride = s->op_stride; R.ncases = n;
+    R.geom_uniform = s->geom_uniform ? 1 : 0;
     R.xi = s->xi_dev; R.xi_s0 = dim;
     R.xk = xk_use; R.xk_s0 = s0; R.xk_s1 = s1;
     R.op = s->op; R.As = s->As; R.as_stride = s->as_stride;
@@ -547,6 +601,7 @@ int wlsqm_solver_solve(wlsqm_solver_t* s, const double* fk, int64_t fk_s0, int64
 
     SolveParams P{};
     P.meta = s->dmeta; P.uni = s->uni; P.op_stride = s->op_stride; P.ncases = n; P.op = s->op;
+    P.geom_uniform = s->geom_uniform ? 1 : 0;
     P.algorithm = s->algorithm; P.max_iter = s->max_iter;
     P.fi_case = s->fi_case; P.fi_case_ld = s->maxno;
     P.xi = s->xi_dev; P.xi_s0 = s->dim;
@@ -636,9 +691,15 @@ int wlsqm_solver_solve(wlsqm_solver_t* s, const double* fk, int64_t fk_s0, int64
         }
         P.case_lo = c0;
         P.ncases = c1;
-        rc = config_solve(s, P, L, rows);
-        if (rc) return rc;
-        CU(launch_solve(s->dim, P, L.blocks, L.threads, L.smem, st));
+        if (pack_eligible(s)) {
+            rc = config_solve_pack(s, P, L, rows);
+            if (rc) return rc;
+            CU(launch_solve_pack(P, L.blocks, L.threads, L.smem, st));
+        } else {
+            rc = config_solve(s, P, L, rows);
+            if (rc) return rc;
+            CU(launch_solve(s->dim, P, L.blocks, L.threads, L.smem, st));
+        }
         if (staged) {
             CU(cudaEventRecord(s->events[ev], st));
             CU(cudaStreamWaitEvent(s_out, s->events[ev], 0));

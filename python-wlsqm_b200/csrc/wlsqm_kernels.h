@@ -34,6 +34,7 @@ struct PrepRegParams {
     const double* xk; long long xk_s0, xk_s1;        // [ncases][nk][dim], last axis contiguous
     double* op;                                      // operator blocks (output)
     double* As; int as_stride;                       // debug: scaled matrices [ncases][as_stride] or nullptr
+    int geom_uniform;                                // every case has the sizes of `uni`; only meta[c].knowns is read
     int nb;                                          // 32-column blocks of the monomial table
     int fit_doubles;                                 // shared-memory doubles per fit region (prep_reg_fit_doubles)
     int warp_doubles;                                // per warp: monomial table + prep_reg_fits_per_warp() fit regions
@@ -42,6 +43,7 @@ struct PrepRegParams {
 struct SolveParams {
     const CaseMeta* meta;
     CaseMeta uni;
+    int geom_uniform;                                // every case has the sizes of `uni`; only meta[c].knowns is read
     long long op_stride;
     long long ncases;                                // cases [case_lo, ncases) are processed by this launch
     long long case_lo;
@@ -61,6 +63,7 @@ struct SolveParams {
     int warp_doubles, off_fi, off_r;                 // per-warp smem carve-up (doubles)
     int bar_off_bytes;                               // start of the mbarrier array
     int f_tma, xk_tma;                               // fk / xk rows qualify for bulk copies (alignment, unit stride)
+    int pack_lw;                                     // packed variant: log2 of the lanes per case
 };
 
 struct InterpParams {
@@ -85,6 +88,7 @@ cudaError_t prepare_reg_occupancy(int dim, int maxorder, int threads, size_t sme
 cudaError_t launch_prepare_reg(int dim, int maxorder, const PrepRegParams& P, int blocks, int threads, size_t smem,
                                cudaStream_t st);
 cudaError_t launch_solve(int dim, const SolveParams& P, int blocks, int threads, size_t smem, cudaStream_t st);
+cudaError_t launch_solve_pack(const SolveParams& P, int blocks, int threads, size_t smem, cudaStream_t st);
 cudaError_t launch_scatter_fi(const CaseMeta* meta, const CaseMeta& uni, long long ncases, const double* fi_case,
                               int fi_case_ld, double* fi_out, long long fi_out_s0, cudaStream_t st);
 cudaError_t launch_interpolate(const InterpParams& P, cudaStream_t st);

@@ -143,11 +143,12 @@ __global__ void __launch_bounds__(PREP_REG_THREADS, PK<DIM, ORD>::MINB) prepare_
 
     auto get_meta = [&](long long c) {
         CaseMeta m;
-        if (P.meta) {
+        if (P.meta && !P.geom_uniform) {
             m = P.meta[c];
         } else {
             m = P.uni;
             m.op_off = c * P.op_stride;
+            if (P.meta) m.knowns = P.meta[c].knowns;   // same sizes everywhere, only the knowns pattern varies
         }
         return m;
     };

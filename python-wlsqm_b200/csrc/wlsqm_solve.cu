@@ -159,6 +159,7 @@ __global__ void __launch_bounds__(ITER ? SOLVE_MAX_THREADS_ITER : SOLVE_MAX_THRE
         if (UNI) {
             m = P.uni;
             m.op_off = c * P.op_stride;
+            if (P.meta) m.knowns = P.meta[c].knowns;   // same sizes everywhere, only the knowns pattern varies
         } else {
             m = P.meta[c];
         }
@@ -208,9 +209,9 @@ __global__ void __launch_bounds__(ITER ? SOLVE_MAX_THREADS_ITER : SOLVE_MAX_THRE
             if (sn >= S) sn -= S;
             issue(sn, c + (long long)(S - 1) * GW);
         }
+        const long long knowns = mt.knowns;
         if (UNI) mt = P.uni;   // loop invariant: lets the compiler hoist everything derived from the record
         const int nk = mt.nk, no = mt.no, nr = mt.nr, nkn = mt.nkn, nq = nk + nkn;
-        const long long knowns = mt.knowns;
         double* st = ring + (size_t)stage * P.stage_doubles;
         const uint32_t st_u32 = ring_u32 + (uint32_t)stage * stage_bytes;
         const double* op = st;
@@ -244,7 +245,7 @@ __global__ void __launch_bounds__(ITER ? SOLVE_MAX_THREADS_ITER : SOLVE_MAX_THRE
         CaseMeta mt_next = mt;
         double gn0 = 0.0, gn1 = 0.0;
         if (i + 1 < n_my) {
-            if (!UNI) mt_next = get_meta(c + GW);
+            if (!UNI || P.meta) mt_next = get_meta(c + GW);
             if (mt_next.nkn) load_g(c + GW, mt_next, gn0, gn1);
         }
         __syncwarp();
@@ -360,6 +361,172 @@ __global__ void __launch_bounds__(ITER ? SOLVE_MAX_THREADS_ITER : SOLVE_MAX_THRE
     if (ITER && lane == 0 && itmax > 0) atomicMax(P.iters_max, itmax);
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Packed variant for small models (no <= 16, ALGO_BASIC, every case with the same sizes): a warp takes
+// CPW = 32 / W consecutive cases per pass (W = smallest power of two >= no), so that the per-pass work
+// -- one bulk copy of CPW contiguous operator blocks, one of CPW fk rows, barrier wait, write-back -- is shared
+// by CPW cases.  Lane (cg, o) owns DOF slot o of case cg: an unknown slot accumulates its whole operator
+// column over q (four independent FMA chains, no cross-lane reduction), a known slot passes its value on.
+// Same arithmetic as solve_kernel; only the summation order over q differs (sequential per column).
+template <bool SENS>
+__global__ void __launch_bounds__(SOLVE_MAX_THREADS) solve_pack_kernel(SolveParams P) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int nwarps = blockDim.x >> 5;
+    const int S = P.stages;
+    double* ring = reinterpret_cast<double*>(smem_raw) + (size_t)warp * P.warp_doubles;
+    const uint32_t ring_u32 = smem_u32(ring);
+    const uint32_t bars_u32 = smem_u32(smem_raw + P.bar_off_bytes) + (uint32_t)(warp * S) * 8u;
+    const uint32_t stage_bytes = (uint32_t)P.stage_doubles * 8u;
+
+    const CaseMeta u = P.uni;
+    const int nk = u.nk, no = u.no, nr = u.nr, nkn = u.nkn;
+    const int lw = P.pack_lw, CPW = 32 >> lw;
+    const int cg = lane >> lw, o = lane & ((1 << lw) - 1);
+    const int ops = (int)P.op_stride;                         // doubles per operator block (even)
+
+    const long long npacks = (P.ncases - P.case_lo + CPW - 1) / CPW;
+    const long long gw = (long long)blockIdx.x * nwarps + warp;
+    const long long GW = (long long)gridDim.x * nwarps;
+    const long long n_my = gw < npacks ? (npacks - gw + GW - 1) / GW : 0;
+
+    auto pack_cases = [&](long long pk) { return (int)min((long long)CPW, P.ncases - (P.case_lo + pk * CPW)); };
+    auto f_by_tma = [&](int ncs) { return P.f_tma && !((ncs * nk) & 1); };
+    auto issue = [&](int s, long long pk) {   // lane 0 only
+        const long long c0 = P.case_lo + pk * CPW;
+        const int ncs = pack_cases(pk);
+        const uint32_t st = ring_u32 + (uint32_t)s * stage_bytes, bar = bars_u32 + (uint32_t)s * 8u;
+        const uint32_t b_op = (uint32_t)(ncs * ops) * 8u;
+        const uint32_t b_f = f_by_tma(ncs) ? (uint32_t)(ncs * nk) * 8u : 0u;
+        mbar_expect_tx_u32(bar, b_op + b_f);
+        if (b_op) tma_load_1d_u32(st, P.op + c0 * P.op_stride, b_op, bar);
+        if (b_f) tma_load_1d_u32(st + (uint32_t)P.off_f * 8u, P.fk + c0 * P.fk_s0, b_f, bar);
+    };
+    // knowns pattern and known value of this lane's slot in pack pk
+    auto load_slot = [&](long long pk, long long& kn, double& g) {
+        const long long c = P.case_lo + pk * CPW + cg;
+        kn = u.knowns;
+        g = 0.0;
+        if (c < P.ncases && o < no) {
+            if (P.meta) kn = P.meta[c].knowns;
+            if ((kn >> o) & 1LL) g = P.fi_in[c * P.fi_in_s0 + o];
+        }
+    };
+
+    if (lane == 0) {
+        for (int s = 0; s < S; ++s) mbar_init_u32(bars_u32 + (uint32_t)s * 8u, 1);
+        fence_mbar_init();
+        for (int s = 0; s < S - 1 && s < n_my; ++s) issue(s, gw + (long long)s * GW);
+    }
+    __syncwarp();
+
+    int stage = 0;
+    uint32_t phase = 0;
+    long long knowns = u.knowns;
+    double g = 0.0;
+    if (n_my > 0 && (nkn || P.meta)) load_slot(gw, knowns, g);
+    long long pk = gw;
+    for (long long i = 0; i < n_my; ++i, pk += GW) {
+        if (lane == 0 && i + S - 1 < n_my) {
+            int sn = stage + S - 1;
+            if (sn >= S) sn -= S;
+            issue(sn, pk + (long long)(S - 1) * GW);
+        }
+        const long long c0 = P.case_lo + pk * CPW;
+        const int ncs = pack_cases(pk);
+        const long long c = c0 + cg;
+        double* st = ring + (size_t)stage * P.stage_doubles;
+        const uint32_t st_u32 = ring_u32 + (uint32_t)stage * stage_bytes;
+        double* fs = st + P.off_f;                 // [CPW][nk]   fk rows of the pack
+        double* ks = st + P.off_xk;                // [CPW][nkn]  known values of the pack
+        if (!f_by_tma(ncs)) {
+            for (int t = lane; t < ncs * nk; t += 32) {
+                const int ci = t / nk, k = t - ci * nk;
+                fs[t] = ld_stream(P.fk + (c0 + ci) * P.fk_s0 + (long long)k * P.fk_s1);
+            }
+        }
+        const bool valid = cg < ncs && o < no;
+        const bool isk = (knowns >> o) & 1LL;
+        const int below = __popcll(knowns & ((1LL << o) - 1));
+        const int j = o - below;
+        if (nkn && valid && isk) ks[cg * nkn + below] = g;
+        // the next pack's knowns pattern and known values travel while this one is being worked on
+        long long kn_next = u.knowns;
+        double g_next = 0.0;
+        if (i + 1 < n_my && (nkn || P.meta)) load_slot(pk + GW, kn_next, g_next);
+        __syncwarp();
+        mbar_wait_u32(bars_u32 + (uint32_t)stage * 8u, phase);
+
+        // ---- fi[unknown slot] = its operator column . fext ------------------------------------------------
+        double v = g;
+        if (valid && !isk) {
+            double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+            const uint32_t rs8 = (uint32_t)nr * 8u;
+            uint32_t pa = st_u32 + (uint32_t)(cg * ops + j) * 8u;
+            uint32_t fa = st_u32 + (uint32_t)(P.off_f + cg * nk) * 8u;
+            int q = nk;
+            for (; q >= 4; q -= 4) {
+                const double x0 = lds_f64(pa), x1 = lds_f64(pa + rs8), x2 = lds_f64(pa + 2u * rs8), x3 = lds_f64(pa + 3u * rs8);
+                const double y0 = lds_f64(fa), y1 = lds_f64(fa + 8u), y2 = lds_f64(fa + 16u), y3 = lds_f64(fa + 24u);
+                a0 = fma(x0, y0, a0);
+                a1 = fma(x1, y1, a1);
+                a2 = fma(x2, y2, a2);
+                a3 = fma(x3, y3, a3);
+                pa += 4u * rs8;
+                fa += 32u;
+            }
+            for (; q > 0; --q) {
+                a0 = fma(lds_f64(pa), lds_f64(fa), a0);
+                pa += rs8;
+                fa += 8u;
+            }
+            uint32_t ka = st_u32 + (uint32_t)(P.off_xk + cg * nkn) * 8u;
+            for (int m = 0; m < nkn; ++m) {
+                a1 = fma(lds_f64(pa), lds_f64(ka), a1);
+                pa += rs8;
+                ka += 8u;
+            }
+            v = (a0 + a1) + (a2 + a3);
+        }
+        if (valid) {
+            P.fi_case[c * P.fi_case_ld + o] = v;
+            if (P.fi_out && !isk) P.fi_out[c * P.fi_out_s0 + o] = v;
+        }
+        // ---- sensitivities: the operator itself, re-indexed by DOF slot (impl.pyx:838-846) ----------------
+        if (SENS && nr > 0) {
+            const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+            if (valid) {
+                double* sp = P.sens + c * P.sens_s0 + o;
+                const double* opp = st + cg * ops + j;
+                for (int k = 0; k < nk; ++k) {
+                    st_stream(sp, isk ? qnan : *opp);
+                    sp += P.sens_s1;
+                    opp += nr;
+                }
+            }
+        }
+        __syncwarp();   // every lane is done with this stage before lane 0 re-arms it
+        if (++stage == S) { stage = 0; phase ^= 1u; }
+        knowns = kn_next;
+        g = g_next;
+    }
+}
+
+cudaError_t launch_solve_pack(const SolveParams& P, int blocks, int threads, size_t smem, cudaStream_t st) {
+    cudaError_t e;
+    if (P.sens) {
+        e = cudaFuncSetAttribute(solve_pack_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        solve_pack_kernel<true><<<blocks, threads, smem, st>>>(P);
+    } else {
+        e = cudaFuncSetAttribute(solve_pack_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        solve_pack_kernel<false><<<blocks, threads, smem, st>>>(P);
+    }
+    return cudaGetLastError();
+}
+
 // Deferred write-back (expert.pyx:548-557): caller's fi <- solver-owned copy, first no_j columns.
 __global__ void scatter_fi_kernel(const CaseMeta* meta, CaseMeta uni, long long ncases, const double* fi_case,
                                   int ld, double* fi_out, long long s0) {
@@ -382,7 +549,7 @@ static cudaError_t launch_one(const SolveParams& P, int blocks, int threads, siz
 
 template <int DIM, bool ITER>
 static cudaError_t launch_su(const SolveParams& P, int blocks, int threads, size_t smem, cudaStream_t st) {
-    const bool sens = P.sens != nullptr, uni = P.meta == nullptr;
+    const bool sens = P.sens != nullptr, uni = P.meta == nullptr || P.geom_uniform;
     if (sens) return uni ? launch_one<DIM, ITER, true, true>(P, blocks, threads, smem, st)
                          : launch_one<DIM, ITER, true, false>(P, blocks, threads, smem, st);
     return uni ? launch_one<DIM, ITER, false, true>(P, blocks, threads, smem, st)
