@@ -1,0 +1,214 @@
+"""GPU parity tests of the kernel variants behind the same API (all through the C ABI):
+
+* the packed solve kernel (several small cases per warp pass): tail packs, mixed knowns patterns with the same
+  sizes ("geometry-uniform" batches), strided fk (no bulk copy), sensitivities;
+* the register/DMMA prepare kernel: several fits per warp through the row phases with odd case counts,
+  all-known cases mixed in, and the shared-memory variant as a second implementation of the same arithmetic;
+* the interpolation kernel: staged (transposed) and direct all-slots output, pitched output rows, per-model
+  orders, 3D.
+
+Tolerances as in tests/test_gpu_parity.py (tests/parity.py states the criterion).
+"""
+import os
+
+import numpy as np
+import pytest
+
+import parity
+import oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+wlsqm = pytest.importorskip("wlsqm_b200")
+
+
+def _scaled_err(got, ref):
+    sc = np.abs(ref).max(axis=0)
+    sc[sc == 0] = 1.0
+    return np.abs(got - ref) / sc
+
+
+def _solve_gpu(dim, nk, od, kn, wm, x, xk, fk, fi0, do_sens=False, algorithm=1, max_iter=3):
+    s = wlsqm.ExpertSolver(dim, nk, od, kn, wm, algorithm=algorithm, do_sens=do_sens, max_iter=max_iter)
+    s.prepare(x, xk)
+    fi = fi0.copy()
+    sens = np.zeros((len(nk), xk.shape[1], fi.shape[1])) if do_sens else None
+    s.solve(fk, fi, sens)
+    return fi, sens, s
+
+
+PACK_CASES = [
+    # dim, order, k, knowns patterns (same popcount), n
+    pytest.param(1, 3, 8, (0b0001, 0b0010), 4001, id="1D-o3-k8-F-or-X-known"),
+    pytest.param(1, 2, 5, (0,), 1003, id="1D-o2-k5"),
+    pytest.param(2, 2, 12, (0b000001, 0b000100, 0b100000), 3001, id="2D-o2-k12-one-known"),
+    pytest.param(2, 3, 24, (0b1, 0b100), 2001, id="cfg4-2D-o3-k24-F-or-Y-known"),
+    pytest.param(2, 1, 7, (0b011, 0b101), 999, id="2D-o1-k7-two-knowns"),
+    pytest.param(3, 1, 9, (0,), 2005, id="3D-o1-k9"),
+    pytest.param(3, 2, 21, (0b1, 0b1000000000), 1501, id="3D-o2-k21-one-known"),
+]
+
+
+@pytest.mark.parametrize("dim,order,k,patterns,n", PACK_CASES)
+def test_packed_solve_vs_oracle(dim, order, k, patterns, n):
+    x, hoods, f = parity.make_case(n, dim, k)
+    xk, fk = parity.gathered(x, f, hoods)
+    no = wlsqm.number_of_dofs(dim, order)
+    rng = np.random.default_rng(1)
+    kn = np.array(patterns, np.int64)[rng.integers(0, len(patterns), n)]
+    nk, od, wm = np.full(n, k, np.int32), np.full(n, order, np.int32), np.full(n, wlsqm.WEIGHT_CENTER, np.int32)
+    fi0 = 0.1 * rng.standard_normal((n, no))
+    fi0[:, 0] = f
+    fi_g, sens_g, _ = _solve_gpu(dim, nk, od, kn, wm, x, xk, fk, fi0, do_sens=True)
+    fi_o, sens_o, _, _ = parity.oracle_solve(dim, nk, od, kn, wm, x, xk, fk, fi0, 1, True)
+    for o in range(no):     # known slots are left untouched, bit for bit
+        m = (kn >> o & 1).astype(bool)
+        assert np.array_equal(fi_g[m, o], fi0[m, o])
+    e = _scaled_err(fi_g, fi_o)
+    assert np.median(e) < 1e-11 and np.quantile(e, 0.99) < 1e-7, (np.median(e), e.max())
+    parity.check_sens(sens_g, sens_o, "packed")
+
+
+def test_packed_solve_strided_fk_and_device_tensors():
+    """fk rows that are not dense (no bulk copy possible) and an fi with extra columns, on the device"""
+    torch = pytest.importorskip("torch")
+    n, k, dim, order = 2503, 8, 1, 3
+    x, hoods, f = parity.make_case(n, dim, k)
+    xk, fk = parity.gathered(x, f, hoods)
+    nk, od, kn, wm = (np.full(n, k, np.int32), np.full(n, order, np.int32), np.full(n, 1, np.int64),
+                      np.full(n, 1, np.int32))
+    fi0 = np.zeros((n, 4))
+    fi0[:, 0] = f
+    fi_ref, _, _ = _solve_gpu(dim, nk, od, kn, wm, x, xk, fk, fi0)
+    s = wlsqm.ExpertSolver(dim, nk, od, kn, wm)
+    s.prepare(torch.from_numpy(x).cuda(), torch.from_numpy(xk).cuda())
+    fk_wide = torch.zeros((n, k + 3), dtype=torch.float64, device="cuda")
+    fk_wide[:, :k] = torch.from_numpy(fk).cuda()
+    fi_wide = torch.full((n, 7), 7.0, dtype=torch.float64, device="cuda")
+    fi_wide[:, :4] = torch.from_numpy(fi0).cuda()
+    s.solve(fk_wide[:, :k], fi_wide[:, :4])
+    torch.cuda.synchronize()
+    got = fi_wide.cpu().numpy()
+    assert np.array_equal(got[:, :4], fi_ref)
+    assert (got[:, 4:] == 7.0).all()
+
+
+def test_packed_and_one_case_per_warp_kernels_agree():
+    """the two solve kernels apply the same operator; only the summation order over the neighbours differs"""
+    n, k, dim, order = 3001, 24, 2, 3
+    x, hoods, f = parity.make_case(n, dim, k)
+    xk, fk = parity.gathered(x, f, hoods)
+    nk, od, kn, wm = (np.full(n, k, np.int32), np.full(n, order, np.int32), np.full(n, 1, np.int64),
+                      np.full(n, 2, np.int32))
+    fi0 = np.zeros((n, 10))
+    fi0[:, 0] = f
+    fi_pack, _, _ = _solve_gpu(dim, nk, od, kn, wm, x, xk, fk, fi0)
+    os.environ["WLSQM_SOLVE_NOPACK"] = "1"
+    try:
+        fi_warp, _, _ = _solve_gpu(dim, nk, od, kn, wm, x, xk, fk, fi0)
+    finally:
+        del os.environ["WLSQM_SOLVE_NOPACK"]
+    e = _scaled_err(fi_pack, fi_warp)
+    # the operator entries of the higher derivatives cancel heavily: re-association noise is cond * eps
+    assert np.median(e) < 1e-13 and e.max() < 1e-8, (np.median(e), e.max())
+
+
+def test_geometry_uniform_batch_large_model():
+    """2D order 4 with the known slot varying from case to case: uniform sizes, per-case knowns pattern"""
+    n, k, dim, order = 3001, 30, 2, 4
+    x, hoods, f = parity.make_case(n, dim, k)
+    xk, fk = parity.gathered(x, f, hoods)
+    rng = np.random.default_rng(2)
+    kn = np.array([wlsqm.b2_F, wlsqm.b2_X, wlsqm.b2_Y2], np.int64)[rng.integers(0, 3, n)]
+    nk, od, wm = np.full(n, k, np.int32), np.full(n, order, np.int32), np.full(n, 1, np.int32)
+    fi0 = 0.05 * rng.standard_normal((n, 15))
+    fi0[:, 0] = f
+    for algo in (wlsqm.ALGO_BASIC, wlsqm.ALGO_ITERATIVE):
+        fi_g, sens_g, _ = _solve_gpu(dim, nk, od, kn, wm, x, xk, fk, fi0, do_sens=True, algorithm=algo)
+        fi_o, sens_o, _, _ = parity.oracle_solve(dim, nk, od, kn, wm, x, xk, fk, fi0, algo, True, 3)
+        for o in range(15):
+            m = (kn >> o & 1).astype(bool)
+            assert np.array_equal(fi_g[m, o], fi0[m, o])
+        e = _scaled_err(fi_g, fi_o)
+        assert np.median(e) < 1e-9 and np.quantile(e, 0.99) < 1e-5, (algo, np.median(e), e.max())
+        parity.check_sens(sens_g, sens_o, "geometry-uniform")
+
+
+@pytest.mark.parametrize("dim,order,k,n", [(2, 4, 30, 1001), (2, 2, 12, 1003), (1, 3, 8, 1002), (3, 1, 10, 1001),
+                                            (3, 3, 40, 301), (3, 4, 60, 151)])
+def test_prepare_variants_agree_and_odd_counts(dim, order, k, n):
+    """register/DMMA kernel (several fits per warp) vs the shared-memory kernel on the same inputs, with a case
+    count that leaves the last warp pass partly empty and with all-known cases (silent no-ops) mixed in"""
+    x, hoods, f = parity.make_case(n, dim, k)
+    xk, fk = parity.gathered(x, f, hoods)
+    no = wlsqm.number_of_dofs(dim, order)
+    nk, od, wm = np.full(n, k, np.int32), np.full(n, order, np.int32), np.full(n, 2, np.int32)
+    kn = np.zeros(n, np.int64)
+    kn[3::11] = 1
+    kn[::7] = (1 << no) - 1          # everything known: the fit is a no-op
+    fi0 = np.zeros((n, no))
+    fi0[:, 0] = f
+    fi0[::7] = 3.25
+    fi_reg, _, _ = _solve_gpu(dim, nk, od, kn, wm, x, xk, fk, fi0)
+    os.environ["WLSQM_PREP_KERNEL"] = "smem"
+    try:
+        fi_smem, _, _ = _solve_gpu(dim, nk, od, kn, wm, x, xk, fk, fi0)
+    finally:
+        del os.environ["WLSQM_PREP_KERNEL"]
+    assert np.array_equal(fi_reg[::7], fi0[::7])
+    fi_o, _, _, _ = parity.oracle_solve(dim, nk, od, kn, wm, x, xk, fk, fi0)
+    a, b = parity.permuted_self_noise(dim, nk, od, kn, wm, x, xk, fk, fi0)
+    parity.check_against_floor(fi_reg, fi_o, b + (fi_o - a), dim, order, "reg-vs-oracle")
+    parity.check_against_floor(fi_smem, fi_o, b + (fi_o - a), dim, order, "smem-vs-oracle")
+
+
+def test_interpolate_variants():
+    """all-slots output: staged (dense rows) == direct (pitched rows) == one call per slot; odd query count"""
+    torch = pytest.importorskip("torch")
+    for dim, order, k, n in ((2, 4, 30, 700), (3, 3, 40, 300), (1, 4, 9, 500)):
+        x, hoods, f = parity.make_case(n, dim, k)
+        xk, fk = parity.gathered(x, f, hoods)
+        no = wlsqm.number_of_dofs(dim, order)
+        nk, od, kn, wm = (np.full(n, k, np.int32), np.full(n, order, np.int32), np.zeros(n, np.int64),
+                          np.full(n, 2, np.int32))
+        fi_g, _, s = _solve_gpu(dim, nk, od, kn, wm, x, xk, fk, np.zeros((n, no)))
+        rng = np.random.default_rng(9)
+        nq = 4 * n + 37
+        I = rng.integers(0, n, nq).astype(np.int64)
+        xq = x[I] + 1e-3 * rng.uniform(-1, 1, (nq,) + x.shape[1:])
+        s.prep_interpolate()
+        out_all, _ = s.interpolate(xq, diff='all', I=I)
+        so = orc.OracleSolver(dim, nk, od, kn, wm)
+        so.xi = x
+        so.fi = fi_g.copy()
+        for d in range(no):
+            o1, _ = s.interpolate(xq, diff=d, I=I)
+            assert np.array_equal(o1, out_all[:, d]), (dim, d)
+            oo = so.interpolate(xq, I, d)
+            assert np.abs(o1 - oo).max() <= 1e-12 * max(np.abs(oo).max(), 1e-300), (dim, d)
+        # device tensors: dense rows take the staged path, the library's own buffer for host output as well
+        xq_t, I_t = torch.from_numpy(xq).cuda(), torch.from_numpy(I).cuda()
+        out_t, _ = s.interpolate(xq_t, diff='all', I=I_t)
+        torch.cuda.synchronize()
+        assert np.array_equal(out_t.cpu().numpy(), out_all)
+
+
+def test_interpolate_per_model_orders():
+    n, k, dim = 1200, 30, 2
+    x, hoods, f = parity.make_case(n, dim, k)
+    xk, fk = parity.gathered(x, f, hoods)
+    rng = np.random.default_rng(4)
+    od = rng.integers(1, 5, n).astype(np.int32)
+    nk, kn, wm = np.full(n, k, np.int32), np.zeros(n, np.int64), np.full(n, 1, np.int32)
+    fi_g, _, s = _solve_gpu(dim, nk, od, kn, wm, x, xk, fk, np.zeros((n, 15)))
+    nq = 3001
+    I = rng.integers(0, n, nq).astype(np.int64)
+    xq = x[I] + 1e-3 * rng.uniform(-1, 1, (nq, 2))
+    s.prep_interpolate()
+    so = orc.OracleSolver(dim, nk, od, kn, wm)
+    so.xi = x
+    so.fi = fi_g.copy()
+    for d in (0, wlsqm.i2_X, wlsqm.i2_XY, wlsqm.i2_Y3, wlsqm.i2_X2Y2):
+        og, _ = s.interpolate(xq, diff=d, I=I)
+        oo = so.interpolate(xq, I, d)
+        assert np.abs(og - oo).max() <= 1e-12 * max(np.abs(oo).max(), 1e-300), d
