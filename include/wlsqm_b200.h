@@ -132,6 +132,46 @@ WLSQM_API int wlsqm_fit_many(int dimension, int64_t ncases, const double* xk, in
 WLSQM_API int wlsqm_interpolate_fit(int dimension, int order, const double* xi, const double* fi, const double* x,
                           int64_t x_s0, int64_t nx, int diff, double* out, int device);
 
+/* ---- spatial search on the device (the caller-side cKDTree steps either side of the fitting path) ----------
+ * The reference has no such functions: its callers build neighbourhoods with scipy.spatial.cKDTree
+ * (examples/expertsolver_example.py:51-66, examples/wlsqm_example.py:100-132) and ExpertSolver searches the
+ * nearest / all nearby local models with it (expert.pyx:676-681, 837, 898-911).  These entry points do the same
+ * searches on the device. */
+typedef struct wlsqm_grid wlsqm_grid_t;
+
+/* uniform search grid over n points x [n][dim] (row stride x_s0; host or device memory) */
+WLSQM_API int wlsqm_grid_create(int dimension, int64_t n, const double* x, int64_t x_s0, int device, wlsqm_grid_t** out);
+WLSQM_API int wlsqm_grid_destroy(wlsqm_grid_t* g);
+WLSQM_API int wlsqm_grid_info(wlsqm_grid_t* g, int64_t* ncells, double* cell_size, int64_t* bytes);
+
+/* k nearest grid points of every query, ordered by (distance, index) -- cKDTree.query(xq, k).  xq == NULL: the
+ * queries are the grid's own points (nq is ignored) and exclude_self drops each point from its own list, i.e.
+ * tree.query(x, k+1)[1][:, 1:].  Outputs [nq][k], any of them may be NULL: indices as int32 and/or int64, squared
+ * distances.  Missing neighbours (fewer than k points, NaN query) are reported as index n, distance inf. */
+WLSQM_API int wlsqm_grid_knn(wlsqm_grid_t* g, const double* xq, int64_t xq_s0, int64_t nq, int k, int exclude_self,
+                   int32_t* idx32, int64_t* idx64, double* d2);
+
+/* x[hoods] / f[hoods]: dst[i][k][0..w) = src[idx[i][k]][0..w)  (the caller-side gathers of the examples).
+ * src [nsrc][w] (row stride src_s0), idx int32 [n][k] (row stride idx_s0), dst [n][k][w] dense. */
+WLSQM_API int wlsqm_gather_hoods(const double* src, int64_t src_s0, int w, const int32_t* idx, int64_t idx_s0, int64_t n,
+                       int k, double* dst, int device, void* cuda_stream);
+
+/* prepare / solve with the neighbourhoods given as index lists (extension): hoods int32 [ncases][>= max nk] into the
+ * point array x [npoints][dim] / the per-point data f [npoints]; xk = x[hoods] and fk = f[hoods] are gathered on
+ * the device.  xi == NULL: the origins are the first ncases points of x.  solve_hoods takes fi / sens like solve. */
+WLSQM_API int wlsqm_solver_prepare_hoods(wlsqm_solver_t* s, const double* x, int64_t x_s0, int64_t npoints,
+                               const int32_t* hoods, int64_t hoods_s0, const double* xi, int64_t xi_s0);
+WLSQM_API int wlsqm_solver_solve_hoods(wlsqm_solver_t* s, const double* f, int64_t f_s0, double* fi, int64_t fi_s0,
+                             double* sens, int64_t sens_s0, int64_t sens_s1, int32_t* iters_out);
+
+/* ExpertSolver.prep_interpolate on the device: index the solver's model origins with a search grid, then
+ * interpolate(mode='nearest') may be called with I == NULL, and mode='continuous' is available:
+ * weighted average over every model within r, weights (1 - sqrt(d2/r2))^2 (expert.pyx:898-985). */
+WLSQM_API int wlsqm_solver_index_models(wlsqm_solver_t* s);
+WLSQM_API int wlsqm_solver_nearest_models(wlsqm_solver_t* s, const double* x, int64_t x_s0, int64_t nx, int64_t* I_out);
+WLSQM_API int wlsqm_solver_interpolate_continuous(wlsqm_solver_t* s, const double* x, int64_t x_s0, int64_t nx, double r,
+                                        int diff, double* out);
+
 /* ---- batched general drivers: wlsqm/utils/lapackdrivers.pyx:1551-1723 ------------------------------ */
 /* A (n,n,nlhs) Fortran-contiguous, b (n,nlhs) Fortran, ipiv (n,nlhs) int32 Fortran, 1-based; in place. */
 WLSQM_API int wlsqm_mgetrf(int n, int64_t nlhs, double* A, int32_t* ipiv, int device);                 /* mgeneralfactor[p] */

@@ -14,6 +14,11 @@
 #include "../../include/wlsqm_b200.h"
 #include "wlsqm_common.cuh"
 #include "wlsqm_kernels.h"
+#include "wlsqm_grid.h"
+
+namespace wlsqm {
+GridView grid_view(const wlsqm_grid* g);
+}
 
 using namespace wlsqm;
 
@@ -30,6 +35,12 @@ int fail(int code, const char* fmt, ...) {
     g_err = buf;
     return code;
 }
+
+}  // namespace
+namespace wlsqm {
+void set_last_error(const char* msg) { g_err = msg ? msg : ""; }
+}  // namespace wlsqm
+namespace {
 
 #define CU(expr)                                                                                   \
     do {                                                                                           \
@@ -84,6 +95,19 @@ struct DevBuf {
     }
 };
 
+// dst[i][k][0..w) = src[idx[i][k]][0..w)
+__global__ void gather_hoods_kernel(const double* __restrict__ src, long long src_s0, int w, const int32_t* __restrict__ idx,
+                                    long long idx_s0, long long n, int k, double* __restrict__ dst) {
+    const long long per = (long long)k * w;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n * per;
+         t += (long long)gridDim.x * blockDim.x) {
+        const long long i = t / per;
+        const int r = (int)(t - i * per);
+        const int kk = r / w, d = r - kk * w;
+        dst[t] = src[(long long)idx[i * idx_s0 + kk] * src_s0 + d];
+    }
+}
+
 // strided 3-level copy  dst[i][a][b] <- src[i*s0 + a*s1 + b*s2], dst dense
 __global__ void gather3_kernel(double* __restrict__ dst, const double* __restrict__ src, long long n, int na, int nb,
                                long long s0, long long s1, long long s2) {
@@ -124,6 +148,9 @@ struct wlsqm_solver {
     int sm_count = 148;
     DevBuf xk_keep;             // dense copy of xk (ALGO_ITERATIVE needs the geometry at solve time)
     DevBuf st_xk, st_fk, st_fi, st_sens, st_x, st_I, st_out;
+    DevBuf hoods_dev, hood_x, hood_f, hood_fk;   // prepare_hoods / solve_hoods: neighbour lists and gathered data
+    long long hood_points = 0;
+    wlsqm_grid* models_grid = nullptr;           // search grid over the model origins (index_models)
     long long bytes_state = 0;
 };
 
@@ -131,7 +158,7 @@ namespace {
 
 long long staging_bytes(const wlsqm_solver* s) {
     return (long long)(s->xk_keep.cap + s->st_xk.cap + s->st_fk.cap + s->st_fi.cap + s->st_sens.cap + s->st_x.cap +
-                       s->st_I.cap + s->st_out.cap);
+                       s->st_I.cap + s->st_out.cap + s->hoods_dev.cap + s->hood_x.cap + s->hood_f.cap + s->hood_fk.cap);
 }
 
 int use_device(const wlsqm_solver* s) {
@@ -486,6 +513,8 @@ int wlsqm_solver_destroy(wlsqm_solver_t* s) {
     cudaFree(s->As); cudaFree(s->iters_dev);
     s->xk_keep.release(); s->st_xk.release(); s->st_fk.release(); s->st_fi.release(); s->st_sens.release();
     s->st_x.release(); s->st_I.release(); s->st_out.release();
+    s->hoods_dev.release(); s->hood_x.release(); s->hood_f.release(); s->hood_fk.release();
+    if (s->models_grid) { wlsqm_grid_destroy(s->models_grid); s->models_grid = nullptr; }
     if (s->own_stream && s->stream) cudaStreamDestroy(s->stream);
     if (s->s_in) cudaStreamDestroy(s->s_in);
     if (s->s_out) cudaStreamDestroy(s->s_out);
@@ -519,6 +548,7 @@ int wlsqm_solver_prepare(wlsqm_solver_t* s, const double* xi, int64_t xi_s0, con
                          int64_t xk_s1) {
     if (!s) return fail(WLSQM_E_VALUE, "NULL solver");
     s->ready = false;
+    if (s->models_grid) { wlsqm_grid_destroy(s->models_grid); s->models_grid = nullptr; }   // the origins may move
     if (s->ncases == 0) { s->ready = true; return WLSQM_OK; }
     if (!xi || !xk) return fail(WLSQM_E_VALUE, "xi and xk must not be NULL");
     int rc = use_device(s);
@@ -770,7 +800,7 @@ int wlsqm_solver_interpolate(wlsqm_solver_t* s, const double* x, int64_t x_s0, c
     const bool x_dev = is_device_ptr(x), I_dev = is_device_ptr(I), out_dev = is_device_ptr(out);
     const long long ow = diff == WLSQM_DIFF_ALL ? s->maxno : 1;
     InterpParams P{};
-    P.dim = s->dim; P.nx = nx; P.diff = diff;
+    P.dim = s->dim; P.nx = nx; P.diff = diff; P.nmodels = s->ncases;
     P.xi = s->xi_dev; P.xi_s0 = s->dim; P.fi = s->fi_case; P.fi_s0 = s->maxno;
     P.order = s->dorder; P.order_uniform = s->uni.order;
     if (x_dev) { P.x = x; P.x_s0 = x_s0; }
@@ -841,6 +871,153 @@ int wlsqm_solver_get_fi(wlsqm_solver_t* s, double* out, int64_t out_s0) {
     rc = from_dense(out, out_s0, s->fi_case, s->maxno, s->ncases, s->maxno, s->stream);
     if (rc) return rc;
     CU(cudaStreamSynchronize(s->stream));
+    return WLSQM_OK;
+}
+
+int wlsqm_gather_hoods(const double* src, int64_t src_s0, int w, const int32_t* idx, int64_t idx_s0, int64_t n, int k,
+                       double* dst, int device, void* cuda_stream) {
+    if (n == 0 || k == 0 || w == 0) return WLSQM_OK;
+    if (!src || !idx || !dst) return fail(WLSQM_E_VALUE, "NULL argument");
+    if (!is_device_ptr(src) || !is_device_ptr(idx) || !is_device_ptr(dst))
+        return fail(WLSQM_E_VALUE, "wlsqm_gather_hoods works on device arrays");
+    CU(cudaSetDevice(device));
+    const long long total = (long long)n * k * w;
+    const unsigned blocks = (unsigned)std::min<long long>((total + 255) / 256, 148LL * 32);
+    gather_hoods_kernel<<<blocks, 256, 0, (cudaStream_t)cuda_stream>>>(src, src_s0, w, idx, idx_s0, n, k, dst);
+    CU(cudaGetLastError());
+    return WLSQM_OK;
+}
+
+// ExpertSolver.prepare with the neighbourhoods given as index lists into a point array: xk = x[hoods] is
+// gathered on the device (the caller-side gather of examples/expertsolver_example.py:59-66).
+int wlsqm_solver_prepare_hoods(wlsqm_solver_t* s, const double* x, int64_t x_s0, int64_t npoints, const int32_t* hoods,
+                               int64_t hoods_s0, const double* xi, int64_t xi_s0) {
+    if (!s) return fail(WLSQM_E_VALUE, "NULL solver");
+    if (s->ncases == 0) return wlsqm_solver_prepare(s, x, x_s0, x, 0, 0);
+    if (!x || !hoods) return fail(WLSQM_E_VALUE, "x and hoods must not be NULL");
+    if (!xi && npoints < s->ncases) return fail(WLSQM_E_VALUE, "without xi, x must hold one point per case");
+    int rc = use_device(s);
+    if (rc) return rc;
+    const int dim = s->dim;
+    const long long n = s->ncases;
+    cudaStream_t st = s->stream;
+    const double* xd = x;
+    long long xs0 = x_s0;
+    if (!is_device_ptr(x)) {
+        rc = s->hood_x.reserve((size_t)npoints * dim * 8);
+        if (rc) return rc;
+        rc = to_dense((double*)s->hood_x.p, x, npoints, dim, x_s0, st);
+        if (rc) return rc;
+        xd = (const double*)s->hood_x.p;
+        xs0 = dim;
+    }
+    rc = s->hoods_dev.reserve((size_t)n * s->maxnk * 4);
+    if (rc) return rc;
+    CU(cudaMemcpy2DAsync(s->hoods_dev.p, (size_t)s->maxnk * 4, hoods, (size_t)hoods_s0 * 4, (size_t)s->maxnk * 4, (size_t)n,
+                         cudaMemcpyDefault, st));
+    s->hood_points = npoints;
+    rc = s->st_xk.reserve((size_t)n * s->maxnk * dim * 8);
+    if (rc) return rc;
+    const long long total = n * s->maxnk * dim;
+    gather_hoods_kernel<<<(unsigned)std::min<long long>((total + 255) / 256, (long long)s->sm_count * 32), 256, 0, st>>>(
+        xd, xs0, dim, (const int32_t*)s->hoods_dev.p, s->maxnk, n, s->maxnk, (double*)s->st_xk.p);
+    CU(cudaGetLastError());
+    const double* xi_use = xi ? xi : xd;
+    const long long xi_use_s0 = xi ? xi_s0 : xs0;
+    rc = wlsqm_solver_prepare(s, xi_use, xi_use_s0, (const double*)s->st_xk.p, (long long)s->maxnk * dim, dim);
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(st));
+    s->st_xk.release();      // (ALGO_ITERATIVE keeps its own copy of the geometry)
+    s->hood_x.release();
+    return WLSQM_OK;
+}
+
+// ExpertSolver.solve with the data given per point: fk = f[hoods] is gathered on the device, so that a time step
+// moves one value per point to the GPU instead of one per (point, neighbour).
+int wlsqm_solver_solve_hoods(wlsqm_solver_t* s, const double* f, int64_t f_s0, double* fi, int64_t fi_s0, double* sens,
+                             int64_t sens_s0, int64_t sens_s1, int32_t* iters_out) {
+    if (!s) return fail(WLSQM_E_VALUE, "NULL solver");
+    if (!s->ready) return fail(WLSQM_E_NOTREADY, "Solver is not in the ready state; prepare() must be called before solve()");
+    if (s->ncases == 0) { if (iters_out) *iters_out = 0; return WLSQM_OK; }
+    if (!s->hoods_dev.p) return fail(WLSQM_E_NOTREADY, "solve_hoods() needs the neighbour lists of prepare_hoods()");
+    if (!f) return fail(WLSQM_E_VALUE, "f must not be NULL");
+    int rc = use_device(s);
+    if (rc) return rc;
+    cudaStream_t st = s->stream;
+    const long long n = s->ncases;
+    const double* fd = f;
+    long long fs0 = f_s0;
+    if (!is_device_ptr(f)) {
+        rc = s->hood_f.reserve((size_t)s->hood_points * 8);
+        if (rc) return rc;
+        rc = to_dense((double*)s->hood_f.p, f, s->hood_points, 1, f_s0, st);
+        if (rc) return rc;
+        fd = (const double*)s->hood_f.p;
+        fs0 = 1;
+    }
+    rc = s->hood_fk.reserve((size_t)n * s->maxnk * 8);
+    if (rc) return rc;
+    const long long total = n * s->maxnk;
+    gather_hoods_kernel<<<(unsigned)std::min<long long>((total + 255) / 256, (long long)s->sm_count * 32), 256, 0, st>>>(
+        fd, fs0, 1, (const int32_t*)s->hoods_dev.p, s->maxnk, n, s->maxnk, (double*)s->hood_fk.p);
+    CU(cudaGetLastError());
+    return wlsqm_solver_solve(s, (const double*)s->hood_fk.p, s->maxnk, 1, fi, fi_s0, sens, sens_s0, sens_s1, iters_out);
+}
+
+int wlsqm_solver_index_models(wlsqm_solver_t* s) {
+    if (!s) return fail(WLSQM_E_VALUE, "NULL solver");
+    if (!s->ready) return fail(WLSQM_E_NOTREADY, "Solver is not in the ready state; prepare() must be called before prep_interpolate()");
+    if (s->models_grid || s->ncases == 0) return WLSQM_OK;
+    int rc = use_device(s);
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(s->stream));
+    return wlsqm_grid_create(s->dim, s->ncases, s->xi_dev, s->dim, s->device, &s->models_grid);
+}
+
+int wlsqm_solver_nearest_models(wlsqm_solver_t* s, const double* x, int64_t x_s0, int64_t nx, int64_t* I_out) {
+    if (!s) return fail(WLSQM_E_VALUE, "NULL solver");
+    if (!s->models_grid) return fail(WLSQM_E_NOTREADY, "Points xi have not been indexed; prep_interpolate() must be called before interpolate()");
+    if (nx == 0) return WLSQM_OK;
+    if (!x || !I_out) return fail(WLSQM_E_VALUE, "NULL argument");
+    return wlsqm_grid_knn(s->models_grid, x, x_s0, nx, 1, 0, nullptr, I_out, nullptr);
+}
+
+int wlsqm_solver_interpolate_continuous(wlsqm_solver_t* s, const double* x, int64_t x_s0, int64_t nx, double r, int diff,
+                                        double* out) {
+    if (!s) return fail(WLSQM_E_VALUE, "NULL solver");
+    if (!s->ready) return fail(WLSQM_E_NOTREADY, "Solver is not in the ready state; prepare() must be called first");
+    if (!s->models_grid) return fail(WLSQM_E_NOTREADY, "Points xi have not been indexed; prep_interpolate() must be called before interpolate()");
+    if (nx == 0) return WLSQM_OK;
+    if (!x || !out) return fail(WLSQM_E_VALUE, "x and out must not be NULL");
+    if (!(r > 0.0)) return fail(WLSQM_E_VALUE, "r must be positive");
+    const int size = number_of_dofs(s->dim, 4);
+    if (diff < 0 || diff >= size) return fail(WLSQM_E_VALUE, "invalid diff %d", diff);
+    int rc = use_device(s);
+    if (rc) return rc;
+    cudaStream_t st = s->stream;
+    const bool x_dev = is_device_ptr(x), out_dev = is_device_ptr(out);
+    InterpParams P{};
+    P.dim = s->dim; P.nx = nx; P.diff = diff;
+    P.xi = s->xi_dev; P.xi_s0 = s->dim; P.fi = s->fi_case; P.fi_s0 = s->maxno;
+    P.order = s->dorder; P.order_uniform = s->uni.order;
+    if (x_dev) { P.x = x; P.x_s0 = x_s0; }
+    else {
+        rc = s->st_x.reserve((size_t)nx * s->dim * 8);
+        if (rc) return rc;
+        rc = to_dense((double*)s->st_x.p, x, nx, s->dim, x_s0, st);
+        if (rc) return rc;
+        P.x = (const double*)s->st_x.p; P.x_s0 = s->dim;
+    }
+    if (out_dev) P.out = out;
+    else {
+        rc = s->st_out.reserve((size_t)nx * 8);
+        if (rc) return rc;
+        P.out = (double*)s->st_out.p;
+    }
+    P.out_s0 = 1;
+    CU(launch_interpolate_continuous(P, grid_view(s->models_grid), r, st));
+    if (!out_dev) CU(cudaMemcpyAsync(out, s->st_out.p, (size_t)nx * 8, cudaMemcpyDeviceToHost, st));
+    if (!x_dev || !out_dev) CU(cudaStreamSynchronize(st));
     return WLSQM_OK;
 }
 

@@ -22,6 +22,7 @@
 #include <type_traits>
 #include "wlsqm_common.cuh"
 #include "wlsqm_kernels.h"
+#include "wlsqm_grid.h"
 
 namespace wlsqm {
 
@@ -78,7 +79,9 @@ __global__ void __launch_bounds__(INTERP_THREADS) interpolate_kernel(InterpParam
     for (int j = 0; j < Q; ++j) {
         const long long m = base + (long long)j * blockDim.x;
         const bool live = m < P.nx;
-        const long long i = idx[j];
+        // "no neighbour found" (index == number of models, cKDTree's convention for a NaN query) -> NaN
+        const bool bad = P.nmodels > 0 && (idx[j] < 0 || idx[j] >= P.nmodels);
+        const long long i = bad ? 0 : idx[j];
         const int order = P.order ? (int)P.order[i] : P.order_uniform;
         const int no = number_of_dofs(DIM, order);
         const double* xo = P.xi + i * P.xi_s0;
@@ -102,13 +105,14 @@ __global__ void __launch_bounds__(INTERP_THREADS) interpolate_kernel(InterpParam
                 constexpr int D = decltype(I)::value;
                 if (P.diff == D) v = eval_slot<DIM, D>(no, fi, mono);     // grid-uniform branch
             });
-            if (live) st_stream(P.out + m, v);
+            if (live) st_stream(P.out + m, bad ? __longlong_as_double(0x7ff8000000000000LL) : v);
         } else {
             // extension: every derivative slot of the model in one pass, out[m][0..no)
             double val[NO];
             static_for<0, NO>([&](auto I) {
                 constexpr int D = decltype(I)::value;
                 val[D] = eval_slot<DIM, D>(no, fi, mono);
+                if (bad) val[D] = __longlong_as_double(0x7ff8000000000000LL);
             });
             if constexpr (STAGE) {
                 // uniform model size and dense rows: transpose through shared memory, then contiguous stores
@@ -132,6 +136,73 @@ __global__ void __launch_bounds__(INTERP_THREADS) interpolate_kernel(InterpParam
             }
         }
     }
+}
+
+// mode='continuous' (expert_interpolate_continuous, wlsqm/fitter/expert.pyx:898-985): weighted average of every
+// local model whose origin lies within r of the query, weights (1 - sqrt(d2 / r2))^2 (alpha = 0, beta = 1,
+// expert.pyx:45-46).  The reference finds the models with cKDTree.query_ball_tree and loops in Python; here one
+// thread per query walks the cells of the model-origin grid that intersect its ball and evaluates on the fly.
+template <int DIM>
+__global__ void __launch_bounds__(128) continuous_kernel(InterpParams P, GridView g, double r) {
+    constexpr int NO = max_no<DIM>();
+    const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= P.nx) return;
+    double q[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) q[d] = P.x[m * P.x_s0 + d];
+    const double r2 = r * r;
+    int c0[3] = {0, 0, 0}, c1[3] = {0, 0, 0};
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) {
+        c0[d] = grid_cell_coord(g, d, q[d] - r);
+        c1[d] = grid_cell_coord(g, d, q[d] + r);
+    }
+    double acc = 0.0, sum_w = 0.0;
+    for (int cz = c0[2]; cz <= c1[2]; ++cz)
+        for (int cy = c0[1]; cy <= c1[1]; ++cy) {
+            const long long row = ((long long)cz * g.dims[1] + cy) * g.dims[0];
+            const int p1 = g.cell_start[row + c1[0] + 1];
+            for (int p = g.cell_start[row + c0[0]]; p < p1; ++p) {     // the cells of one x-row are contiguous
+                double d2 = 0.0, dq[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+                for (int d = 0; d < DIM; ++d) {
+                    dq[d] = q[d] - g.sorted_x[(long long)p * DIM + d];
+                    d2 += dq[d] * dq[d];
+                }
+                if (!(d2 <= r2)) continue;
+                const long long i = g.sorted_idx[p];
+                const int order = P.order ? (int)P.order[i] : P.order_uniform;
+                const int no = number_of_dofs(DIM, order);
+                const double* fg = P.fi + i * P.fi_s0;
+                double fi[NO], mono[NO];
+#pragma unroll
+                for (int s = 0; s < NO; ++s) fi[s] = s < no ? __ldg(fg + s) : 0.0;
+                const Pow5 px = scaled_powers(dq[0]), py = scaled_powers(dq[1]), pz = scaled_powers(dq[2]);
+                static_for<0, NO>([&](auto I) {
+                    constexpr int S = decltype(I)::value;
+                    mono[S] = monomial<DIM, S>(px, py, pz);
+                });
+                double value = 0.0;
+                static_for<0, NO>([&](auto I) {
+                    constexpr int D = decltype(I)::value;
+                    if (P.diff == D) value = eval_slot<DIM, D>(no, fi, mono);
+                });
+                const double tmp = 1.0 - sqrt(d2 / r2);
+                const double w = tmp * tmp;
+                acc += w * value;
+                sum_w += w;
+            }
+        }
+    P.out[m] = acc / sum_w;     // no model within r: 0/0 = NaN, like the reference
+}
+
+cudaError_t launch_interpolate_continuous(const InterpParams& P, const GridView& g, double r, cudaStream_t st) {
+    if (P.nx == 0) return cudaSuccess;
+    const unsigned blocks = (unsigned)((P.nx + 127) / 128);
+    if (P.dim == 1) continuous_kernel<1><<<blocks, 128, 0, st>>>(P, g, r);
+    else if (P.dim == 2) continuous_kernel<2><<<blocks, 128, 0, st>>>(P, g, r);
+    else continuous_kernel<3><<<blocks, 128, 0, st>>>(P, g, r);
+    return cudaGetLastError();
 }
 
 template <int DIM, bool ALL, bool STAGE>

@@ -71,6 +71,7 @@ struct InterpParams {
     long long nx;
     const double* x; long long x_s0;                 // [nx][dim]
     const long long* I;                              // [nx] model index, or nullptr (single model 0)
+    long long nmodels;                               // indices outside [0, nmodels) give NaN (0: not checked)
     const double* xi; long long xi_s0;               // model origins [nmodels][dim]
     const double* fi; long long fi_s0;               // model coefficients [nmodels][fi_s0]
     const signed char* order; int order_uniform;     // per-model order, or uniform
@@ -79,6 +80,9 @@ struct InterpParams {
     int stage_no;                                    // all slots, every model has stage_no DOFs and out_s0 == stage_no:
                                                      // results are transposed through shared memory (else 0)
 };
+
+// thread-local message behind wlsqm_last_error() (wlsqm_capi.cu)
+void set_last_error(const char* msg);
 
 cudaError_t launch_prepare_smem(int dim, const PrepareParams& P, int blocks, int threads, size_t smem, cudaStream_t st);
 int prep_reg_fit_doubles(int dim, int maxorder, int nb, int nkn_max);
@@ -92,6 +96,8 @@ cudaError_t launch_solve_pack(const SolveParams& P, int blocks, int threads, siz
 cudaError_t launch_scatter_fi(const CaseMeta* meta, const CaseMeta& uni, long long ncases, const double* fi_case,
                               int fi_case_ld, double* fi_out, long long fi_out_s0, cudaStream_t st);
 cudaError_t launch_interpolate(const InterpParams& P, cudaStream_t st);
+struct GridView;
+cudaError_t launch_interpolate_continuous(const InterpParams& P, const GridView& g, double r, cudaStream_t st);
 cudaError_t launch_getrf(int n, long long nlhs, double* A, int* ipiv, cudaStream_t st);
 cudaError_t launch_getrs(int n, long long nlhs, const double* LU, const int* ipiv, double* b, cudaStream_t st);
 cudaError_t launch_cond(int n_max, long long ncases, const CaseMeta* meta, const CaseMeta& uni, const double* As,

@@ -49,6 +49,16 @@ SIGNATURES = {
     "wlsqm_fit_many": (_int, [_int, _i64, _vp, _i64, _i64, _vp, _i64, _i64, _vp, _vp, _i64, _vp, _i64, _vp, _i64,
                               _i64, _int, _vp, _vp, _vp, _int, _int, _int, _i32p]),
     "wlsqm_interpolate_fit": (_int, [_int, _int, _vp, _vp, _vp, _i64, _i64, _int, _vp, _int]),
+    "wlsqm_grid_create": (_int, [_int, _i64, _vp, _i64, _int, C.POINTER(_vp)]),
+    "wlsqm_grid_destroy": (_int, [_vp]),
+    "wlsqm_grid_info": (_int, [_vp, _i64p, C.POINTER(C.c_double), _i64p]),
+    "wlsqm_grid_knn": (_int, [_vp, _vp, _i64, _i64, _int, _int, _vp, _vp, _vp]),
+    "wlsqm_gather_hoods": (_int, [_vp, _i64, _int, _vp, _i64, _i64, _int, _vp, _int, _vp]),
+    "wlsqm_solver_prepare_hoods": (_int, [_vp, _vp, _i64, _i64, _vp, _i64, _vp, _i64]),
+    "wlsqm_solver_solve_hoods": (_int, [_vp, _vp, _i64, _vp, _i64, _vp, _i64, _i64, _i32p]),
+    "wlsqm_solver_index_models": (_int, [_vp]),
+    "wlsqm_solver_nearest_models": (_int, [_vp, _vp, _i64, _i64, _vp]),
+    "wlsqm_solver_interpolate_continuous": (_int, [_vp, _vp, _i64, _i64, C.c_double, _int, _vp]),
     "wlsqm_mgetrf": (_int, [_int, _i64, _vp, _vp, _int]),
     "wlsqm_mgetrs": (_int, [_int, _i64, _vp, _vp, _vp, _int]),
     "wlsqm_mgesv": (_int, [_int, _i64, _vp, _vp, _vp, _int]),

@@ -207,6 +207,58 @@ class ExpertSolver:
         _lib.check(_lib.lib().wlsqm_solver_conds(self._handle, out.ctypes.data))
         return out
 
+    # -- neighbourhoods as index lists (extension) ----------------------------------------------------
+    def prepare_hoods(self, x, hoods, xi=None):
+        """``prepare(xi, x[hoods])`` with the gather done on the device (extension).
+
+        x: (npoints, dim) [1D: (npoints,)] float64; hoods: (ncases, >= max nk) int32 indices into x (numpy or
+        CUDA tensor, e.g. from ``PointGrid.knn``); xi: the origins, default ``x[:ncases]``."""
+        self.ready = False
+        from .. import neighbors
+        xa, npts, dim, x_s0 = neighbors._points(x)
+        if dim != self.dimension:
+            raise ValueError("x has %d coordinates, the solver has dimension %d" % (dim, self.dimension))
+        ha = _lib.as_arr(hoods, np.int32, 2, "hoods")
+        if ha.shape[0] < self.ncases or (self.ncases and ha.shape[1] < self._maxnk):
+            raise ValueError("hoods must have shape (>= ncases, >= max nk)")
+        xi_p, xi_s0 = None, 0
+        if xi is not None:
+            xia, nxi, dimi, xi_s0 = neighbors._points(xi, "xi")
+            if dimi != dim or nxi < self.ncases:
+                raise ValueError("xi must hold one origin per case")
+            xi_p = xia.ptr
+        elif npts < self.ncases:
+            raise ValueError("without xi, x must hold one point per case")
+        self._use_stream()
+        _lib.check(_lib.lib().wlsqm_solver_prepare_hoods(self._handle, xa.ptr, x_s0, npts, ha.ptr, ha.strides[0], xi_p, xi_s0))
+        self.xi = xi if xi is not None else x[:self.ncases]
+        self.xk, self.tree = None, None
+        self._hood_points = npts
+        self.ready = True
+
+    def solve_hoods(self, f, fi, sens=None):
+        """``solve(f[hoods], fi, sens)`` with the gather done on the device (extension; needs prepare_hoods).
+        f: (npoints,) float64 -- one value per point instead of one per (point, neighbour)."""
+        if not self.ready:
+            raise RuntimeError("Solver is not in the ready state; prepare() must be called before solve()")
+        fa = _lib.as_arr(f, np.float64, 1, "f", last_contig=False)
+        if fa.shape[0] < getattr(self, "_hood_points", 0):
+            raise ValueError("f must hold one value per point of the x given to prepare_hoods()")
+        fi_a = _lib.as_arr(fi, np.float64, 2, "fi", writable=True)
+        if fi_a.shape[0] < self.ncases or (self.ncases and fi_a.shape[1] < self._maxno):
+            raise ValueError("fi must have shape (>= ncases, >= %d)" % self._maxno)
+        sens_p, s0, s1 = None, 0, 0
+        if self.do_sens:
+            if sens is None:
+                raise ValueError("sens must be given when do_sens is set")
+            sens_a = _lib.as_arr(sens, np.float64, 3, "sens", writable=True)
+            sens_p, s0, s1 = sens_a.ptr, sens_a.strides[0], sens_a.strides[1]
+        self._use_stream()
+        it = C.c_int32(0)
+        _lib.check(_lib.lib().wlsqm_solver_solve_hoods(self._handle, fa.ptr, fa.strides[0] if fa.shape[0] > 1 else 1,
+                                                       fi_a.ptr, fi_a.strides[0], sens_p, s0, s1, C.byref(it)))
+        return int(it.value)
+
     # -- solve ------------------------------------------------------------------------------------------
     def solve(self, fk, fi, sens=None):
         """Fit the model to the data fk using the prepared geometry (``expert.pyx:467-655``).
@@ -252,13 +304,25 @@ class ExpertSolver:
             xi = xi.detach().cpu().numpy()
         return np.asarray(xi)
 
-    def prep_interpolate(self):
-        """Index the model origins xi with a kd-tree (``expert.pyx:658-681``).  The nearest-model search
-        stays SciPy's cKDTree on the host, so the index I is the reference's by construction."""
+    def prep_interpolate(self, search=None):
+        """Index the model origins xi for the nearest-model search (``expert.pyx:658-681``).
+
+        search='scipy' (default for host arrays): SciPy's cKDTree on the host, so that the index I is the
+        reference's by construction.  search='gpu' (default when xi is a CUDA tensor; extension): a uniform
+        grid on the device -- the same nearest model wherever distances are distinct, without the 1.8 us per
+        query host step.  mode='continuous' always searches on the device."""
         if not self.ready:
             raise RuntimeError("Solver is not in the ready state; prepare() must be called before prep_interpolate()")
-        if self.host is not None:
+        if search is None:
+            search = 'gpu' if _lib._is_torch_tensor(self.xi) and self.xi.is_cuda else 'scipy'
+        if search not in ('scipy', 'gpu'):
+            raise ValueError("search must be 'scipy' or 'gpu'; got %r" % (search,))
+        self._use_stream()
+        _lib.check(_lib.lib().wlsqm_solver_index_models(self._handle))
+        if self.host is not None and self.host.tree is not None:
             self.tree = self.host.tree
+        elif search == 'gpu':
+            self.tree = _DeviceModelIndex(self)
         else:
             import scipy.spatial
             xi = self._xi_host()
@@ -292,10 +356,21 @@ class ExpertSolver:
             x_s0 = 1
         self._use_stream()
         if mode == 'continuous':
-            return self._interpolate_continuous(x_a, float(r), cdiff), np.asanyarray(None)
+            return self._interpolate_continuous(x_a, x_s0, float(r), cdiff), np.asanyarray(None)
 
-        if I is None:
-            xh = x.detach().cpu().numpy() if _lib._is_torch_tensor(x) else np.asarray(x)
+        if I is None and (isinstance(self.tree, _DeviceModelIndex) or x_a.is_cuda):
+            # nearest model by the device-side grid (extension); I stays where x lives
+            if x_a.is_cuda:
+                import torch
+                I_out = torch.empty((nx,), dtype=torch.int64, device=x.device)
+                ip = int(I_out.data_ptr())
+            else:
+                I_out = np.empty((nx,), dtype=np.int_)
+                ip = I_out.ctypes.data
+            _lib.check(_lib.lib().wlsqm_solver_nearest_models(self._handle, x_a.ptr, x_s0, nx, ip))
+            I_use = I_out
+        elif I is None:
+            xh = np.asarray(x)
             xq = xh if dim >= 2 else np.atleast_2d(xh).T
             _d, I_h = self.tree.query(xq, k=1)
             I_out = np.ascontiguousarray(I_h, dtype=np.int_)
@@ -321,30 +396,43 @@ class ExpertSolver:
         _lib.check(_lib.lib().wlsqm_solver_interpolate(self._handle, x_a.ptr, x_s0, I_a.ptr, nx, cdiff, out_p, width))
         return out, (I_out if x_a.is_cuda and _lib._is_torch_tensor(I_out) else np.asanyarray(I_out))
 
-    def _interpolate_continuous(self, x_a, r, cdiff):
+    def _interpolate_continuous(self, x_a, x_s0, r, cdiff):
         """mode='continuous' (``expert_interpolate_continuous``, ``expert.pyx:898-985``): weighted average
-        over every local model whose origin lies within r; weights (1 - sqrt(d2/r2))^2.  The model
-        evaluations run on the GPU as one batch of (query, model) pairs; the ball search is SciPy's."""
-        import scipy.spatial
-        dim = self.dimension
-        xh = x_a.keep.detach().cpu().numpy() if x_a.is_cuda else x_a.np
-        xq = xh if dim >= 2 else np.atleast_2d(xh).T
-        nx = xq.shape[0]
-        lists = scipy.spatial.cKDTree(data=xq).query_ball_tree(other=self.tree, r=r)
-        counts = np.fromiter((len(L) for L in lists), dtype=np.int64, count=nx)
-        qidx = np.repeat(np.arange(nx, dtype=np.int64), counts)
-        midx = np.fromiter((li for L in lists for li in L), dtype=np.int64, count=int(counts.sum()))
-        xi = self._xi_host()
-        xi2 = xi if dim >= 2 else np.atleast_2d(xi).T
-        xp = np.ascontiguousarray(xq[qidx, :dim])
-        vals = np.empty((len(qidx),), dtype=np.float64)
-        if len(qidx):
-            _lib.check(_lib.lib().wlsqm_solver_interpolate(
-                self._handle, xp.ctypes.data, dim, midx.ctypes.data, len(qidx), cdiff, vals.ctypes.data, 1))
-        d2 = ((xp - xi2[midx, :dim]) ** 2).sum(axis=1)
-        tmp = 1. - np.sqrt(d2 / (r * r))
-        w = tmp * tmp                       # alpha = 0, beta = 1 (expert.pyx:45-46)
-        acc = np.bincount(qidx, weights=w * vals, minlength=nx)
-        sum_w = np.bincount(qidx, weights=w, minlength=nx)
-        with np.errstate(invalid='ignore', divide='ignore'):
-            return acc / sum_w
+        over every local model whose origin lies within r; weights (1 - sqrt(d2/r2))^2.  One kernel: each query
+        walks the cells of the model-origin grid that meet its ball and evaluates the models on the fly."""
+        if cdiff < 0:
+            raise ValueError("diff='all' is not available in mode='continuous'")
+        nx = x_a.shape[0]
+        if x_a.is_cuda:
+            import torch
+            out = torch.empty((nx,), dtype=torch.float64, device=x_a.keep.device)
+            op = int(out.data_ptr())
+        else:
+            out = np.empty((nx,), dtype=np.float64)
+            op = out.ctypes.data
+        _lib.check(_lib.lib().wlsqm_solver_interpolate_continuous(self._handle, x_a.ptr, x_s0, nx, r, cdiff, op))
+        return out
+
+
+class _DeviceModelIndex:
+    """Stands where the reference keeps its cKDTree (``ExpertSolver.tree``) when the nearest-model search runs
+    on the device; ``query(x, k=1)`` answers like ``cKDTree.query``."""
+
+    def __init__(self, solver):
+        import weakref
+        self._solver = weakref.ref(solver)
+
+    def query(self, x, k=1):
+        s = self._solver()
+        if k != 1:
+            raise ValueError("the model index answers k=1 queries")
+        from .. import neighbors
+        xa, nx, dim, x_s0 = neighbors._points(x)
+        I = np.empty((nx,), dtype=np.int_)
+        if xa.is_cuda:
+            import torch
+            It = torch.empty((nx,), dtype=torch.int64, device=x.device)
+            _lib.check(_lib.lib().wlsqm_solver_nearest_models(s._handle, xa.ptr, x_s0, nx, int(It.data_ptr())))
+            return None, It
+        _lib.check(_lib.lib().wlsqm_solver_nearest_models(s._handle, xa.ptr, x_s0, nx, I.ctypes.data))
+        return None, I
