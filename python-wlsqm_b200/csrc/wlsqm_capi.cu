@@ -303,7 +303,7 @@ int config_solve_pack(const wlsqm_solver* s, SolveParams& P, LaunchCfg& L, long 
     const size_t stage_bytes = (size_t)stage_doubles * 8;
     int S = env_int("WLSQM_SOLVE_STAGES", 2);
     S = std::max(2, std::min(S, 8));
-    int warps = env_int("WLSQM_SOLVE_WARPS", 16);
+    int warps = env_int("WLSQM_SOLVE_WARPS", 8);     // 8-warp CTAs: three fit per SM for 2 KB packs (measured best)
     warps = std::max(1, std::min(warps, SOLVE_MAX_THREADS / 32));
     int wd = 0;
     for (;;) {
@@ -324,7 +324,7 @@ int config_solve_pack(const wlsqm_solver* s, SolveParams& P, LaunchCfg& L, long 
     L.threads = warps * 32;
     L.smem = (size_t)P.bar_off_bytes + (size_t)warps * S * 8;
     int ctas = (int)(SMEM_PER_SM / (L.smem + 1024));
-    ctas = std::max(1, std::min(ctas, std::max(1, env_int("WLSQM_SOLVE_MAXWARPS_SM", stage_bytes >= 3072 ? 16 : 32) / warps)));
+    ctas = std::max(1, std::min(ctas, std::max(1, env_int("WLSQM_SOLVE_MAXWARPS_SM", 32) / warps)));
     const long long packs = (ncases_launch + cpw - 1) / cpw;
     long long need = (packs + warps - 1) / warps;
     L.blocks = (int)std::max<long long>(1, std::min<long long>((long long)s->sm_count * ctas, need));
