@@ -77,6 +77,14 @@ WLSQM_API int wlsqm_solver_create(int dimension, int64_t ncases, const int32_t* 
                         const int64_t* knowns, const int32_t* weighting_method, int algorithm, int do_sens,
                         int max_iter, int debug, int device, wlsqm_solver_t** out);
 
+/* ExpertSolver(..., host=other): guest mode (expert.pyx:163-189,243-263; Case_new(host=...) infra.pyx:528-544).  The
+ * guest borrows the host's prepared state (operators, per-case records, origins) and owns only its solution copy:
+ * several fields on one geometry cost one set of operators.  Sizes and debug flag are the host's; algorithm, do_sens,
+ * max_iter are the guest's own (an ALGO_ITERATIVE guest needs an ALGO_ITERATIVE host).  The host must outlive the guest.
+ * wlsqm_solver_prepare on a guest (or wlsqm_solver_prepare_guest) computes nothing and marks it ready. */
+WLSQM_API int wlsqm_solver_create_guest(wlsqm_solver_t* host, int algorithm, int do_sens, int max_iter, wlsqm_solver_t** out);
+WLSQM_API int wlsqm_solver_prepare_guest(wlsqm_solver_t* s);
+
 /* ExpertSolver.__del__ (expert.pyx:267-286) / CaseManager_del (infra.pyx:497) */
 WLSQM_API int wlsqm_solver_destroy(wlsqm_solver_t* s);
 

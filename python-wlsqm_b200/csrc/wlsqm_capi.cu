@@ -151,6 +151,7 @@ struct wlsqm_solver {
     DevBuf hoods_dev, hood_x, hood_f, hood_fk;   // prepare_hoods / solve_hoods: neighbour lists and gathered data
     long long hood_points = 0;
     wlsqm_grid* models_grid = nullptr;           // search grid over the model origins (index_models)
+    wlsqm_solver* lender = nullptr;              // guest mode: op / dmeta / dorder / xi_dev / As / xk_keep belong to this solver
     long long bytes_state = 0;
 };
 
@@ -509,9 +510,13 @@ int wlsqm_solver_destroy(wlsqm_solver_t* s) {
     if (!s) return WLSQM_OK;
     cudaSetDevice(s->device);
     if (s->stream) cudaStreamSynchronize(s->stream);
-    cudaFree(s->dmeta); cudaFree(s->dorder); cudaFree(s->op); cudaFree(s->fi_case); cudaFree(s->xi_dev);
-    cudaFree(s->As); cudaFree(s->iters_dev);
-    s->xk_keep.release(); s->st_xk.release(); s->st_fk.release(); s->st_fi.release(); s->st_sens.release();
+    if (!s->lender) {
+        cudaFree(s->dmeta); cudaFree(s->dorder); cudaFree(s->op); cudaFree(s->xi_dev); cudaFree(s->As);
+        s->xk_keep.release();
+    } else {
+        s->xk_keep.p = nullptr; s->xk_keep.cap = 0;
+    }
+    cudaFree(s->fi_case); cudaFree(s->iters_dev); s->st_xk.release(); s->st_fk.release(); s->st_fi.release(); s->st_sens.release();
     s->st_x.release(); s->st_I.release(); s->st_out.release();
     s->hoods_dev.release(); s->hood_x.release(); s->hood_f.release(); s->hood_fk.release();
     if (s->models_grid) { wlsqm_grid_destroy(s->models_grid); s->models_grid = nullptr; }
@@ -521,6 +526,74 @@ int wlsqm_solver_destroy(wlsqm_solver_t* s) {
     for (cudaEvent_t e : s->events) cudaEventDestroy(e);
     cudaGetLastError();
     delete s;
+    return WLSQM_OK;
+}
+
+// ExpertSolver(..., host=other) (expert.pyx:163-189, 243-263; infra.pyx:528-544): the guest borrows the host's
+// geometry-dependent state -- here the operator blocks, per-case records, origins (and the kept xk of an iterative
+// host) -- and owns only its solution copy, iteration counters and staging.  Several fields on one geometry then
+// cost one set of operators.  The host must outlive the guest (the Python class keeps a reference).
+int wlsqm_solver_create_guest(wlsqm_solver_t* host, int algorithm, int do_sens, int max_iter, wlsqm_solver_t** out) {
+    if (!out) return fail(WLSQM_E_VALUE, "out is NULL");
+    *out = nullptr;
+    if (!host) return fail(WLSQM_E_VALUE, "NULL host solver");
+    if (algorithm != WLSQM_ALGO_BASIC && algorithm != WLSQM_ALGO_ITERATIVE)
+        return fail(WLSQM_E_VALUE, "Unknown algorithm specifier %d; see wlsqm.fitter.defs for valid specifiers ALGO_*", algorithm);
+    if (algorithm == WLSQM_ALGO_ITERATIVE && host->algorithm != WLSQM_ALGO_ITERATIVE)
+        return fail(WLSQM_E_VALUE, "an ALGO_ITERATIVE guest needs an ALGO_ITERATIVE host (the host keeps the geometry xk)");
+    const wlsqm_solver* root = host->lender ? host->lender : host;
+    wlsqm_solver* s = new (std::nothrow) wlsqm_solver();
+    if (!s) return fail(WLSQM_E_MEMORY, "out of host memory");
+    s->dim = root->dim; s->device = root->device; s->algorithm = algorithm; s->do_sens = do_sens ? 1 : 0;
+    s->max_iter = max_iter; s->debug = root->debug; s->ncases = root->ncases;
+    s->maxnk = root->maxnk; s->maxno = root->maxno; s->maxnr = root->maxnr; s->maxnq = root->maxnq;
+    s->maxorder = root->maxorder; s->maxnkn = root->maxnkn;
+    s->uniform = root->uniform; s->any_knowns = root->any_knowns; s->uniform_no = root->uniform_no;
+    s->geom_uniform = root->geom_uniform;
+    s->uni = root->uni; s->op_stride = root->op_stride; s->op_total = root->op_total;
+    try {
+        s->hmeta = root->hmeta;
+    } catch (...) {
+        delete s;
+        return fail(WLSQM_E_MEMORY, "out of host memory");
+    }
+    s->sm_count = root->sm_count;
+    s->lender = const_cast<wlsqm_solver*>(root);
+    s->dmeta = root->dmeta; s->dorder = root->dorder; s->op = root->op; s->xi_dev = root->xi_dev;
+    s->As = root->As; s->as_stride = root->as_stride;
+    s->xk_keep.p = root->xk_keep.p; s->xk_keep.cap = 0;
+    int rc = use_device(s);
+    if (rc) { s->lender = nullptr; s->dmeta = nullptr; s->dorder = nullptr; s->op = nullptr; s->xi_dev = nullptr; s->As = nullptr; s->xk_keep.p = nullptr; delete s; return rc; }
+    cudaError_t e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { wlsqm_solver_destroy(s); return fail(WLSQM_E_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
+    s->own_stream = true;
+    const size_t fb = (size_t)s->ncases * s->maxno * 8;
+    if (fb && cudaMalloc((void**)&s->fi_case, fb) != cudaSuccess) { cudaGetLastError(); wlsqm_solver_destroy(s); return fail(WLSQM_E_MEMORY, "cudaMalloc(%zu bytes) failed", fb); }
+    s->bytes_state += (long long)fb;
+    if (algorithm == WLSQM_ALGO_ITERATIVE) {
+        const size_t ib = ((size_t)s->ncases + 1) * 4;
+        if (cudaMalloc((void**)&s->iters_dev, ib) != cudaSuccess) { cudaGetLastError(); wlsqm_solver_destroy(s); return fail(WLSQM_E_MEMORY, "cudaMalloc(%zu bytes) failed", ib); }
+        s->bytes_state += (long long)ib;
+    }
+    if (s->fi_case) cudaMemsetAsync(s->fi_case, 0, fb, s->stream);
+    e = cudaStreamSynchronize(s->stream);
+    if (e != cudaSuccess) { wlsqm_solver_destroy(s); return fail(WLSQM_E_CUDA, "guest initialisation: %s", cudaGetErrorString(e)); }
+    s->ready = root->ready;
+    *out = s;
+    return WLSQM_OK;
+}
+
+// guest.prepare(): nothing to compute -- the operators are the host's; the guest is ready when its host is
+int wlsqm_solver_prepare_guest(wlsqm_solver_t* s) {
+    if (!s || !s->lender) return fail(WLSQM_E_VALUE, "not a guest solver");
+    if (!s->lender->ready) return fail(WLSQM_E_NOTREADY, "In guest mode, host must be in the ready state");
+    int rc = use_device(s);
+    if (rc) return rc;
+    // the host may have re-prepared (and re-allocated its kept geometry) since the guest was created
+    s->xk_keep.p = s->lender->xk_keep.p;
+    if (s->models_grid) { wlsqm_grid_destroy(s->models_grid); s->models_grid = nullptr; }
+    CU(cudaStreamSynchronize(s->lender->stream));     // the host's prepare may still be in flight on its stream
+    s->ready = true;
     return WLSQM_OK;
 }
 
@@ -547,6 +620,7 @@ int wlsqm_solver_synchronize(wlsqm_solver_t* s) {
 int wlsqm_solver_prepare(wlsqm_solver_t* s, const double* xi, int64_t xi_s0, const double* xk, int64_t xk_s0,
                          int64_t xk_s1) {
     if (!s) return fail(WLSQM_E_VALUE, "NULL solver");
+    if (s->lender) return wlsqm_solver_prepare_guest(s);
     s->ready = false;
     if (s->models_grid) { wlsqm_grid_destroy(s->models_grid); s->models_grid = nullptr; }   // the origins may move
     if (s->ncases == 0) { s->ready = true; return WLSQM_OK; }

@@ -36,6 +36,8 @@ SIGNATURES = {
     "wlsqm_pinned_alloc": (_vp, [_i64]),
     "wlsqm_pinned_free": (None, [_vp]),
     "wlsqm_solver_create": (_int, [_int, _i64, _vp, _vp, _vp, _vp, _int, _int, _int, _int, _int, C.POINTER(_vp)]),
+    "wlsqm_solver_create_guest": (_int, [_vp, _int, _int, _int, C.POINTER(_vp)]),
+    "wlsqm_solver_prepare_guest": (_int, [_vp]),
     "wlsqm_solver_destroy": (_int, [_vp]),
     "wlsqm_solver_set_stream": (_int, [_vp, _vp]),
     "wlsqm_solver_synchronize": (_int, [_vp]),

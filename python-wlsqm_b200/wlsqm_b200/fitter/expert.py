@@ -123,9 +123,16 @@ class ExpertSolver:
             raise ValueError("order must be 0, 1, 2, 3 or 4")
 
         h = C.c_void_p()
-        _lib.check(_lib.lib().wlsqm_solver_create(
-            dimension, ncases, nk_a.ctypes.data, order_a.ctypes.data, knowns_a.ctypes.data, wm_a.ctypes.data,
-            algorithm, do_sens, max_iter, debug, self.device, C.byref(h)))
+        # guest mode: borrow the host's operators (one set of operators for several fields on one geometry);
+        # an iterative guest of a non-iterative host needs the geometry itself and prepares on its own
+        self._borrows = (host is not None and getattr(host, "_handle", None) is not None
+                         and (algorithm != defs.ALGO_ITERATIVE or host.algorithm == defs.ALGO_ITERATIVE))
+        if self._borrows:
+            _lib.check(_lib.lib().wlsqm_solver_create_guest(host._handle, algorithm, do_sens, max_iter, C.byref(h)))
+        else:
+            _lib.check(_lib.lib().wlsqm_solver_create(
+                dimension, ncases, nk_a.ctypes.data, order_a.ctypes.data, knowns_a.ctypes.data, wm_a.ctypes.data,
+                algorithm, do_sens, max_iter, debug, self.device, C.byref(h)))
         self._handle = h
         self.manager_pw = h   # the reference keeps its CaseManager pointer under this name (expert.pyx:257-260)
         if host is not None:
@@ -133,6 +140,7 @@ class ExpertSolver:
 
     # -- lifetime -----------------------------------------------------------------------------------
     def close(self):
+        """Free the device state now (guests of this solver must be closed first)."""
         h, self._handle = getattr(self, "_handle", None), None
         if h is not None and h.value:
             _lib.lib().wlsqm_solver_destroy(h)
@@ -169,6 +177,10 @@ class ExpertSolver:
             # guest mode: geometry (and operators) are the host's (expert.pyx:348-385)
             self.xk, self.xi = self.host.xk, self.host.xi
             xi, xk = self.xi, self.xk
+            if self._borrows:
+                _lib.check(_lib.lib().wlsqm_solver_prepare_guest(self._handle))
+                self.ready = True
+                return
         dim = self.dimension
         if dim >= 2:
             xi_a = _lib.as_arr(xi, np.float64, 2, "xi")

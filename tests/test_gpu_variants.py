@@ -212,3 +212,41 @@ def test_interpolate_per_model_orders():
         og, _ = s.interpolate(xq, diff=d, I=I)
         oo = so.interpolate(xq, I, d)
         assert np.abs(og - oo).max() <= 1e-12 * max(np.abs(oo).max(), 1e-300), d
+
+
+def test_guest_mode_borrows_the_hosts_operators():
+    """ExpertSolver(host=...) (expert.pyx:163-189): same geometry, another field -- the guest owns no operators"""
+    n, k, dim, order = 2001, 30, 2, 4
+    x, hoods, f = parity.make_case(n, dim, k)
+    xk, fk = parity.gathered(x, f, hoods)
+    g2 = np.cos(3.0 * x[:, 0]) * x[:, 1]
+    gk = np.ascontiguousarray(g2[hoods])
+    nk, od, kn, wm = (np.full(n, k, np.int32), np.full(n, order, np.int32), np.full(n, 1, np.int64),
+                      np.full(n, 2, np.int32))
+    for algo in (wlsqm.ALGO_BASIC, wlsqm.ALGO_ITERATIVE):
+        host = wlsqm.ExpertSolver(dim, nk, od, kn, wm, algorithm=algo, max_iter=3)
+        host.prepare(x, xk)
+        guest = wlsqm.ExpertSolver(dim, nk, od, kn, wm, algorithm=algo, max_iter=3, do_sens=True, host=host)
+        assert guest._borrows
+        guest.prepare(x, xk)            # arguments are ignored in guest mode, like the reference
+        assert guest.ready and guest.memory_used()[0] < host.memory_used()[0] / 10
+        fi_h = np.zeros((n, 15)); fi_h[:, 0] = f
+        fi_g = np.zeros((n, 15)); fi_g[:, 0] = g2
+        sens = np.zeros((n, k, 15))
+        host.solve(fk, fi_h)
+        guest.solve(gk, fi_g, sens)
+        # an independent solver on the same geometry gives the same numbers, bit for bit
+        fi_i, sens_i, _ = _solve_gpu(dim, nk, od, kn, wm, x, xk, gk, np.where(np.arange(15) == 0, g2[:, None], 0.0),
+                                     do_sens=True, algorithm=algo)
+        assert np.array_equal(fi_g, fi_i)
+        assert np.array_equal(np.nan_to_num(sens), np.nan_to_num(sens_i))
+        # the host's own solution is not disturbed by the guest
+        fi_h2 = np.zeros((n, 15)); fi_h2[:, 0] = f
+        host.solve(fk, fi_h2)
+        assert np.array_equal(fi_h, fi_h2)
+        guest.close()
+        host.close()
+    with pytest.raises(ValueError, match="must match"):
+        host = wlsqm.ExpertSolver(dim, nk, od, kn, wm)
+        host.prepare(x, xk)
+        wlsqm.ExpertSolver(dim, nk, od, np.zeros(n, np.int64), wm, host=host)
