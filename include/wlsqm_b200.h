@@ -69,6 +69,14 @@ WLSQM_API int wlsqm_number_of_dofs(int dimension, int order);
 WLSQM_API void* wlsqm_pinned_alloc(int64_t bytes);
 WLSQM_API void wlsqm_pinned_free(void* p);
 
+/* Device memory of the library comes from one stream-ordered CUDA memory pool per device: what a destroyed solver or
+ * a finished one-shot fit gives back stays cached (up to WLSQM_POOL_KEEP_MB, default 2048; WLSQM_POOL=0 disables the
+ * pool) so that the next call does not pay cudaMalloc / cudaFree -- the counterpart of the reference building its
+ * per-call arena with one malloc (CaseManager_commit, wlsqm/fitter/infra.pyx:545-632).  stats: bytes reserved from
+ * the driver / in use (-1 before the first allocation on that device); trim: return the cached blocks. */
+WLSQM_API int wlsqm_pool_stats(int device, int64_t* reserved, int64_t* used);
+WLSQM_API int wlsqm_pool_trim(int device);
+
 /* ---- ExpertSolver: wlsqm/fitter/expert.pyx:66-781 ------------------------------------------------ */
 
 /* ExpertSolver.__init__ (expert.pyx:92-263) + CaseManager_new/Case_new/commit (infra.pyx:308-471,545-632).

@@ -15,6 +15,7 @@
 #include "wlsqm_common.cuh"
 #include "wlsqm_kernels.h"
 #include "wlsqm_grid.h"
+#include "wlsqm_mem.h"
 
 namespace wlsqm {
 GridView grid_view(const wlsqm_grid* g);
@@ -71,25 +72,27 @@ int is_device_ptr(const void* p) {
     return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
 }
 
+// A device buffer that only grows.  Blocks come from the library's memory pool (wlsqm_mem.h).
 struct DevBuf {
     void* p = nullptr;
     size_t cap = 0;
     int reserve(size_t bytes) {
         if (bytes <= cap) return WLSQM_OK;
-        if (p) cudaFree(p);
+        if (p) dev_free_sync(p);     // growing a live buffer: earlier work may still read the old block
         p = nullptr;
         cap = 0;
         if (bytes == 0) return WLSQM_OK;
-        cudaError_t e = cudaMalloc(&p, bytes);
+        cudaError_t e = dev_alloc(&p, bytes);
         if (e != cudaSuccess) {
             cudaGetLastError();
-            return fail(WLSQM_E_MEMORY, "cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+            return fail(WLSQM_E_MEMORY, "device allocation of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
         }
         cap = bytes;
         return WLSQM_OK;
     }
+    // the caller has synchronised the streams that used the buffer
     void release() {
-        if (p) cudaFree(p);
+        if (p) dev_free(p);
         p = nullptr;
         cap = 0;
     }
@@ -392,6 +395,20 @@ void wlsqm_pinned_free(void* p) {
     if (p) cudaFreeHost(p);
 }
 
+int wlsqm_pool_stats(int device, int64_t* reserved, int64_t* used) {
+    long long r = -1, u = -1;
+    dev_pool_stats(device, &r, &u);
+    if (reserved) *reserved = r;
+    if (used) *used = u;
+    return WLSQM_OK;
+}
+
+int wlsqm_pool_trim(int device) {
+    if (wlsqm_device_count() < 1) return fail(WLSQM_E_CUDA, "no CUDA device available (there is no CPU fallback)");
+    dev_pool_trim(device);
+    return WLSQM_OK;
+}
+
 int wlsqm_solver_create(int dimension, int64_t ncases, const int32_t* nk, const int32_t* order, const int64_t* knowns,
                         const int32_t* wm, int algorithm, int do_sens, int max_iter, int debug, int device,
                         wlsqm_solver_t** out) {
@@ -410,14 +427,20 @@ int wlsqm_solver_create(int dimension, int64_t ncases, const int32_t* nk, const 
     if (!s) return fail(WLSQM_E_MEMORY, "out of host memory");
     s->dim = dimension; s->device = device; s->algorithm = algorithm; s->do_sens = do_sens ? 1 : 0;
     s->max_iter = max_iter; s->debug = debug ? 1 : 0; s->ncases = ncases;
+    // Uniform batches (every case with the same nk / order / knowns / weighting -- the usual ExpertSolver and
+    // fit_*_many call) are recognised by one pass of comparisons and keep no per-case records at all.
+    bool all_same = true;
+    for (long long i = 1; i < ncases && all_same; ++i)
+        all_same = nk[i] == nk[0] && order[i] == order[0] && knowns[i] == knowns[0] && wm[i] == wm[0];
+    const long long nrec = all_same ? std::min<long long>(ncases, 1) : ncases;
     try {
-        s->hmeta.resize((size_t)ncases);
+        s->hmeta.resize((size_t)nrec);
     } catch (...) {
         delete s;
         return fail(WLSQM_E_MEMORY, "out of host memory");
     }
     long long off = 0;
-    for (long long i = 0; i < ncases; ++i) {
+    for (long long i = 0; i < nrec; ++i) {
         const int no = number_of_dofs(dimension, order[i]);
         if (no < 0) { delete s; return fail(WLSQM_E_VALUE, "case %lld: order must be 0..4, got %d", i, order[i]); }
         if (nk[i] < 0) { delete s; return fail(WLSQM_E_VALUE, "case %lld: nk must be >= 0, got %d", i, nk[i]); }
@@ -447,6 +470,7 @@ int wlsqm_solver_create(int dimension, int64_t ncases, const int32_t* nk, const 
             if (m.nk != f.nk || m.order != f.order || m.nkn != f.nkn || m.wm != f.wm) s->geom_uniform = false;
         }
     }
+    if (all_same) off *= ncases;
     s->op_total = off;
     if (ncases > 0) {
         s->uni = s->hmeta[0];
@@ -468,10 +492,10 @@ int wlsqm_solver_create(int dimension, int64_t ncases, const int32_t* nk, const 
     auto alloc = [&](void** p, size_t bytes) -> int {
         *p = nullptr;
         if (bytes == 0) return WLSQM_OK;
-        cudaError_t e2 = cudaMalloc(p, bytes);
+        cudaError_t e2 = dev_alloc(p, bytes);
         if (e2 != cudaSuccess) {
             cudaGetLastError();
-            return fail(WLSQM_E_MEMORY, "cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e2));
+            return fail(WLSQM_E_MEMORY, "device allocation of %zu bytes failed: %s", bytes, cudaGetErrorString(e2));
         }
         s->bytes_state += (long long)bytes;
         return WLSQM_OK;
@@ -509,14 +533,17 @@ int wlsqm_solver_create(int dimension, int64_t ncases, const int32_t* nk, const 
 int wlsqm_solver_destroy(wlsqm_solver_t* s) {
     if (!s) return WLSQM_OK;
     cudaSetDevice(s->device);
+    // every stream that may still touch the solver's buffers, then the blocks go back to the pool unsynchronised
     if (s->stream) cudaStreamSynchronize(s->stream);
+    if (s->s_in) cudaStreamSynchronize(s->s_in);
+    if (s->s_out) cudaStreamSynchronize(s->s_out);
     if (!s->lender) {
-        cudaFree(s->dmeta); cudaFree(s->dorder); cudaFree(s->op); cudaFree(s->xi_dev); cudaFree(s->As);
+        dev_free(s->dmeta); dev_free(s->dorder); dev_free(s->op); dev_free(s->xi_dev); dev_free(s->As);
         s->xk_keep.release();
     } else {
         s->xk_keep.p = nullptr; s->xk_keep.cap = 0;
     }
-    cudaFree(s->fi_case); cudaFree(s->iters_dev); s->st_xk.release(); s->st_fk.release(); s->st_fi.release(); s->st_sens.release();
+    dev_free(s->fi_case); dev_free(s->iters_dev); s->st_xk.release(); s->st_fk.release(); s->st_fi.release(); s->st_sens.release();
     s->st_x.release(); s->st_I.release(); s->st_out.release();
     s->hoods_dev.release(); s->hood_x.release(); s->hood_f.release(); s->hood_fk.release();
     if (s->models_grid) { wlsqm_grid_destroy(s->models_grid); s->models_grid = nullptr; }
@@ -568,11 +595,11 @@ int wlsqm_solver_create_guest(wlsqm_solver_t* host, int algorithm, int do_sens, 
     if (e != cudaSuccess) { wlsqm_solver_destroy(s); return fail(WLSQM_E_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
     s->own_stream = true;
     const size_t fb = (size_t)s->ncases * s->maxno * 8;
-    if (fb && cudaMalloc((void**)&s->fi_case, fb) != cudaSuccess) { cudaGetLastError(); wlsqm_solver_destroy(s); return fail(WLSQM_E_MEMORY, "cudaMalloc(%zu bytes) failed", fb); }
+    if (fb && dev_alloc((void**)&s->fi_case, fb) != cudaSuccess) { cudaGetLastError(); wlsqm_solver_destroy(s); return fail(WLSQM_E_MEMORY, "cudaMalloc(%zu bytes) failed", fb); }
     s->bytes_state += (long long)fb;
     if (algorithm == WLSQM_ALGO_ITERATIVE) {
         const size_t ib = ((size_t)s->ncases + 1) * 4;
-        if (cudaMalloc((void**)&s->iters_dev, ib) != cudaSuccess) { cudaGetLastError(); wlsqm_solver_destroy(s); return fail(WLSQM_E_MEMORY, "cudaMalloc(%zu bytes) failed", ib); }
+        if (dev_alloc((void**)&s->iters_dev, ib) != cudaSuccess) { cudaGetLastError(); wlsqm_solver_destroy(s); return fail(WLSQM_E_MEMORY, "cudaMalloc(%zu bytes) failed", ib); }
         s->bytes_state += (long long)ib;
     }
     if (s->fi_case) cudaMemsetAsync(s->fi_case, 0, fb, s->stream);
@@ -832,7 +859,7 @@ int wlsqm_solver_solve(wlsqm_solver_t* s, const double* fk, int64_t fk_s0, int64
         CU(cudaMemcpyAsync(tmp.data(), s->st_sens.p, tmp.size() * 8, cudaMemcpyDeviceToHost, s_out));
         CU(cudaStreamSynchronize(s_out));
         for (long long i = 0; i < n; ++i) {
-            const CaseMeta& m = s->hmeta[(size_t)i];
+            const CaseMeta& m = s->hmeta.size() > (size_t)i ? s->hmeta[(size_t)i] : s->uni;
             if (m.nr < 1) continue;     // silent no-op case: sens untouched
             for (int k = 0; k < m.nk; ++k)
                 memcpy(sens + i * sens_s0 + (long long)k * sens_s1, tmp.data() + (size_t)i * plane + (size_t)k * s->maxno,

@@ -23,6 +23,7 @@
 #include "../../include/wlsqm_b200.h"
 #include "wlsqm_grid.h"
 #include "wlsqm_kernels.h"
+#include "wlsqm_mem.h"
 
 using namespace wlsqm;
 
@@ -243,7 +244,7 @@ int wlsqm_grid_destroy(wlsqm_grid_t* g) {
     if (!g) return WLSQM_OK;
     cudaSetDevice(g->device);
     if (g->stream) cudaStreamSynchronize(g->stream);
-    cudaFree(g->cell_start); cudaFree(g->sorted_idx); cudaFree(g->sorted_x);
+    dev_free(g->cell_start); dev_free(g->sorted_idx); dev_free(g->sorted_x);
     if (g->stream) cudaStreamDestroy(g->stream);
     cudaGetLastError();
     delete g;
@@ -271,20 +272,20 @@ int wlsqm_grid_create(int dimension, int64_t n, const double* x, int64_t x_s0, i
     const double* xdev = x;
     long long s0 = x_s0;
     if (!is_dev(x)) {
-        if (cudaMalloc(&xd, (size_t)n * dimension * 8) != cudaSuccess) return bail(gfail(WLSQM_E_MEMORY, "cudaMalloc failed (grid points)"));
+        if (dev_alloc((void**)&xd, (size_t)n * dimension * 8) != cudaSuccess) return bail(gfail(WLSQM_E_MEMORY, "cudaMalloc failed (grid points)"));
         e = cudaMemcpy2DAsync(xd, (size_t)dimension * 8, x, (size_t)x_s0 * 8, (size_t)dimension * 8, (size_t)n, cudaMemcpyHostToDevice, st);
-        if (e != cudaSuccess) { cudaFree(xd); return bail(gfail(WLSQM_E_CUDA, cudaGetErrorString(e))); }
+        if (e != cudaSuccess) { dev_free(xd); return bail(gfail(WLSQM_E_CUDA, cudaGetErrorString(e))); }
         xdev = xd;
         s0 = dimension;
     }
     unsigned long long* mm = nullptr;
     int *cid = nullptr, *idx = nullptr, *cid_s = nullptr, *counts = nullptr;
     void* tmp = nullptr;
-    auto cleanup = [&]() { cudaFree(xd); cudaFree(mm); cudaFree(cid); cudaFree(idx); cudaFree(cid_s); cudaFree(counts); cudaFree(tmp); };
-    auto fail_here = [&](int code, const char* msg) { cleanup(); return bail(gfail(code, msg)); };
+    auto cleanup = [&]() { dev_free(xd); dev_free(mm); dev_free(cid); dev_free(idx); dev_free(cid_s); dev_free(counts); dev_free(tmp); };
+    auto fail_here = [&](int code, const char* msg) { cudaStreamSynchronize(st); cleanup(); return bail(gfail(code, msg)); };
 
     // ---- bounding box -> cell size ----------------------------------------------------------------------
-    if (cudaMalloc(&mm, 6 * 8) != cudaSuccess) return fail_here(WLSQM_E_MEMORY, "cudaMalloc failed");
+    if (dev_alloc((void**)&mm, 6 * 8) != cudaSuccess) return fail_here(WLSQM_E_MEMORY, "cudaMalloc failed");
     unsigned long long init[6] = {~0ULL, ~0ULL, ~0ULL, 0ULL, 0ULL, 0ULL};
     cudaMemcpyAsync(mm, init, sizeof init, cudaMemcpyHostToDevice, st);
     bbox_kernel<<<296, 256, 0, st>>>(xdev, s0, n, dimension, mm);
@@ -332,11 +333,11 @@ int wlsqm_grid_create(int dimension, int64_t n, const double* x, int64_t x_s0, i
     g->ncells = ncells;
 
     // ---- cell ids, stable sort by cell, start offsets ------------------------------------------------------
-    bool okm = cudaMalloc(&cid, (size_t)n * 4) == cudaSuccess && cudaMalloc(&idx, (size_t)n * 4) == cudaSuccess &&
-               cudaMalloc(&cid_s, (size_t)n * 4) == cudaSuccess && cudaMalloc(&counts, (size_t)(ncells + 1) * 4) == cudaSuccess &&
-               cudaMalloc(&g->cell_start, (size_t)(ncells + 1) * 4) == cudaSuccess &&
-               cudaMalloc(&g->sorted_idx, (size_t)n * 4) == cudaSuccess &&
-               cudaMalloc(&g->sorted_x, (size_t)n * dimension * 8) == cudaSuccess;
+    bool okm = dev_alloc((void**)&cid, (size_t)n * 4) == cudaSuccess && dev_alloc((void**)&idx, (size_t)n * 4) == cudaSuccess &&
+               dev_alloc((void**)&cid_s, (size_t)n * 4) == cudaSuccess && dev_alloc((void**)&counts, (size_t)(ncells + 1) * 4) == cudaSuccess &&
+               dev_alloc((void**)&g->cell_start, (size_t)(ncells + 1) * 4) == cudaSuccess &&
+               dev_alloc((void**)&g->sorted_idx, (size_t)n * 4) == cudaSuccess &&
+               dev_alloc((void**)&g->sorted_x, (size_t)n * dimension * 8) == cudaSuccess;
     if (!okm) return fail_here(WLSQM_E_MEMORY, "cudaMalloc failed (grid)");
     g->bytes = (ncells + 1) * 4 + n * 4 + n * dimension * 8;
     cudaMemsetAsync(counts, 0, (size_t)(ncells + 1) * 4, st);
@@ -347,7 +348,7 @@ int wlsqm_grid_create(int dimension, int64_t n, const double* x, int64_t x_s0, i
     while ((1LL << bits) < ncells) ++bits;
     cub::DeviceRadixSort::SortPairs(nullptr, tb1, cid, cid_s, idx, g->sorted_idx, (int)n, 0, bits, st);
     cub::DeviceScan::ExclusiveSum(nullptr, tb2, counts, g->cell_start, (int)(ncells + 1), st);
-    if (cudaMalloc(&tmp, std::max(tb1, tb2) + 16) != cudaSuccess) return fail_here(WLSQM_E_MEMORY, "cudaMalloc failed (sort)");
+    if (dev_alloc((void**)&tmp, std::max(tb1, tb2) + 16) != cudaSuccess) return fail_here(WLSQM_E_MEMORY, "cudaMalloc failed (sort)");
     size_t tb = std::max(tb1, tb2) + 16;
     cub::DeviceRadixSort::SortPairs(tmp, tb, cid, cid_s, idx, g->sorted_idx, (int)n, 0, bits, st);
     tb = std::max(tb1, tb2) + 16;
@@ -376,17 +377,17 @@ int wlsqm_grid_knn(wlsqm_grid_t* g, const double* xq, int64_t xq_s0, int64_t nq,
     double* xqd = nullptr;
     int32_t* o32 = idx32; int64_t* o64 = idx64; double* od2 = d2;
     void *b32 = nullptr, *b64 = nullptr, *bd2 = nullptr;
-    auto done = [&](int rc) { cudaFree(xqd); cudaFree(b32); cudaFree(b64); cudaFree(bd2); return rc; };
+    auto done = [&](int rc) { dev_free(xqd); dev_free(b32); dev_free(b64); dev_free(bd2); return rc; };
     const double* xqv = xq;
     long long s0 = xq_s0;
     if (xq && !is_dev(xq)) {
-        if (cudaMalloc(&xqd, (size_t)nq * g->dim * 8) != cudaSuccess) return done(gfail(WLSQM_E_MEMORY, "cudaMalloc failed (queries)"));
+        if (dev_alloc((void**)&xqd, (size_t)nq * g->dim * 8) != cudaSuccess) return done(gfail(WLSQM_E_MEMORY, "cudaMalloc failed (queries)"));
         GCU(cudaMemcpy2DAsync(xqd, (size_t)g->dim * 8, xq, (size_t)xq_s0 * 8, (size_t)g->dim * 8, (size_t)nq, cudaMemcpyHostToDevice, st));
         xqv = xqd; s0 = g->dim;
     }
-    if (idx32 && !is_dev(idx32)) { if (cudaMalloc(&b32, cnt * 4) != cudaSuccess) return done(gfail(WLSQM_E_MEMORY, "cudaMalloc failed")); o32 = (int32_t*)b32; }
-    if (idx64 && !is_dev(idx64)) { if (cudaMalloc(&b64, cnt * 8) != cudaSuccess) return done(gfail(WLSQM_E_MEMORY, "cudaMalloc failed")); o64 = (int64_t*)b64; }
-    if (d2 && !is_dev(d2)) { if (cudaMalloc(&bd2, cnt * 8) != cudaSuccess) return done(gfail(WLSQM_E_MEMORY, "cudaMalloc failed")); od2 = (double*)bd2; }
+    if (idx32 && !is_dev(idx32)) { if (dev_alloc((void**)&b32, cnt * 4) != cudaSuccess) return done(gfail(WLSQM_E_MEMORY, "cudaMalloc failed")); o32 = (int32_t*)b32; }
+    if (idx64 && !is_dev(idx64)) { if (dev_alloc((void**)&b64, cnt * 8) != cudaSuccess) return done(gfail(WLSQM_E_MEMORY, "cudaMalloc failed")); o64 = (int64_t*)b64; }
+    if (d2 && !is_dev(d2)) { if (dev_alloc((void**)&bd2, cnt * 8) != cudaSuccess) return done(gfail(WLSQM_E_MEMORY, "cudaMalloc failed")); od2 = (double*)bd2; }
     cudaError_t e;
     if (g->dim == 1) e = launch_knn_d<1>(g->v, xqv, s0, nq, k, exclude_self, o32, o64, od2, st);
     else if (g->dim == 2) e = launch_knn_d<2>(g->v, xqv, s0, nq, k, exclude_self, o32, o64, od2, st);

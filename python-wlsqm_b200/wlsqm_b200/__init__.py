@@ -12,5 +12,5 @@ from .fitter.defs import *      # noqa: F401,F403
 from .fitter.simple import *    # noqa: F401,F403
 from .fitter.interp import *    # noqa: F401,F403
 from .fitter.expert import *    # noqa: F401,F403
-from ._lib import pinned_empty, pinned_free, LIB_PATH  # noqa: F401
+from ._lib import pinned_empty, pinned_free, pool_stats, pool_trim, LIB_PATH  # noqa: F401
 from .neighbors import PointGrid, knn_hoods, gather  # noqa: F401  (extension: device-side neighbour search)

@@ -35,6 +35,8 @@ SIGNATURES = {
     "wlsqm_number_of_dofs": (_int, [_int, _int]),
     "wlsqm_pinned_alloc": (_vp, [_i64]),
     "wlsqm_pinned_free": (None, [_vp]),
+    "wlsqm_pool_stats": (_int, [_int, _i64p, _i64p]),
+    "wlsqm_pool_trim": (_int, [_int]),
     "wlsqm_solver_create": (_int, [_int, _i64, _vp, _vp, _vp, _vp, _int, _int, _int, _int, _int, C.POINTER(_vp)]),
     "wlsqm_solver_create_guest": (_int, [_vp, _int, _int, _int, C.POINTER(_vp)]),
     "wlsqm_solver_prepare_guest": (_int, [_vp]),
@@ -216,3 +218,16 @@ def pinned_free(arr: np.ndarray):
     ent = _PINNED.pop(arr.ctypes.data, None)
     if ent is not None:
         lib().wlsqm_pinned_free(ent[1])
+
+
+def pool_stats(device=None):
+    """(reserved, used) bytes of the library's device memory pool on ``device`` (``wlsqm_pool_stats``); (-1, -1) before
+    the first allocation there."""
+    r, u = C.c_int64(-1), C.c_int64(-1)
+    check(lib().wlsqm_pool_stats(int(default_device() if device is None else device), C.byref(r), C.byref(u)))
+    return int(r.value), int(u.value)
+
+
+def pool_trim(device=None):
+    """Return the cached blocks of the library's device memory pool to the driver (``wlsqm_pool_trim``)."""
+    check(lib().wlsqm_pool_trim(int(default_device() if device is None else device)))
