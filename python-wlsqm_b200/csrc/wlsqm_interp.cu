@@ -6,19 +6,23 @@
 //   expert_interpolate_nearest             wlsqm/fitter/expert.pyx:874-895   (the prange over queries)
 //   interpolate_fit                        wlsqm/fitter/interp.pyx:34-143    (single model, I == nullptr)
 //
-// The reference hard-codes, per (dimension, derivative), a table that shifts coefficients into a
-// scratch polynomial `fi2` and evaluates that with a nested Horner form.  Here the derivative
-// d^(p,q,r) of  sum_s fi[s] x^a y^b z^c/(a! b! c!)  is evaluated directly as
-//   sum_{a>=p, b>=q, c>=r} fi[s] x^(a-p) y^(b-q) z^(c-r) / ((a-p)! (b-q)! (c-r)!)
-// from the slot exponent tables, which are compile-time: the list of (slot, shifted monomial) terms of
-// every derivative is unrolled, the shifted monomials are shared between derivatives (they are the
-// model's own monomials of lower order), and a term costs one FMA.  A derivative slot >= no gives 0,
-// as interp.pyx:690-694.
+// The model is  f(x) = sum_s fi[s] dx^a dy^b dz^c / (a! b! c!)  with fi[s] the derivative values at the origin.
 //
-// One thread per query.  The model row fi[I[m]] (no doubles) and its origin are loaded once into
-// registers; queries that share a model hit the same lines in L1.  diff = WLSQM_DIFF_ALL (extension)
-// writes every slot: the warp's 32 x no results are transposed through shared memory so that the
-// global stores are contiguous.
+// One derivative slot D = (p,q,r) (the reference's interface): the reference hard-codes, per (dimension,
+// derivative), a table that shifts coefficients into a scratch polynomial `fi2` and evaluates that with a nested
+// Horner form.  Here the same nested form is generated from the compile-time slot exponent tables,
+//   d^D f = sum_{c>=r} dz^(c-r)/(c-r)! sum_{b>=q} dy^(b-q)/(b-q)! sum_{a>=p} fi[a,b,c] dx^(a-p)/(a-p)!,
+// each sum as  u0 + h/1 (u1 + h/2 (u2 + h/3 (u3 + ...))), and only the coefficients that D needs are loaded.
+// A derivative slot >= no gives 0, as interp.pyx:690-694.
+//
+// All slots in one pass (WLSQM_DIFF_ALL, extension): every derivative of the model at the query is the Taylor
+// shift of the coefficient array, done in place, axis by axis (u_i += h/(i+1) u_{i+1}, repeated): 2D order 4 costs
+// 40 FMAs and no registers beyond the 15 coefficients (the term-by-term form needs 70 FMAs and 45 live values).
+//
+// One thread per query, INTERP_Q queries per thread with their index and coordinate loads issued together.
+// WLSQM_DIFF_ALL with dense uniform rows: the warp's 32 x no results are transposed through shared memory so
+// that the global stores are contiguous.
+#include <cstdlib>
 #include <type_traits>
 #include "wlsqm_common.cuh"
 #include "wlsqm_kernels.h"
@@ -39,28 +43,79 @@ __host__ __device__ constexpr int slot_of(int a, int b, int c) {
     return -1;
 }
 
-// value of derivative slot D of the model (fi[0..no), monomials mono[s] = dx^a dy^b dz^c/(a! b! c!))
+// f(HI), f(HI-1), ..., f(LO) with compile-time indices (nothing if HI < LO)
+template <int HI, int LO, typename F>
+__device__ __forceinline__ void static_rfor(F&& f) {
+    if constexpr (HI >= LO) { f(std::integral_constant<int, HI>{}); static_rfor<HI - 1, LO>(f); }
+}
+
+// h / (t+1), t = 0..3: the factors of the nested form  u0 + h/1 (u1 + h/2 (u2 + h/3 (u3 + h/4 u4)))
+struct Steps { double s[4]; };
+__device__ __forceinline__ Steps steps_of(double h) { return Steps{{h, 0.5 * h, (1.0 / 3.0) * h, 0.25 * h}}; }
+
+// Value of derivative slot D of the model whose coefficients are at fg[0..no): nested Horner form over the
+// coefficients with exponents >= those of D.  Only those coefficients are read.
 template <int DIM, int D>
-__device__ __forceinline__ double eval_slot(int no, const double (&fi)[max_no<DIM>()], const double (&mono)[max_no<DIM>()]) {
-    double acc = 0.0;
-    // highest slots first (small terms first), like eval_taylor
-    static_for<0, max_no<DIM>()>([&](auto I) {
-        constexpr int S = max_no<DIM>() - 1 - decltype(I)::value;
-        constexpr SlotExp e = slot_exp<DIM>(S);
-        constexpr SlotExp d = slot_exp<DIM>(D);
-        if constexpr (S >= D && e.a >= d.a && e.b >= d.b && e.c >= d.c) {
-            constexpr int M = slot_of<DIM>(e.a - d.a, e.b - d.b, e.c - d.c);   // the shifted monomial is a lower slot
-            if (S < no) acc = fma(fi[S], mono[M], acc);
-        }
+__device__ __forceinline__ double eval_diff(const double* __restrict__ fg, int no, const Steps& hx, const Steps& hy,
+                                            const Steps& hz) {
+    constexpr SlotExp d = slot_exp<DIM>(D);
+    constexpr int p = d.a, q = d.b, r = d.c;
+    constexpr int CMAX = DIM >= 3 ? 4 - p - q : 0;
+    double vz = 0.0;
+    static_rfor<CMAX, r>([&](auto Cc) {
+        constexpr int c = decltype(Cc)::value;
+        constexpr int BMAX = DIM >= 2 ? 4 - p - c : 0;
+        double vy = 0.0;
+        static_rfor<BMAX, q>([&](auto Bc) {
+            constexpr int b = decltype(Bc)::value;
+            constexpr int AMAX = 4 - b - c;
+            double vx = 0.0;
+            static_rfor<AMAX, p>([&](auto Ac) {
+                constexpr int a = decltype(Ac)::value;
+                constexpr int S = slot_of<DIM>(a, b, c);
+                const double u = S < no ? __ldg(fg + S) : 0.0;
+                if constexpr (a == AMAX) vx = u;
+                else vx = fma(vx, hx.s[a - p], u);
+            });
+            if constexpr (b == BMAX) vy = vx;
+            else vy = fma(vy, hy.s[b - q], vx);
+        });
+        if constexpr (c == CMAX) vz = vy;
+        else vz = fma(vz, hz.s[c - r], vy);
     });
-    return acc;
+    return vz;
+}
+
+// In-place Taylor shift of the coefficient array along one axis: afterwards u[(a, b, c)] holds the a-th partial
+// derivative along AXIS, at offset h, of the line of coefficients with the other two exponents fixed.
+template <int DIM, int AXIS>
+__device__ __forceinline__ void taylor_shift(double (&u)[max_no<DIM>()], double h) {
+    const Steps st = steps_of(h);
+    static_for<0, 5>([&](auto Bc) {
+        static_for<0, 5>([&](auto Cc) {
+            constexpr int b = decltype(Bc)::value, c = decltype(Cc)::value;   // the other two exponents, in axis order
+            constexpr int A = 4 - b - c;
+            constexpr bool line = A >= 1 && (DIM >= 3 || c == 0) && (DIM >= 2 || b == 0);
+            if constexpr (line) {
+                static_for<0, A>([&](auto Jc) {
+                    constexpr int j = decltype(Jc)::value;
+                    static_rfor<A - 1, j>([&](auto Ic) {
+                        constexpr int i = decltype(Ic)::value;
+                        constexpr int S0 = AXIS == 0 ? slot_of<DIM>(i, b, c) : (AXIS == 1 ? slot_of<DIM>(b, i, c) : slot_of<DIM>(b, c, i));
+                        constexpr int S1 = AXIS == 0 ? slot_of<DIM>(i + 1, b, c) : (AXIS == 1 ? slot_of<DIM>(b, i + 1, c) : slot_of<DIM>(b, c, i + 1));
+                        u[S0] = fma(st.s[i], u[S1], u[S0]);
+                    });
+                });
+            }
+        });
+    });
 }
 
 // ALL = every derivative slot (WLSQM_DIFF_ALL); STAGE = transpose the warp's results through shared memory.
 // Each thread owns INTERP_Q queries, blockDim apart (coalesced), and issues their index and coordinate loads
 // together before the dependent model-row loads: the kernel is bound by load latency, not by arithmetic.
-template <int DIM, bool ALL, bool STAGE>
-__global__ void __launch_bounds__(INTERP_THREADS) interpolate_kernel(InterpParams P) {
+template <int DIM, bool ALL, bool STAGE, int MINB>
+__global__ void __launch_bounds__(INTERP_THREADS, MINB) interpolate_kernel(InterpParams P) {
     constexpr int NO = max_no<DIM>();
     constexpr int Q = INTERP_Q;
     extern __shared__ __align__(16) double stage[];     // STAGE: [warps][32 * no]
@@ -89,31 +144,26 @@ __global__ void __launch_bounds__(INTERP_THREADS) interpolate_kernel(InterpParam
         const double dy = DIM >= 2 ? xq[j][DIM >= 2 ? 1 : 0] - xo[DIM >= 2 ? 1 : 0] : 0.0;
         const double dz = DIM >= 3 ? xq[j][DIM >= 3 ? 2 : 0] - xo[DIM >= 3 ? 2 : 0] : 0.0;
         const double* fg = P.fi + i * P.fi_s0;
-        double fi[NO], mono[NO];
-#pragma unroll
-        for (int s = 0; s < NO; ++s) fi[s] = s < no ? __ldg(fg + s) : 0.0;
-        {
-            const Pow5 px = scaled_powers(dx), py = scaled_powers(dy), pz = scaled_powers(dz);
-            static_for<0, NO>([&](auto I) {
-                constexpr int S = decltype(I)::value;
-                mono[S] = monomial<DIM, S>(px, py, pz);
-            });
-        }
         if constexpr (!ALL) {
+            const Steps hx = steps_of(dx), hy = steps_of(dy), hz = steps_of(dz);
             double v = 0.0;
             static_for<0, NO>([&](auto I) {
                 constexpr int D = decltype(I)::value;
-                if (P.diff == D) v = eval_slot<DIM, D>(no, fi, mono);     // grid-uniform branch
+                if (P.diff == D) v = eval_diff<DIM, D>(fg, no, hx, hy, hz);     // grid-uniform branch
             });
             if (live) st_stream(P.out + m, bad ? __longlong_as_double(0x7ff8000000000000LL) : v);
         } else {
             // extension: every derivative slot of the model in one pass, out[m][0..no)
-            double val[NO];
-            static_for<0, NO>([&](auto I) {
-                constexpr int D = decltype(I)::value;
-                val[D] = eval_slot<DIM, D>(no, fi, mono);
-                if (bad) val[D] = __longlong_as_double(0x7ff8000000000000LL);
-            });
+            double u[NO];
+#pragma unroll
+            for (int s = 0; s < NO; ++s) u[s] = s < no ? __ldg(fg + s) : 0.0;
+            taylor_shift<DIM, 0>(u, dx);
+            if constexpr (DIM >= 2) taylor_shift<DIM, 1>(u, dy);
+            if constexpr (DIM >= 3) taylor_shift<DIM, 2>(u, dz);
+            if (bad) {
+#pragma unroll
+                for (int s = 0; s < NO; ++s) u[s] = __longlong_as_double(0x7ff8000000000000LL);
+            }
             if constexpr (STAGE) {
                 // uniform model size and dense rows: transpose through shared memory, then contiguous stores
                 const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -122,7 +172,7 @@ __global__ void __launch_bounds__(INTERP_THREADS) interpolate_kernel(InterpParam
                 __syncwarp();
 #pragma unroll
                 for (int d = 0; d < NO; ++d)
-                    if (d < nno) st[lane * nno + d] = val[d];
+                    if (d < nno) st[lane * nno + d] = u[d];
                 __syncwarp();
                 const long long m0 = m - lane;                       // first query of this warp
                 const long long left = (P.nx - m0) * nno;            // doubles this warp may still write
@@ -132,7 +182,7 @@ __global__ void __launch_bounds__(INTERP_THREADS) interpolate_kernel(InterpParam
                 double* o = P.out + m * P.out_s0;
 #pragma unroll
                 for (int d = 0; d < NO; ++d)
-                    if (d < no) st_stream(o + d, val[d]);
+                    if (d < no) st_stream(o + d, u[d]);
             }
         }
     }
@@ -174,18 +224,11 @@ __global__ void __launch_bounds__(128) continuous_kernel(InterpParams P, GridVie
                 const int order = P.order ? (int)P.order[i] : P.order_uniform;
                 const int no = number_of_dofs(DIM, order);
                 const double* fg = P.fi + i * P.fi_s0;
-                double fi[NO], mono[NO];
-#pragma unroll
-                for (int s = 0; s < NO; ++s) fi[s] = s < no ? __ldg(fg + s) : 0.0;
-                const Pow5 px = scaled_powers(dq[0]), py = scaled_powers(dq[1]), pz = scaled_powers(dq[2]);
-                static_for<0, NO>([&](auto I) {
-                    constexpr int S = decltype(I)::value;
-                    mono[S] = monomial<DIM, S>(px, py, pz);
-                });
+                const Steps hx = steps_of(dq[0]), hy = steps_of(dq[1]), hz = steps_of(dq[2]);
                 double value = 0.0;
                 static_for<0, NO>([&](auto I) {
                     constexpr int D = decltype(I)::value;
-                    if (P.diff == D) value = eval_slot<DIM, D>(no, fi, mono);
+                    if (P.diff == D) value = eval_diff<DIM, D>(fg, no, hx, hy, hz);
                 });
                 const double tmp = 1.0 - sqrt(d2 / r2);
                 const double w = tmp * tmp;
@@ -205,21 +248,31 @@ cudaError_t launch_interpolate_continuous(const InterpParams& P, const GridView&
     return cudaGetLastError();
 }
 
-template <int DIM, bool ALL, bool STAGE>
+template <int DIM, bool ALL, bool STAGE, int MINB>
 static cudaError_t launch_interp_t(const InterpParams& P, unsigned blocks, size_t smem, cudaStream_t st) {
     if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(interpolate_kernel<DIM, ALL, STAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(interpolate_kernel<DIM, ALL, STAGE, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
-    interpolate_kernel<DIM, ALL, STAGE><<<blocks, INTERP_THREADS, smem, st>>>(P);
+    interpolate_kernel<DIM, ALL, STAGE, MINB><<<blocks, INTERP_THREADS, smem, st>>>(P);
     return cudaGetLastError();
+}
+
+// resident CTAs per SM the register budget is held to (WLSQM_INTERP_MINB overrides, for tuning)
+template <int DIM, bool ALL, bool STAGE>
+static cudaError_t launch_interp_m(const InterpParams& P, unsigned blocks, size_t smem, cudaStream_t st) {
+    static const int forced = [] { const char* v = getenv("WLSQM_INTERP_MINB"); return (v && *v) ? atoi(v) : 0; }();
+    const int minb = forced > 0 ? forced : (DIM == 3 ? 2 : 4);
+    if (minb <= 2) return launch_interp_t<DIM, ALL, STAGE, 2>(P, blocks, smem, st);
+    if (minb == 3) return launch_interp_t<DIM, ALL, STAGE, 3>(P, blocks, smem, st);
+    return launch_interp_t<DIM, ALL, STAGE, 4>(P, blocks, smem, st);
 }
 
 template <int DIM>
 static cudaError_t launch_interp_d(const InterpParams& P, unsigned blocks, size_t smem, cudaStream_t st) {
-    if (P.diff >= 0) return launch_interp_t<DIM, false, false>(P, blocks, 0, st);
-    if (P.stage_no > 0) return launch_interp_t<DIM, true, true>(P, blocks, smem, st);
-    return launch_interp_t<DIM, true, false>(P, blocks, 0, st);
+    if (P.diff >= 0) return launch_interp_m<DIM, false, false>(P, blocks, 0, st);
+    if (P.stage_no > 0) return launch_interp_m<DIM, true, true>(P, blocks, smem, st);
+    return launch_interp_m<DIM, true, false>(P, blocks, 0, st);
 }
 
 cudaError_t launch_interpolate(const InterpParams& Pin, cudaStream_t st) {

@@ -9,7 +9,7 @@ properties of the mathematics):
     whole batch (what the multi-GPU sharding of DESIGN.md section 5 relies on),
   * hood indexing: device-side kNN == cKDTree on a sample, gather-on-device path == pre-gathered path, bit for bit,
   * knowns left untouched bit for bit at every point; sens^T fk == fi; NaN pattern of sens,
-  * interpolate: one all-slots pass == 15 reference-style calls bit for bit; evaluation at the model origin returns
+  * interpolate: one all-slots pass == 15 reference-style calls to a few ulp; evaluation at the model origin returns
     the stored coefficient exactly,
   * the oracle on every ~1000th case, with the noise-floor criterion of tests/parity.py.
 
@@ -204,9 +204,12 @@ def test_cfg5_full_size_interpolate(cloud2d):
     xq = x_d[I] + 0.3 * wl.H0 * (2 * torch.rand((nq, 2), dtype=torch.float64, device="cuda", generator=g) - 1)
     allv, _ = s.interpolate(xq, diff="all", I=I)
     assert tuple(allv.shape) == (nq, no)
+    # the all-slots pass (in-place Taylor shift) and the reference-style per-slot calls (nested Horner form) are two
+    # evaluation orders of the same polynomial: equal to a few ulp of the largest term
     for dslot in range(no):
         one, _ = s.interpolate(xq, diff=dslot, I=I)
-        assert torch.equal(one, allv[:, dslot]), dslot
+        err = float((one - allv[:, dslot]).abs().max() / allv[:, dslot].abs().max())
+        assert err <= 1e-13, (dslot, err)
     # evaluation at the model's own origin returns the stored coefficient exactly (every monomial but 1 vanishes)
     I0 = torch.arange(n, device="cuda", dtype=torch.int64)
     at0, _ = s.interpolate(x_d, diff="all", I=I0)

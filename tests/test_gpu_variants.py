@@ -163,7 +163,7 @@ def test_prepare_variants_agree_and_odd_counts(dim, order, k, n):
 
 
 def test_interpolate_variants():
-    """all-slots output: staged (dense rows) == direct (pitched rows) == one call per slot; odd query count"""
+    """all-slots output: staged (dense rows) == direct (pitched rows) ~= one call per slot (few ulp); odd query count"""
     torch = pytest.importorskip("torch")
     for dim, order, k, n in ((2, 4, 30, 700), (3, 3, 40, 300), (1, 4, 9, 500)):
         x, hoods, f = parity.make_case(n, dim, k)
@@ -183,7 +183,9 @@ def test_interpolate_variants():
         so.fi = fi_g.copy()
         for d in range(no):
             o1, _ = s.interpolate(xq, diff=d, I=I)
-            assert np.array_equal(o1, out_all[:, d]), (dim, d)
+            # all-slots pass = in-place Taylor shift, per-slot call = nested Horner form: same polynomial, two
+            # evaluation orders
+            assert np.abs(o1 - out_all[:, d]).max() <= 1e-13 * max(np.abs(o1).max(), 1e-300), (dim, d)
             oo = so.interpolate(xq, I, d)
             assert np.abs(o1 - oo).max() <= 1e-12 * max(np.abs(oo).max(), 1e-300), (dim, d)
         # device tensors: dense rows take the staged path, the library's own buffer for host output as well
