@@ -120,6 +120,74 @@ __device__ __forceinline__ double eval_taylor(int no, const double* __restrict__
     return acc;
 }
 
+// index of the slot with exponents (a,b,c), or -1 (compile-time search through the slot table)
+template <int DIM>
+__host__ __device__ constexpr int slot_of(int a, int b, int c) {
+    for (int s = 0; s < max_no<DIM>(); ++s) {
+        const SlotExp e = slot_exp<DIM>(s);
+        if (e.a == a && e.b == b && e.c == c) return s;
+    }
+    return -1;
+}
+
+// f(HI), f(HI-1), ..., f(LO) with compile-time indices (nothing if HI < LO)
+template <int HI, int LO, typename F>
+__device__ __forceinline__ void static_rfor(F&& f) {
+    if constexpr (HI >= LO) { f(std::integral_constant<int, HI>{}); static_rfor<HI - 1, LO>(f); }
+}
+
+// h / (t+1), t = 0..3: the factors of the nested form  u0 + h/1 (u1 + h/2 (u2 + h/3 (u3 + h/4 u4)))
+struct Steps { double s[4]; };
+__device__ __forceinline__ Steps steps_of(double h) { return Steps{{h, 0.5 * h, (1.0 / 3.0) * h, 0.25 * h}}; }
+
+// Value of derivative slot D of the model with coefficients coef(S), S < no: nested Horner form over the
+// coefficients with exponents >= those of D.  Only those coefficients are read.  D = 0 is the model value, the
+// same nested form as taylor_{1,2,3}D (wlsqm/fitter/polyeval.pyx:874-948 / 550-734 / 82-354).
+template <int DIM, int D, typename Coef>
+__device__ __forceinline__ double eval_diff_from(Coef&& coef, int no, const Steps& hx, const Steps& hy, const Steps& hz) {
+    constexpr SlotExp d = slot_exp<DIM>(D);
+    constexpr int p = d.a, q = d.b, r = d.c;
+    constexpr int CMAX = DIM >= 3 ? 4 - p - q : 0;
+    double vz = 0.0;
+    static_rfor<CMAX, r>([&](auto Cc) {
+        constexpr int c = decltype(Cc)::value;
+        constexpr int BMAX = DIM >= 2 ? 4 - p - c : 0;
+        double vy = 0.0;
+        static_rfor<BMAX, q>([&](auto Bc) {
+            constexpr int b = decltype(Bc)::value;
+            constexpr int AMAX = 4 - b - c;
+            double vx = 0.0;
+            static_rfor<AMAX, p>([&](auto Ac) {
+                constexpr int a = decltype(Ac)::value;
+                constexpr int S = slot_of<DIM>(a, b, c);
+                const double u = S < no ? coef(S) : 0.0;
+                if constexpr (a == AMAX) vx = u;
+                else vx = fma(vx, hx.s[a - p], u);
+            });
+            if constexpr (b == BMAX) vy = vx;
+            else vy = fma(vy, hy.s[b - q], vx);
+        });
+        if constexpr (c == CMAX) vz = vy;
+        else vz = fma(vz, hz.s[c - r], vy);
+    });
+    return vz;
+}
+
+// coefficients in global memory (read-only path)
+template <int DIM, int D>
+__device__ __forceinline__ double eval_diff(const double* __restrict__ fg, int no, const Steps& hx, const Steps& hy,
+                                            const Steps& hz) {
+    return eval_diff_from<DIM, D>([&](int S) { return __ldg(fg + S); }, no, hx, hy, hz);
+}
+
+// Model value at offset (dx,dy,dz) from the origin, coefficients anywhere (shared memory in the solve kernel's
+// refinement loop): one broadcast load and one FMA per coefficient.
+template <int DIM>
+__device__ __forceinline__ double eval_taylor_nested(int no, const double* fi, double dx, double dy, double dz) {
+    const Steps hx = steps_of(dx), hy = steps_of(DIM >= 2 ? dy : 0.0), hz = steps_of(DIM >= 3 ? dz : 0.0);
+    return eval_diff_from<DIM, 0>([&](int S) { return fi[S]; }, no, hx, hy, hz);
+}
+
 __device__ __forceinline__ double warp_max(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));

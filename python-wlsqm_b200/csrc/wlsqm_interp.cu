@@ -33,59 +33,6 @@ namespace wlsqm {
 constexpr int INTERP_THREADS = 256;
 constexpr int INTERP_Q = 4;        // queries per thread
 
-// index of the slot with exponents (a,b,c), or -1 (compile-time search through the slot table)
-template <int DIM>
-__host__ __device__ constexpr int slot_of(int a, int b, int c) {
-    for (int s = 0; s < max_no<DIM>(); ++s) {
-        const SlotExp e = slot_exp<DIM>(s);
-        if (e.a == a && e.b == b && e.c == c) return s;
-    }
-    return -1;
-}
-
-// f(HI), f(HI-1), ..., f(LO) with compile-time indices (nothing if HI < LO)
-template <int HI, int LO, typename F>
-__device__ __forceinline__ void static_rfor(F&& f) {
-    if constexpr (HI >= LO) { f(std::integral_constant<int, HI>{}); static_rfor<HI - 1, LO>(f); }
-}
-
-// h / (t+1), t = 0..3: the factors of the nested form  u0 + h/1 (u1 + h/2 (u2 + h/3 (u3 + h/4 u4)))
-struct Steps { double s[4]; };
-__device__ __forceinline__ Steps steps_of(double h) { return Steps{{h, 0.5 * h, (1.0 / 3.0) * h, 0.25 * h}}; }
-
-// Value of derivative slot D of the model whose coefficients are at fg[0..no): nested Horner form over the
-// coefficients with exponents >= those of D.  Only those coefficients are read.
-template <int DIM, int D>
-__device__ __forceinline__ double eval_diff(const double* __restrict__ fg, int no, const Steps& hx, const Steps& hy,
-                                            const Steps& hz) {
-    constexpr SlotExp d = slot_exp<DIM>(D);
-    constexpr int p = d.a, q = d.b, r = d.c;
-    constexpr int CMAX = DIM >= 3 ? 4 - p - q : 0;
-    double vz = 0.0;
-    static_rfor<CMAX, r>([&](auto Cc) {
-        constexpr int c = decltype(Cc)::value;
-        constexpr int BMAX = DIM >= 2 ? 4 - p - c : 0;
-        double vy = 0.0;
-        static_rfor<BMAX, q>([&](auto Bc) {
-            constexpr int b = decltype(Bc)::value;
-            constexpr int AMAX = 4 - b - c;
-            double vx = 0.0;
-            static_rfor<AMAX, p>([&](auto Ac) {
-                constexpr int a = decltype(Ac)::value;
-                constexpr int S = slot_of<DIM>(a, b, c);
-                const double u = S < no ? __ldg(fg + S) : 0.0;
-                if constexpr (a == AMAX) vx = u;
-                else vx = fma(vx, hx.s[a - p], u);
-            });
-            if constexpr (b == BMAX) vy = vx;
-            else vy = fma(vy, hy.s[b - q], vx);
-        });
-        if constexpr (c == CMAX) vz = vy;
-        else vz = fma(vz, hz.s[c - r], vy);
-    });
-    return vz;
-}
-
 // In-place Taylor shift of the coefficient array along one axis: afterwards u[(a, b, c)] holds the a-th partial
 // derivative along AXIS, at offset h, of the line of coefficients with the other two exponents fixed.
 template <int DIM, int AXIS>

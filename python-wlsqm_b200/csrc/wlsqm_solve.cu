@@ -292,13 +292,22 @@ __global__ void __launch_bounds__(ITER ? SOLVE_MAX_THREADS_ITER : SOLVE_MAX_THRE
                     }
                 }
             } else {
+                // columns 0..31 of every row: one store per row; columns 32..no-1 (at most three): the 32 lanes take
+                // the tails of TR = 32 / nt rows per store instead of one nearly empty store per row
                 double* sp = sn + lane;
                 const double* opp = op;
                 for (int k = 0; k < nk; ++k) {
                     st_stream(sp, unk0 ? opp[j0] : qnan);
-                    if (in1) st_stream(sp + 32, unk1 ? opp[j1] : qnan);
                     sp += P.sens_s1;
                     opp += nr;
+                }
+                const int nt = no - 32, TR = 32 / nt;
+                const int tr = lane / nt, to = 32 + lane % nt;
+                if (tr < TR) {
+                    const bool tkn = (knowns >> to) & 1LL;
+                    const int tj = to - __popcll(knowns & ((1LL << to) - 1));
+                    for (int k = tr; k < nk; k += TR)
+                        st_stream(sn + (long long)k * P.sens_s1 + to, tkn ? qnan : op[k * nr + tj]);
                 }
             }
         }
@@ -317,7 +326,7 @@ __global__ void __launch_bounds__(ITER ? SOLVE_MAX_THREADS_ITER : SOLVE_MAX_THRE
                     const double dx = xks[k * DIM] - xi0;
                     const double dy = DIM >= 2 ? xks[k * DIM + (DIM >= 2 ? 1 : 0)] - xi1 : 0.0;
                     const double dz = DIM >= 3 ? xks[k * DIM + (DIM >= 3 ? 2 : 0)] - xi2 : 0.0;
-                    const double r = fext[k] - eval_taylor<DIM>(no, fis, dx, dy, dz);
+                    const double r = fext[k] - eval_taylor_nested<DIM>(no, fis, dx, dy, dz);
                     rs[k] = r;
                     const double ar = fabs(r);
                     nrm = ar > nrm ? ar : nrm;          // `if tmp > norm` (impl.pyx:1037-1041)
