@@ -250,7 +250,10 @@ int config_solve(const wlsqm_solver* s, SolveParams& P, LaunchCfg& L, long long 
     // each) beat prefetch depth there (measured: 3D order 4 k=60 with sens, 16.7 -> 9.6 ms per 1M points).
     int S = env_int("WLSQM_SOLVE_STAGES", (iter && stage_bytes >= 8192) ? 1 : 2);
     S = std::max(1, std::min(S, 8));
-    const int max_warps = (iter ? SOLVE_MAX_THREADS_ITER : SOLVE_MAX_THREADS) / 32;
+    // ALGO_ITERATIVE in 1D / 2D: 12-warp CTAs at 80 registers, two per SM (the refinement loop is latency-bound:
+    // 24 resident warps beat 16)
+    const bool iter_small = iter && s->dim < 3;
+    const int max_warps = (iter ? (iter_small ? SOLVE_ITER12_THREADS : SOLVE_MAX_THREADS_ITER) : SOLVE_MAX_THREADS) / 32;
     int warps = env_int("WLSQM_SOLVE_WARPS", 16);
     warps = std::max(1, std::min(warps, max_warps));
     size_t per_warp = 0;
@@ -281,7 +284,7 @@ int config_solve(const wlsqm_solver* s, SolveParams& P, LaunchCfg& L, long long 
     L.threads = warps * 32;
     L.smem = (size_t)P.bar_off_bytes + (size_t)warps * S * 8;
     int ctas = (int)(SMEM_PER_SM / (L.smem + 1024));
-    ctas = std::max(1, std::min(ctas, std::max(1, env_int("WLSQM_SOLVE_MAXWARPS_SM", stage_bytes >= 3072 ? 16 : 32) / warps)));
+    ctas = std::max(1, std::min(ctas, std::max(1, env_int("WLSQM_SOLVE_MAXWARPS_SM", iter_small ? 24 : (stage_bytes >= 3072 ? 16 : 32)) / warps)));
     long long need = (ncases_launch + warps - 1) / warps;
     L.blocks = (int)std::max<long long>(1, std::min<long long>((long long)s->sm_count * ctas, need));
     return WLSQM_OK;
