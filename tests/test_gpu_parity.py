@@ -186,7 +186,8 @@ def test_interpolate_nearest_all_diffs_vs_oracle():
         oo = so.interpolate(xq, I, d)
         scale = max(np.abs(oo).max(), 1e-300)
         assert np.abs(og - oo).max() / scale < 1e-12, (d, np.abs(og - oo).max() / scale)
-        assert np.allclose(allg[:, d], og, rtol=1e-13, atol=1e-300)
+        # all-slots pass (in-place Taylor shift) vs per-slot call (nested Horner): two evaluation orders
+        assert np.abs(allg[:, d] - og).max() <= 1e-13 * scale
     # a model index equal to ncases ("no neighbour found") poisons the whole output (expert.pyx:862-870);
     # with current SciPy a NaN query already raises inside cKDTree.query, for the reference as for us
     I_bad = I[:10].copy()
