@@ -194,6 +194,17 @@ WLSQM_API int wlsqm_mgetrf(int n, int64_t nlhs, double* A, int32_t* ipiv, int de
 WLSQM_API int wlsqm_mgetrs(int n, int64_t nlhs, const double* LU, const int32_t* ipiv, double* b, int device); /* mgeneralfactored[p] */
 WLSQM_API int wlsqm_mgesv(int n, int64_t nlhs, double* A, int32_t* ipiv, double* b, int device);       /* mgeneral[p] */
 
+/* ---- batched symmetric drivers: wlsqm/utils/lapackdrivers.pyx:1107-1354, 204-278 -------------------- */
+/* Bunch-Kaufman U D U^T with LAPACK's uplo = 'U' conventions (only the upper triangle of A is read and written; ipiv is
+ * dsytrf's: > 0 a 1x1 block, a pair of equal negative entries a 2x2 block).  Same layouts as the general drivers.
+ * msytrf = msymmetricfactor[p] (dsytrf, :1199-1233,1275-1314); msytrs = msymmetricfactored[p] (dsytrs, :1236-1272,
+ * 1317-1354); msysv = msymmetric[p] (dsysv, :1107-1196; ipiv may be NULL -- the reference discards it);
+ * msymmetrize = msymmetrize[p] (A <- (A + A^T)/2, :204-278). */
+WLSQM_API int wlsqm_msytrf(int n, int64_t nlhs, double* A, int32_t* ipiv, int device);
+WLSQM_API int wlsqm_msytrs(int n, int64_t nlhs, const double* UDU, const int32_t* ipiv, double* b, int device);
+WLSQM_API int wlsqm_msysv(int n, int64_t nlhs, double* A, int32_t* ipiv, double* b, int device);
+WLSQM_API int wlsqm_msymmetrize(int n, int64_t nlhs, double* A, int device);
+
 #ifdef __cplusplus
 }
 #endif

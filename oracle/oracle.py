@@ -185,6 +185,144 @@ def mgetrs(LU, ipiv, b):
     b[...] = bt.T
 
 
+# ---- symmetric indefinite drivers: numpy restatement of LAPACK's dsytf2 / dsytrs, uplo = 'U' ------------------
+# The reference reaches them through scipy.linalg.cython_lapack (wlsqm/utils/lapackdrivers.pyx:73-80; call sites
+# :1139-1146 dsysv, :1222-1230 dsytrf, :1263-1270 dsytrs), i.e. SciPy's bundled OpenBLAS/LAPACK (SciPy 1.18.1 here;
+# the reference pins scipy>=1.9).  The algorithm is the published Bunch-Kaufman diagonal pivoting of LAPACK 3.x
+# dsytf2.f / dsytrs.f; pinned by tests/golden/golden_sym.npz (outputs of the unmodified reference).
+
+def sytf2_upper(A):
+    """in place on the upper triangle of the (n, n) array A; returns ipiv (int32, LAPACK's 1-based signed convention)"""
+    n = A.shape[0]
+    ipiv = np.zeros(n, dtype=np.int32)
+    alpha = (1.0 + np.sqrt(17.0)) / 8.0
+    k = n - 1
+    while k >= 0:
+        kstep, kp = 1, k
+        absakk = abs(A[k, k])
+        imax, colmax = 0, 0.0
+        if k > 0:
+            imax = int(np.argmax(np.abs(A[:k, k])))
+            colmax = abs(A[imax, k])
+        if max(absakk, colmax) == 0.0 or absakk != absakk:
+            kp = k
+        else:
+            if absakk >= alpha * colmax:
+                kp = k
+            else:
+                rowmax = np.abs(A[imax, imax + 1:k + 1]).max()
+                if imax > 0:
+                    rowmax = max(rowmax, np.abs(A[:imax, imax]).max())
+                if absakk >= alpha * colmax * (colmax / rowmax):
+                    kp = k
+                elif abs(A[imax, imax]) >= alpha * rowmax:
+                    kp = imax
+                else:
+                    kp, kstep = imax, 2
+            kk = k - kstep + 1
+            if kp != kk:
+                A[:kp, [kk, kp]] = A[:kp, [kp, kk]]
+                t = A[kp + 1:kk, kk].copy()
+                A[kp + 1:kk, kk] = A[kp, kp + 1:kk]
+                A[kp, kp + 1:kk] = t
+                A[kk, kk], A[kp, kp] = A[kp, kp], A[kk, kk]
+                if kstep == 2:
+                    A[k - 1, k], A[kp, k] = A[kp, k], A[k - 1, k]
+            if kstep == 1:
+                r1 = 1.0 / A[k, k]
+                x = A[:k, k].copy()
+                for j in range(k):
+                    if x[j] != 0.0:
+                        A[:j + 1, j] += x[:j + 1] * (-r1 * x[j])
+                A[:k, k] *= r1
+            elif k > 1:
+                d12 = A[k - 1, k]
+                d22, d11 = A[k - 1, k - 1] / d12, A[k, k] / d12
+                t = 1.0 / (d11 * d22 - 1.0)
+                d12 = t / d12
+                for j in range(k - 2, -1, -1):
+                    wkm1 = d12 * (d11 * A[j, k - 1] - A[j, k])
+                    wk = d12 * (d22 * A[j, k] - A[j, k - 1])
+                    A[:j + 1, j] = A[:j + 1, j] - A[:j + 1, k] * wk - A[:j + 1, k - 1] * wkm1
+                    A[j, k], A[j, k - 1] = wk, wkm1
+        if kstep == 1:
+            ipiv[k] = kp + 1
+        else:
+            ipiv[k] = ipiv[k - 1] = -(kp + 1)
+        k -= kstep
+    return ipiv
+
+
+def sytrs_upper(A, ipiv, b):
+    """b <- A^-1 b with the factors of sytf2_upper, in place"""
+    n = A.shape[0]
+    k = n - 1
+    while k >= 0:
+        if ipiv[k] > 0:
+            kp = ipiv[k] - 1
+            if kp != k:
+                b[k], b[kp] = b[kp], b[k]
+            b[:k] -= A[:k, k] * b[k]
+            b[k] *= 1.0 / A[k, k]
+            k -= 1
+        else:
+            kp = -ipiv[k] - 1
+            if kp != k - 1:
+                b[k - 1], b[kp] = b[kp], b[k - 1]
+            b[:k - 1] -= A[:k - 1, k] * b[k]
+            b[:k - 1] -= A[:k - 1, k - 1] * b[k - 1]
+            akm1k = A[k - 1, k]
+            akm1, ak = A[k - 1, k - 1] / akm1k, A[k, k] / akm1k
+            denom = akm1 * ak - 1.0
+            bkm1, bk = b[k - 1] / akm1k, b[k] / akm1k
+            b[k - 1] = (ak * bkm1 - bk) / denom
+            b[k] = (akm1 * bk - bkm1) / denom
+            k -= 2
+    k = 0
+    while k < n:
+        if ipiv[k] > 0:
+            b[k] -= A[:k, k] @ b[:k]
+            kp = ipiv[k] - 1
+            if kp != k:
+                b[k], b[kp] = b[kp], b[k]
+            k += 1
+        else:
+            b[k] -= A[:k, k] @ b[:k]
+            b[k + 1] -= A[:k, k + 1] @ b[:k]
+            kp = -ipiv[k] - 1
+            if kp != k:
+                b[k], b[kp] = b[kp], b[k]
+            k += 2
+    return b
+
+
+def msytrf(A, ipiv):
+    """batched restatement of msymmetricfactor_c (lapackdrivers.pyx:1215-1233): A (n,n,nlhs) F, ipiv (n,nlhs) F"""
+    for l in range(A.shape[2]):
+        M = np.array(A[:, :, l])
+        ipiv[:, l] = sytf2_upper(M)
+        iu = np.triu_indices(A.shape[0])
+        A[:, :, l][iu] = M[iu]
+
+
+def msytrs(A, ipiv, b):
+    """batched restatement of msymmetricfactored_c (lapackdrivers.pyx:1263-1272)"""
+    for l in range(A.shape[2]):
+        x = np.array(b[:, l])
+        sytrs_upper(np.array(A[:, :, l]), ipiv[:, l], x)
+        b[:, l] = x
+
+
+def msymmetrize(A):
+    """msymmetrize_c (lapackdrivers.pyx:219-230)"""
+    n = A.shape[0]
+    for j in range(1, n):
+        for i in range(j):
+            t = 0.5 * (A[i, j, :] + A[j, i, :])
+            A[i, j, :] = t
+            A[j, i, :] = t
+
+
 def load_reference():
     """Import the compiled unmodified reference from oracle/_ref (None if it is not built)."""
     ref = HERE / "_ref"

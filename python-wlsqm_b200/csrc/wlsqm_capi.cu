@@ -1182,14 +1182,16 @@ int wlsqm_interpolate_fit(int dimension, int order, const double* xi, const doub
     return done(WLSQM_OK);
 }
 
-static int lapack_common(int n, int64_t nlhs, double* A, int32_t* ipiv, double* b, int device, int do_factor, int do_solve) {
+static int lapack_common(int n, int64_t nlhs, double* A, int32_t* ipiv, double* b, int device, int do_factor, int do_solve,
+                         int sym = 0) {
     if (n < 0 || nlhs < 0) return fail(WLSQM_E_VALUE, "n and nlhs must be >= 0");
     if (n == 0 || nlhs == 0) return WLSQM_OK;
     if (wlsqm_device_count() < 1) return fail(WLSQM_E_CUDA, "no CUDA device available (there is no CPU fallback)");
     CU(cudaSetDevice(device));
     const size_t na = (size_t)n * n * nlhs * 8, np = (size_t)n * nlhs * 4, nb = (size_t)n * nlhs * 8;
     DevBuf ba, bp, bb;
-    const bool a_dev = is_device_ptr(A), p_dev = is_device_ptr(ipiv), b_dev = b ? is_device_ptr(b) != 0 : true;
+    // ipiv may be NULL for the symmetric dsysv driver (the reference's msymmetric keeps its pivots to itself)
+    const bool a_dev = is_device_ptr(A), p_dev = ipiv ? is_device_ptr(ipiv) != 0 : true, b_dev = b ? is_device_ptr(b) != 0 : true;
     int rc = WLSQM_OK;
     if (!a_dev) rc = ba.reserve(na);
     if (!rc && !p_dev) rc = bp.reserve(np);
@@ -1204,10 +1206,14 @@ static int lapack_common(int n, int64_t nlhs, double* A, int32_t* ipiv, double* 
     if (!a_dev) e = cudaMemcpyAsync(dA, A, na, cudaMemcpyHostToDevice, st);
     if (e == cudaSuccess && !p_dev && !do_factor) e = cudaMemcpyAsync(dP, ipiv, np, cudaMemcpyHostToDevice, st);
     if (e == cudaSuccess && do_solve && !b_dev) e = cudaMemcpyAsync(dB, b, nb, cudaMemcpyHostToDevice, st);
-    if (e == cudaSuccess && do_factor) e = launch_getrf(n, nlhs, dA, dP, st);
-    if (e == cudaSuccess && do_solve) e = launch_getrs(n, nlhs, dA, dP, dB, st);
+    if (sym) {
+        if (e == cudaSuccess) e = launch_sy(n, nlhs, dA, dP, do_solve ? dB : nullptr, do_factor, st);
+    } else {
+        if (e == cudaSuccess && do_factor) e = launch_getrf(n, nlhs, dA, dP, st);
+        if (e == cudaSuccess && do_solve) e = launch_getrs(n, nlhs, dA, dP, dB, st);
+    }
     if (e == cudaSuccess && do_factor && !a_dev) e = cudaMemcpyAsync(A, dA, na, cudaMemcpyDeviceToHost, st);
-    if (e == cudaSuccess && do_factor && !p_dev) e = cudaMemcpyAsync(ipiv, dP, np, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess && do_factor && !p_dev && ipiv) e = cudaMemcpyAsync(ipiv, dP, np, cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess && do_solve && !b_dev) e = cudaMemcpyAsync(b, dB, nb, cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     if (e == cudaErrorInvalidValue) return done(fail(WLSQM_E_VALUE, "n = %d is too large for the shared-memory LU", n));
@@ -1226,6 +1232,40 @@ int wlsqm_mgetrs(int n, int64_t nlhs, const double* LU, const int32_t* ipiv, dou
 int wlsqm_mgesv(int n, int64_t nlhs, double* A, int32_t* ipiv, double* b, int device) {
     if (!A || !ipiv || !b) return fail(WLSQM_E_VALUE, "NULL argument");
     return lapack_common(n, nlhs, A, ipiv, b, device, 1, 1);
+}
+
+int wlsqm_msytrf(int n, int64_t nlhs, double* A, int32_t* ipiv, int device) {
+    if (!A || !ipiv) return fail(WLSQM_E_VALUE, "NULL argument");
+    return lapack_common(n, nlhs, A, ipiv, nullptr, device, 1, 0, 1);
+}
+int wlsqm_msytrs(int n, int64_t nlhs, const double* UDU, const int32_t* ipiv, double* b, int device) {
+    if (!UDU || !ipiv || !b) return fail(WLSQM_E_VALUE, "NULL argument");
+    return lapack_common(n, nlhs, const_cast<double*>(UDU), const_cast<int32_t*>(ipiv), b, device, 0, 1, 1);
+}
+int wlsqm_msysv(int n, int64_t nlhs, double* A, int32_t* ipiv, double* b, int device) {
+    if (!A || !b) return fail(WLSQM_E_VALUE, "NULL argument");
+    return lapack_common(n, nlhs, A, ipiv, b, device, 1, 1, 1);
+}
+int wlsqm_msymmetrize(int n, int64_t nlhs, double* A, int device) {
+    if (n < 0 || nlhs < 0) return fail(WLSQM_E_VALUE, "n and nlhs must be >= 0");
+    if (n == 0 || nlhs == 0) return WLSQM_OK;
+    if (!A) return fail(WLSQM_E_VALUE, "NULL argument");
+    if (wlsqm_device_count() < 1) return fail(WLSQM_E_CUDA, "no CUDA device available (there is no CPU fallback)");
+    CU(cudaSetDevice(device));
+    const size_t na = (size_t)n * n * nlhs * 8;
+    const bool a_dev = is_device_ptr(A);
+    DevBuf ba;
+    if (!a_dev) { int rc = ba.reserve(na); if (rc) return rc; }
+    cudaStream_t st = nullptr;
+    double* dA = a_dev ? A : (double*)ba.p;
+    cudaError_t e = cudaSuccess;
+    if (!a_dev) e = cudaMemcpyAsync(dA, A, na, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = launch_symmetrize(n, nlhs, dA, st);
+    if (e == cudaSuccess && !a_dev) e = cudaMemcpyAsync(A, dA, na, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    ba.release();
+    if (e != cudaSuccess) return fail(WLSQM_E_CUDA, "msymmetrize: %s", cudaGetErrorString(e));
+    return WLSQM_OK;
 }
 
 }  // extern "C"

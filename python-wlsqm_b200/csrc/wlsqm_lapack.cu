@@ -144,6 +144,254 @@ cudaError_t launch_getrs(int n, long long nlhs, const double* LU, const int* ipi
     return cudaGetLastError();
 }
 
+// ---- symmetric indefinite systems: Bunch-Kaufman U D U^T (dsytrf / dsytrs / dsysv, uplo = 'U') ---------------
+// Replaces the batched symmetric drivers of wlsqm/utils/lapackdrivers.pyx:
+//   msymmetricfactor[p]_c   :1199-1233, 1275-1314   (dsytrf 'U' per system)
+//   msymmetricfactored[p]_c :1236-1272, 1317-1354   (dsytrs 'U' per system, one right-hand side each)
+//   msymmetric[p]_c         :1107-1196              (dsysv = both)
+//   msymmetrize[p]_c        :204-278                (A <- (A + A^T)/2)
+// Same layout as the general drivers; ipiv is LAPACK's: ipiv[k] > 0 = 1x1 block, rows/columns k and ipiv[k]
+// interchanged; ipiv[k] = ipiv[k-1] < 0 = 2x2 block in (k-1, k), rows/columns k-1 and -ipiv[k] interchanged.
+// Only the upper triangle is read and written.  The factorisation is LAPACK's unblocked dsytf2 (the algorithm
+// dsytrf runs for matrices up to its block size), diagonal pivoting with alpha = (1 + sqrt(17)) / 8.
+
+// index of the first entry of largest magnitude among v(i), i = lo .. hi-1 (idamax); v by callable; warp-wide result
+template <typename V>
+__device__ __forceinline__ int warp_idamax(int lo, int hi, int lane, V&& v, double& vmax) {
+    double best = -1.0;
+    int bi = lo;
+    for (int i = lo + lane; i < hi; i += 32) {
+        const double a = fabs(v(i));
+        if (a > best) { best = a; bi = i; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+    }
+    vmax = best < 0.0 ? 0.0 : best;
+    return bi;
+}
+
+// A: n x n column-major in shared memory (leading dimension lda), upper triangle; ipiv 0-based row indices with
+// LAPACK's sign convention applied on store (see sytrf_kernel); w: 2n doubles of scratch
+__device__ __forceinline__ void warp_sytf2_upper(int n, double* A, int lda, int* ipiv, double* w, int lane) {
+    const double alpha = (1.0 + sqrt(17.0)) / 8.0;
+    int k = n - 1;                      // 0-based index of the current column
+    while (k >= 0) {
+        int kstep = 1, kp = k;
+        const double absakk = fabs(A[k + lda * k]);
+        double colmax = 0.0;
+        int imax = 0;
+        if (k > 0) imax = warp_idamax(0, k, lane, [&](int i) { return A[i + lda * k]; }, colmax);
+        if (fmax(absakk, colmax) == 0.0 || absakk != absakk) {
+            kp = k;                     // singular (or NaN) column: no interchange, LAPACK sets info and goes on
+        } else {
+            if (absakk >= alpha * colmax) {
+                kp = k;
+            } else {
+                // largest off-diagonal entry in row imax of the leading (k+1) x (k+1) block
+                double rowmax = 0.0, r2 = 0.0;
+                warp_idamax(imax + 1, k + 1, lane, [&](int j) { return A[imax + lda * j]; }, rowmax);
+                if (imax > 0) {
+                    warp_idamax(0, imax, lane, [&](int i) { return A[i + lda * imax]; }, r2);
+                    rowmax = fmax(rowmax, r2);
+                }
+                if (absakk >= alpha * colmax * (colmax / rowmax)) kp = k;
+                else if (fabs(A[imax + lda * imax]) >= alpha * rowmax) kp = imax;
+                else { kp = imax; kstep = 2; }
+            }
+            const int kk = k - kstep + 1;
+            if (kp != kk) {
+                // interchange rows and columns kk and kp in the leading block
+                for (int i = lane; i < kp; i += 32) {
+                    const double t = A[i + lda * kk]; A[i + lda * kk] = A[i + lda * kp]; A[i + lda * kp] = t;
+                }
+                for (int j = kp + 1 + lane; j < kk; j += 32) {
+                    const double t = A[j + lda * kk]; A[j + lda * kk] = A[kp + lda * j]; A[kp + lda * j] = t;
+                }
+                if (lane == 0) {
+                    double t = A[kk + lda * kk]; A[kk + lda * kk] = A[kp + lda * kp]; A[kp + lda * kp] = t;
+                    if (kstep == 2) { t = A[k - 1 + lda * k]; A[k - 1 + lda * k] = A[kp + lda * k]; A[kp + lda * k] = t; }
+                }
+                __syncwarp();
+            }
+            if (kstep == 1) {
+                // A := A - U(k) D(k) U(k)^T = A - x x^T / d  (dsyr), then x := x / d
+                const double r1 = 1.0 / A[k + lda * k];
+                for (int j = 0; j < k; ++j) {
+                    const double xj = A[j + lda * k];
+                    if (xj != 0.0) {
+                        const double t = -r1 * xj;
+                        for (int i = lane; i <= j; i += 32) A[i + lda * j] = fma(A[i + lda * k], t, A[i + lda * j]);
+                    }
+                }
+                __syncwarp();
+                for (int i = lane; i < k; i += 32) A[i + lda * k] *= r1;
+                __syncwarp();
+            } else if (k > 1) {
+                double d12 = A[k - 1 + lda * k];
+                const double d22 = A[k - 1 + lda * (k - 1)] / d12, d11 = A[k + lda * k] / d12;
+                const double t = 1.0 / (d11 * d22 - 1.0);
+                d12 = t / d12;
+                for (int j = lane; j < k - 1; j += 32) {
+                    w[j] = d12 * (d11 * A[j + lda * (k - 1)] - A[j + lda * k]);        // wkm1
+                    w[n + j] = d12 * (d22 * A[j + lda * k] - A[j + lda * (k - 1)]);    // wk
+                }
+                __syncwarp();
+                for (int j = k - 2; j >= 0; --j) {
+                    const double wkm1 = w[j], wk = w[n + j];
+                    for (int i = lane; i <= j; i += 32)
+                        A[i + lda * j] = A[i + lda * j] - A[i + lda * k] * wk - A[i + lda * (k - 1)] * wkm1;
+                }
+                __syncwarp();
+                for (int j = lane; j < k - 1; j += 32) {
+                    A[j + lda * k] = w[n + j];
+                    A[j + lda * (k - 1)] = w[j];
+                }
+                __syncwarp();
+            }
+        }
+        if (lane == 0) {
+            if (kstep == 1) ipiv[k] = kp + 1;
+            else { ipiv[k] = -(kp + 1); ipiv[k - 1] = -(kp + 1); }
+        }
+        k -= kstep;
+    }
+    __syncwarp();
+}
+
+// dsytrs 'U', one right-hand side: b := A^-1 b with A = U D U^T from warp_sytf2_upper (ipiv 1-based, LAPACK signs)
+__device__ __forceinline__ void warp_sytrs_upper(int n, const double* A, int lda, const int* ipiv, double* b, int lane) {
+    // U D x = b
+    int k = n - 1;
+    while (k >= 0) {
+        if (ipiv[k] > 0) {
+            const int kp = ipiv[k] - 1;
+            if (lane == 0 && kp != k) { const double t = b[k]; b[k] = b[kp]; b[kp] = t; }
+            __syncwarp();
+            const double bk = b[k];
+            for (int i = lane; i < k; i += 32) b[i] -= A[i + lda * k] * bk;
+            __syncwarp();
+            if (lane == 0) b[k] = bk * (1.0 / A[k + lda * k]);
+            __syncwarp();
+            k -= 1;
+        } else {
+            const int kp = -ipiv[k] - 1;
+            if (lane == 0 && kp != k - 1) { const double t = b[k - 1]; b[k - 1] = b[kp]; b[kp] = t; }
+            __syncwarp();
+            const double bk = b[k], bkm = b[k - 1];
+            for (int i = lane; i < k - 1; i += 32) b[i] = (b[i] - A[i + lda * k] * bk) - A[i + lda * (k - 1)] * bkm;
+            __syncwarp();
+            if (lane == 0) {
+                const double akm1k = A[k - 1 + lda * k];
+                const double akm1 = A[k - 1 + lda * (k - 1)] / akm1k, ak = A[k + lda * k] / akm1k;
+                const double denom = akm1 * ak - 1.0;
+                const double bkm1 = bkm / akm1k, bkk = bk / akm1k;
+                b[k - 1] = (ak * bkm1 - bkk) / denom;
+                b[k] = (akm1 * bkk - bkm1) / denom;
+            }
+            __syncwarp();
+            k -= 2;
+        }
+    }
+    // U^T x = b
+    k = 0;
+    while (k < n) {
+        const int nb = ipiv[k] > 0 ? 1 : 2;
+        double d0 = 0.0, d1 = 0.0;
+        for (int i = lane; i < k; i += 32) {
+            d0 = fma(A[i + lda * k], b[i], d0);
+            if (nb == 2) d1 = fma(A[i + lda * (k + 1)], b[i], d1);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            d0 += __shfl_xor_sync(0xffffffffu, d0, o);
+            d1 += __shfl_xor_sync(0xffffffffu, d1, o);
+        }
+        __syncwarp();
+        if (lane == 0) {
+            b[k] -= d0;
+            if (nb == 2) b[k + 1] -= d1;
+            const int kp = (ipiv[k] > 0 ? ipiv[k] : -ipiv[k]) - 1;
+            if (kp != k) { const double t = b[k]; b[k] = b[kp]; b[kp] = t; }
+        }
+        __syncwarp();
+        k += nb;
+    }
+}
+
+// factor (and, with bg != nullptr, solve) nlhs symmetric systems; do_factor = 0: A and ipiv hold factors already
+__global__ void sy_kernel(int n, long long nlhs, double* __restrict__ Ag, int* __restrict__ ipivg, double* __restrict__ bg,
+                          int do_factor, int warp_doubles) {
+    extern __shared__ __align__(16) double smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int lda = n | 1;
+    double* A = smem + (size_t)warp * warp_doubles;
+    double* w = A + (size_t)lda * n;          // 2n scratch, the first n double as the right-hand side
+    int* piv = reinterpret_cast<int*>(w + 2 * n);
+    for (long long l = (long long)blockIdx.x * nwarps + warp; l < nlhs; l += (long long)gridDim.x * nwarps) {
+        double* g = Ag + l * (long long)n * n;
+        for (int t = lane; t < n * n; t += 32) A[(t % n) + lda * (t / n)] = g[t];
+        if (!do_factor)
+            for (int t = lane; t < n; t += 32) piv[t] = ipivg[l * n + t];
+        __syncwarp();
+        if (do_factor) {
+            warp_sytf2_upper(n, A, lda, piv, w, lane);
+            // only the upper triangle (incl. diagonal) is written back: the strict lower triangle is not referenced
+            for (int t = lane; t < n * n; t += 32) {
+                const int i = t % n, j = t / n;
+                if (i <= j) g[t] = A[i + lda * j];
+            }
+            if (ipivg)
+                for (int t = lane; t < n; t += 32) ipivg[l * n + t] = piv[t];
+        }
+        if (bg) {
+            for (int t = lane; t < n; t += 32) w[t] = bg[l * n + t];
+            __syncwarp();
+            warp_sytrs_upper(n, A, lda, piv, w, lane);
+            for (int t = lane; t < n; t += 32) bg[l * n + t] = w[t];
+        }
+        __syncwarp();
+    }
+}
+
+__global__ void symmetrize_kernel(int n, long long nlhs, double* __restrict__ Ag) {
+    const long long per = (long long)n * n;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < nlhs * per; t += (long long)gridDim.x * blockDim.x) {
+        const long long l = t / per;
+        const int r = (int)(t - l * per), i = r % n, j = r / n;
+        if (i < j) {   // strict upper triangle: this thread owns the pair (i,j), (j,i)
+            double* g = Ag + l * per;
+            const double v = 0.5 * (g[i + (long long)n * j] + g[j + (long long)n * i]);
+            g[i + (long long)n * j] = v;
+            g[j + (long long)n * i] = v;
+        }
+    }
+}
+
+cudaError_t launch_sy(int n, long long nlhs, double* A, int* ipiv, double* b, int do_factor, cudaStream_t st) {
+    if (nlhs == 0 || n == 0) return cudaSuccess;
+    int warps, wd;
+    size_t smem;
+    if (lapack_cfg(n, warps, smem, wd, 2 * n + (n + 1) / 2 + 1)) return cudaErrorInvalidValue;
+    cudaError_t e = cudaFuncSetAttribute(sy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    long long blocks = (nlhs + warps - 1) / warps;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    sy_kernel<<<(unsigned)blocks, warps * 32, smem, st>>>(n, nlhs, A, ipiv, b, do_factor, wd);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_symmetrize(int n, long long nlhs, double* A, cudaStream_t st) {
+    if (nlhs == 0 || n < 2) return cudaSuccess;
+    long long blocks = ((long long)n * n * nlhs + 255) / 256;
+    if (blocks > 148 * 32) blocks = 148 * 32;
+    symmetrize_kernel<<<(unsigned)blocks, 256, 0, st>>>(n, nlhs, A);
+    return cudaGetLastError();
+}
+
 // ---- condition numbers ---------------------------------------------------------------------------
 __global__ void cond_kernel(long long ncases, const CaseMeta* meta, CaseMeta uni, const double* __restrict__ As,
                             int as_stride, double* __restrict__ cond, int warp_doubles) {

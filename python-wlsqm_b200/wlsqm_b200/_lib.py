@@ -66,6 +66,10 @@ SIGNATURES = {
     "wlsqm_mgetrf": (_int, [_int, _i64, _vp, _vp, _int]),
     "wlsqm_mgetrs": (_int, [_int, _i64, _vp, _vp, _vp, _int]),
     "wlsqm_mgesv": (_int, [_int, _i64, _vp, _vp, _vp, _int]),
+    "wlsqm_msytrf": (_int, [_int, _i64, _vp, _vp, _int]),
+    "wlsqm_msytrs": (_int, [_int, _i64, _vp, _vp, _vp, _int]),
+    "wlsqm_msysv": (_int, [_int, _i64, _vp, _vp, _vp, _int]),
+    "wlsqm_msymmetrize": (_int, [_int, _i64, _vp, _int]),
 }
 
 

@@ -1,8 +1,10 @@
-"""Batched general dense drivers on the GPU: ``mgeneral[p]``, ``mgeneralfactor[p]``, ``mgeneralfactored[p]``.
+"""Batched dense drivers on the GPU: ``mgeneral[p]``, ``mgeneralfactor[p]``, ``mgeneralfactored[p]`` and their
+symmetric counterparts ``msymmetric[p]``, ``msymmetricfactor[p]``, ``msymmetricfactored[p]``, ``msymmetrize[p]``.
 
-Host-side mirror of the batched *general* family of ``wlsqm/utils/lapackdrivers.pyx:1551-1723`` (the
-pieces on the fitter's path; the symmetric / tridiagonal / scaling utilities of that module are a
-generic LAPACK convenience layer outside the hot path -- keep importing the reference for those).
+Host-side mirror of the batched families of ``wlsqm/utils/lapackdrivers.pyx`` (general: ``:1551-1723``, on the
+fitter's path; symmetric: ``:1107-1354`` and ``:204-278``).  The single-system convenience
+wrappers of that module (``general``, ``symmetric``, ``tridiag``, the ``rescale_*`` family, ...) solve one small
+system per call and have nothing to batch -- keep importing the reference for those.
 Layout is the reference's: ``A`` (n, n, nlhs) Fortran-contiguous, ``b`` (n, nlhs) Fortran,
 ``ipiv`` (n, nlhs) int32 Fortran, 1-based pivots; everything is overwritten in place; LAPACK's ``info``
 is not reported (the reference drops it too: a singular system silently yields inf/NaN).
@@ -14,7 +16,9 @@ import numpy as np
 
 from .. import _lib
 
-__all__ = ["mgeneral", "mgeneralp", "mgeneralfactor", "mgeneralfactorp", "mgeneralfactored", "mgeneralfactoredp"]
+__all__ = ["mgeneral", "mgeneralp", "mgeneralfactor", "mgeneralfactorp", "mgeneralfactored", "mgeneralfactoredp",
+           "msymmetric", "msymmetricp", "msymmetricfactor", "msymmetricfactorp", "msymmetricfactored",
+           "msymmetricfactoredp", "msymmetrize", "msymmetrizep"]
 
 
 def _f3(a, name, dtype, ndim):
@@ -32,7 +36,8 @@ def _f3(a, name, dtype, ndim):
         for d in t.shape:
             exp.append(acc)
             acc *= int(d)
-        if tuple(exp) != tuple(int(s) for s in t.stride()) and t.numel() > 1:
+        # (the stride of an axis of length 1 is arbitrary)
+        if any(int(d) > 1 and e != int(st) for d, e, st in zip(t.shape, exp, t.stride())):
             raise ValueError(f"{name}: tensor must be Fortran-contiguous")
         return int(t.data_ptr()), tuple(int(d) for d in t.shape), t.device.index
     if not isinstance(a, np.ndarray):
@@ -108,3 +113,69 @@ def mgeneralfactorp(A, ipiv, ntasks=1, device=None):
 def mgeneralfactoredp(LU, ipiv, b, ntasks=1, device=None):
     """``lapackdrivers.pyx:1695-1723``"""
     return mgeneralfactored(LU, ipiv, b, device)
+
+
+# ---- symmetric family (Bunch-Kaufman U D U^T, LAPACK uplo = 'U') ------------------------------------------------
+
+def msymmetricfactor(A, ipiv, device=None):
+    """U D U^T-factor nlhs independent symmetric n x n matrices in place (dsytrf 'U' each;
+    ``lapackdrivers.pyx:1199-1233``).  Only the upper triangle of each matrix is read and written; ``ipiv`` is
+    dsytrf's pivot array."""
+    pa, sa, da = _f3(A, "A", np.float64, 3)
+    pp, sp, dp = _f3(ipiv, "ipiv", np.int32, 2)
+    n, n2, nlhs = sa
+    if n != n2 or sp != (n, nlhs):
+        raise ValueError("shape mismatch: A (n,n,nlhs), ipiv (n,nlhs)")
+    _lib.check(_lib.lib().wlsqm_msytrf(n, nlhs, pa, pp, int(_dev(device, da, dp))))
+
+
+def msymmetricfactored(A, ipiv, b, device=None):
+    """Solve with factors from :func:`msymmetricfactor`; b is overwritten by x (dsytrs 'U' each;
+    ``lapackdrivers.pyx:1236-1272``)."""
+    pa, sa, da = _f3(A, "A", np.float64, 3)
+    pp, sp, dp = _f3(ipiv, "ipiv", np.int32, 2)
+    pb, sb, db = _f3(b, "b", np.float64, 2)
+    n, n2, nlhs = sa
+    if n != n2 or sp != (n, nlhs) or sb != (n, nlhs):
+        raise ValueError("shape mismatch: A (n,n,nlhs), ipiv (n,nlhs), b (n,nlhs)")
+    _lib.check(_lib.lib().wlsqm_msytrs(n, nlhs, pa, pp, pb, int(_dev(device, da, dp, db))))
+
+
+def msymmetric(A, b, device=None):
+    """Solve nlhs independent symmetric systems (dsysv 'U' each; ``lapackdrivers.pyx:1107-1150``): the upper
+    triangle of A is overwritten by its factors, b by the solution."""
+    pa, sa, da = _f3(A, "A", np.float64, 3)
+    pb, sb, db = _f3(b, "b", np.float64, 2)
+    n, n2, nlhs = sa
+    if n != n2 or sb != (n, nlhs):
+        raise ValueError("shape mismatch: A (n,n,nlhs), b (n,nlhs)")
+    _lib.check(_lib.lib().wlsqm_msysv(n, nlhs, pa, None, pb, int(_dev(device, da, db))))
+
+
+def msymmetrize(A, device=None):
+    """``A[:, :, k] = 0.5 * (A[:, :, k] + A[:, :, k].T)`` for every k, in place (``lapackdrivers.pyx:204-230``)."""
+    pa, sa, da = _f3(A, "A", np.float64, 3)
+    n, n2, nlhs = sa
+    if n != n2:
+        raise ValueError("shape mismatch: A (n,n,nlhs)")
+    _lib.check(_lib.lib().wlsqm_msymmetrize(n, nlhs, pa, int(_dev(device, da))))
+
+
+def msymmetricp(A, b, ntasks=1, device=None):
+    """``lapackdrivers.pyx:1153-1196``"""
+    return msymmetric(A, b, device)
+
+
+def msymmetricfactorp(A, ipiv, ntasks=1, device=None):
+    """``lapackdrivers.pyx:1275-1314``"""
+    return msymmetricfactor(A, ipiv, device)
+
+
+def msymmetricfactoredp(A, ipiv, b, ntasks=1, device=None):
+    """``lapackdrivers.pyx:1317-1354``"""
+    return msymmetricfactored(A, ipiv, b, device)
+
+
+def msymmetrizep(A, ntasks=1, device=None):
+    """``lapackdrivers.pyx:233-278``"""
+    return msymmetrize(A, device)

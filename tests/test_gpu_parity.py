@@ -277,3 +277,58 @@ def test_mgeneral_drivers_vs_numpy():
         A2, b2 = A.copy(order='F'), b.copy(order='F')
         ld.mgeneralp(A2, b2, 8)
         assert np.array_equal(b2, x)
+
+
+def test_msymmetric_drivers_vs_reference_golden_and_lapack():
+    """batched Bunch-Kaufman drivers: outputs of the unmodified reference (tests/golden/golden_sym.npz),
+    the oracle's dsytf2 / dsytrs restatement, and numpy on larger batches; host arrays and CUDA tensors"""
+    from pathlib import Path
+    from wlsqm_b200.utils import lapackdrivers as ld
+    g = np.load(Path(__file__).resolve().parent / "golden" / "golden_sym.npz")
+    for nm in (str(s) for s in g["names"]):
+        A, b = g[f"{nm}/A"], g[f"{nm}/b"]
+        n, _, nlhs = A.shape
+        F = np.asfortranarray(A.copy())
+        low_before = np.tril(F.transpose(2, 0, 1), -1).copy()
+        ipiv = np.zeros((n, nlhs), dtype=np.int32, order="F")
+        ld.msymmetricfactor(F, ipiv)
+        assert np.array_equal(ipiv, g[f"{nm}/ipiv"]), nm                       # pivot sequence: exact
+        iu = np.triu_indices(n)
+        for l in range(nlhs):
+            assert np.allclose(F[:, :, l][iu], g[f"{nm}/F"][:, :, l][iu], rtol=1e-10, atol=1e-12), (nm, l)
+        assert np.array_equal(np.tril(F.transpose(2, 0, 1), -1), low_before)    # strict lower triangle not referenced
+        x = np.asfortranarray(b.copy())
+        ld.msymmetricfactoredp(F, ipiv, x, 4)
+        sc = np.abs(g[f"{nm}/x"]).max(axis=0)
+        assert (np.abs(x - g[f"{nm}/x"]).max(axis=0) <= 1e-9 * sc).all(), nm
+        A2, x2 = np.asfortranarray(A.copy()), np.asfortranarray(b.copy())
+        ld.msymmetricp(A2, x2, 8)
+        assert np.array_equal(x2, x)
+        S = np.asfortranarray(g[f"{nm}/G"].copy())
+        ld.msymmetrizep(S, 2)
+        assert np.array_equal(S, g[f"{nm}/S"]), nm
+    # larger batches against numpy and the restatement (pivots exact), incl. sizes beyond one warp's lane count
+    rng = np.random.default_rng(1)
+    torch = pytest.importorskip("torch")
+    for n in (1, 2, 5, 15, 36, 70):
+        nlhs = 257
+        A = rng.standard_normal((n, n, nlhs))
+        A = np.asfortranarray(0.5 * (A + A.transpose(1, 0, 2)))
+        A[np.arange(n), np.arange(n), ::3] *= 1e-3                              # provoke 2x2 blocks
+        b = np.asfortranarray(rng.standard_normal((n, nlhs)))
+        x_ref = np.stack([np.linalg.solve(A[:, :, l], b[:, l]) for l in range(nlhs)], axis=1)
+        F, ipiv = A.copy(order="F"), np.zeros((n, nlhs), dtype=np.int32, order="F")
+        ld.msymmetricfactor(F, ipiv)
+        Fo, ipo = A.copy(order="F"), np.zeros_like(ipiv)
+        orc.msytrf(Fo, ipo)
+        assert np.array_equal(ipiv, ipo), n
+        x = b.copy(order="F")
+        ld.msymmetricfactored(F, ipiv, x)
+        err = np.abs(x - x_ref).max(axis=0) / np.abs(x_ref).max(axis=0)
+        assert np.median(err) < 1e-12 and err.max() < 1e-7, (n, err.max())
+        # CUDA tensors, zero copy (Fortran order = transposed view of a C-contiguous tensor)
+        A_t = torch.from_numpy(np.ascontiguousarray(A.transpose(2, 1, 0))).cuda().permute(2, 1, 0)
+        b_t = torch.from_numpy(np.ascontiguousarray(b.T)).cuda().t()
+        ld.msymmetric(A_t, b_t)
+        torch.cuda.synchronize()
+        assert np.array_equal(b_t.cpu().numpy(), x)
