@@ -1209,8 +1209,9 @@ static int lapack_common(int n, int64_t nlhs, double* A, int32_t* ipiv, double* 
     if (sym) {
         if (e == cudaSuccess) e = launch_sy(n, nlhs, dA, dP, do_solve ? dB : nullptr, do_factor, st);
     } else {
-        if (e == cudaSuccess && do_factor) e = launch_getrf(n, nlhs, dA, dP, st);
-        if (e == cudaSuccess && do_solve) e = launch_getrs(n, nlhs, dA, dP, dB, st);
+        if (e == cudaSuccess && do_factor && do_solve) e = launch_gesv(n, nlhs, dA, dP, dB, st);
+        else if (e == cudaSuccess && do_factor) e = launch_getrf(n, nlhs, dA, dP, st);
+        else if (e == cudaSuccess && do_solve) e = launch_getrs(n, nlhs, dA, dP, dB, st);
     }
     if (e == cudaSuccess && do_factor && !a_dev) e = cudaMemcpyAsync(A, dA, na, cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess && do_factor && !p_dev && ipiv) e = cudaMemcpyAsync(ipiv, dP, np, cudaMemcpyDeviceToHost, st);

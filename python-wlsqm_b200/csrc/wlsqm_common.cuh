@@ -62,6 +62,12 @@ __host__ __device__ inline int number_of_dofs(int dim, int order) {   // infra.p
     return N[dim-1][order];
 }
 
+// the same count in closed form, C(order + DIM, DIM), for kernels: no table lookup in the dependency chain
+// index -> order -> number of coefficients -> coefficient loads
+template <int DIM> __host__ __device__ constexpr int dofs_of(int order) {
+    return DIM == 1 ? order + 1 : (DIM == 2 ? ((order + 1) * (order + 2)) / 2 : ((order + 1) * (order + 2) * (order + 3)) / 6);
+}
+
 // ---------------------------------------------------------------------------------------------
 // device helpers
 // ---------------------------------------------------------------------------------------------

@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(INTERP_THREADS, MINB) interpolate_kernel(Inter
         const bool bad = P.nmodels > 0 && (idx[j] < 0 || idx[j] >= P.nmodels);
         const long long i = bad ? 0 : idx[j];
         const int order = P.order ? (int)P.order[i] : P.order_uniform;
-        const int no = number_of_dofs(DIM, order);
+        const int no = dofs_of<DIM>(order);
         const double* xo = P.xi + i * P.xi_s0;
         const double dx = xq[j][0] - xo[0];
         const double dy = DIM >= 2 ? xq[j][DIM >= 2 ? 1 : 0] - xo[DIM >= 2 ? 1 : 0] : 0.0;
@@ -169,7 +169,7 @@ __global__ void __launch_bounds__(128) continuous_kernel(InterpParams P, GridVie
                 if (!(d2 <= r2)) continue;
                 const long long i = g.sorted_idx[p];
                 const int order = P.order ? (int)P.order[i] : P.order_uniform;
-                const int no = number_of_dofs(DIM, order);
+                const int no = dofs_of<DIM>(order);
                 const double* fg = P.fi + i * P.fi_s0;
                 const Steps hx = steps_of(dq[0]), hy = steps_of(dq[1]), hz = steps_of(dq[2]);
                 double value = 0.0;

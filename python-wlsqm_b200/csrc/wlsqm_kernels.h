@@ -101,6 +101,7 @@ struct GridView;
 cudaError_t launch_interpolate_continuous(const InterpParams& P, const GridView& g, double r, cudaStream_t st);
 cudaError_t launch_getrf(int n, long long nlhs, double* A, int* ipiv, cudaStream_t st);
 cudaError_t launch_getrs(int n, long long nlhs, const double* LU, const int* ipiv, double* b, cudaStream_t st);
+cudaError_t launch_gesv(int n, long long nlhs, double* A, int* ipiv, double* b, cudaStream_t st);
 cudaError_t launch_sy(int n, long long nlhs, double* A, int* ipiv, double* b, int do_factor, cudaStream_t st);
 cudaError_t launch_symmetrize(int n, long long nlhs, double* A, cudaStream_t st);
 cudaError_t launch_cond(int n_max, long long ncases, const CaseMeta* meta, const CaseMeta& uni, const double* As,

@@ -12,10 +12,14 @@
 // cond_kernel: 2-norm condition number of the scaled problem matrices kept by prepare(debug=True)
 // (svd_c -> dgesvd, lapackdrivers.pyx:1756-1774, called from impl.pyx:662-682), by one-sided
 // (Hestenes) Jacobi SVD, one warp per matrix.
+#include <cstdlib>
 #include "wlsqm_common.cuh"
 #include "wlsqm_kernels.h"
 
 namespace wlsqm {
+
+cudaError_t launch_getrf(int n, long long nlhs, double* A, int* ipiv, cudaStream_t st);
+cudaError_t launch_getrs(int n, long long nlhs, const double* LU, const int* ipiv, double* b, cudaStream_t st);
 
 // LU of the n x n column-major matrix A (leading dimension lda) held in shared memory; warp-cooperative.
 __device__ __forceinline__ void warp_getrf(int n, double* A, int lda, int* ipiv, int lane) {
@@ -106,6 +110,196 @@ __global__ void getrs_kernel(int n, long long nlhs, const double* __restrict__ L
     }
 }
 
+// ---- n <= 32: rows in registers, several systems per warp ---------------------------------------------------
+// LPF lanes per system (LPF = 4, 8, 16, 32 >= n), FPW = 32 / LPF systems side by side in a warp, lane = matrix row held
+// in LPF registers (every loop over columns is unrolled).  Partial pivoting without moving rows: the pivot lane
+// publishes its row to shared memory at the pivot's position -- which is the LAPACK-layout LU that is written back --
+// and the other lanes eliminate in registers (the scheme of prepare_reg_kernel's LU phase).  dgesv solves its right-hand
+// side in the same pass: lane = row keeps its multipliers and its U row, the substitutions broadcast one value per
+// step by shuffle (no second read of the factors).
+//   mode 0: dgetrf (A -> LU, ipiv)     mode 1: dgesv (A -> LU, ipiv; b -> x)     mode 2: dgetrs (LU, ipiv given; b -> x)
+// max / min over the LPF consecutive lanes of a lane's group: one warp-wide REDUX per group (independent, so their
+// latencies overlap) instead of a dependent shuffle butterfly
+template <int LPF>
+__device__ __forceinline__ unsigned lu_group_max(unsigned v, int grp) {
+    if constexpr (LPF == 32) return __reduce_max_sync(0xffffffffu, v);
+    if constexpr (LPF <= 8) {      // many small groups: a short butterfly inside the group is cheaper
+#pragma unroll
+        for (int o = 1; o < LPF; o <<= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
+        return v;
+    }
+    unsigned r = 0u;
+#pragma unroll
+    for (int g = 0; g < 32 / LPF; ++g) {
+        const unsigned m = __reduce_max_sync(0xffffffffu, grp == g ? v : 0u);
+        if (grp == g) r = m;
+    }
+    return r;
+}
+template <int LPF>
+__device__ __forceinline__ unsigned lu_group_min(unsigned v, int grp) {
+    if constexpr (LPF == 32) return __reduce_min_sync(0xffffffffu, v);
+    if constexpr (LPF <= 8) {
+#pragma unroll
+        for (int o = 1; o < LPF; o <<= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, o));
+        return v;
+    }
+    unsigned r = 0u;
+#pragma unroll
+    for (int g = 0; g < 32 / LPF; ++g) {
+        const unsigned m = __reduce_min_sync(0xffffffffu, grp == g ? v : 0xffffffffu);
+        if (grp == g) r = m;
+    }
+    return r;
+}
+
+template <int LPF>
+__global__ void __launch_bounds__(256, LPF == 32 ? 2 : (LPF == 16 ? 3 : 4)) lu_reg_kernel(int n, long long nlhs, double* __restrict__ Ag, int* __restrict__ ipivg,
+                                                     double* __restrict__ bg, int mode) {
+    constexpr int FPW = 32 / LPF;
+    constexpr int LDG = LPF + 2;                      // row stride of the published LU (even: 16 B aligned rows)
+    constexpr unsigned FULL = 0xffffffffu;
+    extern __shared__ __align__(16) double smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int grp = lane / LPF, jl = lane % LPF;
+    double* G = smem + ((size_t)warp * FPW + grp) * (LPF * LDG + LPF);   // [LPF][LDG] LU rows in pivot order
+    double* bs = G + LPF * LDG;                                            // [LPF] right-hand side (mode 2)
+    const long long nn = (long long)n * n;
+    const long long nsets = (nlhs + FPW - 1) / FPW;
+    for (long long set = (long long)blockIdx.x * nwarps + warp; set < nsets; set += (long long)gridDim.x * nwarps) {
+        const long long sys = set * FPW + grp;
+        const bool live = sys < nlhs;
+        const bool row = live && jl < n;
+        double* ag = Ag + (live ? sys : 0) * nn;
+        double a[LPF];
+#pragma unroll
+        for (int m = 0; m < LPF; ++m) a[m] = (row && m < n) ? ag[jl + (long long)n * m] : 0.0;
+        int mystep = jl;          // position of this lane's row in the pivot order
+        if (mode != 2) {
+            bool act = row;
+            int pos = jl;         // current position of this lane's row in LAPACK's (swapped) row order
+            int myipiv = 0;       // ipiv[jl]
+            mystep = -1;
+#pragma unroll
+            for (int p = 0; p < LPF; ++p) {
+                if (p < n) {      // warp-uniform
+                    // pivot = first row of largest |a[.][p]| in current row order (idamax).  The magnitude of a
+                    // non-negative double orders like its bit pattern: REDUX on the high words, the low words and the
+                    // position only among the lanes that tie (a NaN entry counts as 0 so that every lane agrees)
+                    double mag = fabs(a[p]);
+                    if (!(mag == mag)) mag = 0.0;
+                    const unsigned khi = (unsigned)__double2hiint(mag), klo = (unsigned)__double2loint(mag);
+                    const unsigned hi = lu_group_max<LPF>(act ? khi : 0u, grp);
+                    const bool c1 = act && khi == hi;
+                    const unsigned lo = lu_group_max<LPF>(c1 ? klo : 0u, grp);
+                    const bool c2 = c1 && klo == lo;
+                    const int bpos = (int)lu_group_min<LPF>(c2 ? (unsigned)pos : 0xffffu, grp);
+                    const bool win = c2 && pos == bpos;
+                    if (jl == p) myipiv = bpos + 1;
+                    const bool piv = live && win;
+                    if (piv) {
+#pragma unroll
+                        for (int m = 0; m < LPF; m += 2) *reinterpret_cast<double2*>(G + p * LDG + m) = make_double2(a[m], a[m + 1]);
+                        mystep = p;
+                        act = false;
+                    } else if (act && pos == p) {
+                        pos = bpos;             // the row that sat at position p takes the pivot row's old place
+                    }
+                    __syncwarp();
+                    if (act) {
+                        const double rp = 1.0 / G[p * LDG + p];
+                        const double l = a[p] * rp;
+                        a[p] = l;
+#pragma unroll
+                        for (int m = ((p + 1) & ~1); m < LPF; m += 2) {
+                            const double2 u2 = *reinterpret_cast<const double2*>(G + p * LDG + m);
+                            if (m > p) a[m] = fma(-l, u2.x, a[m]);
+                            a[m + 1] = fma(-l, u2.y, a[m + 1]);
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+            // LU back to the caller, LAPACK layout: row p of the factors is G[p]
+            if (row) {
+#pragma unroll
+                for (int m = 0; m < LPF; ++m)
+                    if (m < n) ag[jl + (long long)n * m] = G[jl * LDG + m];
+                if (ipivg) ipivg[sys * n + jl] = myipiv;
+            }
+        }
+        if (mode != 0) {
+            // lane = row jl of the pivot order from here on: the factors are re-read from G (mode 1), the right-hand
+            // side is permuted through shared memory; each substitution step broadcasts one value from a fixed lane
+            double y = 0.0;
+            if (mode == 2) {
+                if (row) bs[jl] = bg[sys * n + jl];
+                __syncwarp();
+                if (live && jl == 0)
+                    for (int p = 0; p < n; ++p) {
+                        const int ip = ipivg[sys * n + p] - 1;
+                        if (ip != p && ip >= 0 && ip < n) { const double t = bs[p]; bs[p] = bs[ip]; bs[ip] = t; }
+                    }
+            } else {
+                if (row && mystep >= 0) bs[mystep] = bg[sys * n + jl];   // the row's own entry travels with the row
+#pragma unroll
+                for (int m = 0; m < LPF; m += 2) {
+                    const double2 v = *reinterpret_cast<const double2*>(G + jl * LDG + m);
+                    a[m] = v.x;
+                    a[m + 1] = v.y;
+                }
+            }
+            __syncwarp();
+            if (row) y = bs[jl];
+            // L y = P b (unit lower)
+#pragma unroll
+            for (int p = 0; p < LPF; ++p) {
+                if (p < n) {
+                    const double yp = __shfl_sync(FULL, y, grp * LPF + p);
+                    if (jl > p) y = fma(-a[p], yp, y);
+                }
+            }
+            // U x = y
+#pragma unroll
+            for (int m = LPF - 1; m >= 0; --m) {
+                if (m < n) {
+                    if (jl == m) y = y / a[m];
+                    const double xm = __shfl_sync(FULL, y, grp * LPF + m);
+                    if (jl < m) y = fma(-a[m], xm, y);
+                }
+            }
+            if (row) bg[sys * n + jl] = y;
+        }
+        __syncwarp();
+    }
+}
+
+template <int LPF>
+static cudaError_t launch_lu_reg_t(int n, long long nlhs, double* A, int* ipiv, double* b, int mode, cudaStream_t st) {
+    constexpr int FPW = 32 / LPF;
+    const int warps = 8;
+    const size_t smem = (size_t)warps * FPW * (LPF * (LPF + 2) + LPF) * 8;
+    cudaError_t e = cudaFuncSetAttribute(lu_reg_kernel<LPF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    const long long nsets = (nlhs + FPW - 1) / FPW;
+    long long blocks = (nsets + warps - 1) / warps;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    lu_reg_kernel<LPF><<<(unsigned)blocks, warps * 32, smem, st>>>(n, nlhs, A, ipiv, b, mode);
+    return cudaGetLastError();
+}
+
+// n <= 32 (and not disabled by WLSQM_LU_SMEM=1, the A/B switch of the tests)
+static bool lu_reg_ok(int n) {
+    static const bool off = [] { const char* v = getenv("WLSQM_LU_SMEM"); return v && v[0] == '1'; }();
+    return n <= 32 && !off;
+}
+static cudaError_t launch_lu_reg(int n, long long nlhs, double* A, int* ipiv, double* b, int mode, cudaStream_t st) {
+    if (n <= 4) return launch_lu_reg_t<4>(n, nlhs, A, ipiv, b, mode, st);
+    if (n <= 8) return launch_lu_reg_t<8>(n, nlhs, A, ipiv, b, mode, st);
+    if (n <= 16) return launch_lu_reg_t<16>(n, nlhs, A, ipiv, b, mode, st);
+    return launch_lu_reg_t<32>(n, nlhs, A, ipiv, b, mode, st);
+}
+
 static int lapack_cfg(int n, int& warps, size_t& smem, int& warp_doubles, int extra) {
     const int lda = n | 1;
     warp_doubles = (lda * n + extra + 1) & ~1;
@@ -118,8 +312,17 @@ static int lapack_cfg(int n, int& warps, size_t& smem, int& warp_doubles, int ex
     return 0;
 }
 
+cudaError_t launch_gesv(int n, long long nlhs, double* A, int* ipiv, double* b, cudaStream_t st) {
+    if (nlhs == 0 || n == 0) return cudaSuccess;
+    if (lu_reg_ok(n)) return launch_lu_reg(n, nlhs, A, ipiv, b, 1, st);
+    cudaError_t e = launch_getrf(n, nlhs, A, ipiv, st);
+    if (e == cudaSuccess) e = launch_getrs(n, nlhs, A, ipiv, b, st);
+    return e;
+}
+
 cudaError_t launch_getrf(int n, long long nlhs, double* A, int* ipiv, cudaStream_t st) {
     if (nlhs == 0 || n == 0) return cudaSuccess;
+    if (lu_reg_ok(n)) return launch_lu_reg(n, nlhs, A, ipiv, nullptr, 0, st);
     int warps, wd;
     size_t smem;
     if (lapack_cfg(n, warps, smem, wd, (n + 1) / 2 + 1)) return cudaErrorInvalidValue;
@@ -133,6 +336,7 @@ cudaError_t launch_getrf(int n, long long nlhs, double* A, int* ipiv, cudaStream
 
 cudaError_t launch_getrs(int n, long long nlhs, const double* LU, const int* ipiv, double* b, cudaStream_t st) {
     if (nlhs == 0 || n == 0) return cudaSuccess;
+    if (lu_reg_ok(n)) return launch_lu_reg(n, nlhs, const_cast<double*>(LU), const_cast<int*>(ipiv), b, 2, st);
     int warps, wd;
     size_t smem;
     if (lapack_cfg(n, warps, smem, wd, n + 1)) return cudaErrorInvalidValue;
