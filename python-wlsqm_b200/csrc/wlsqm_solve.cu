@@ -264,6 +264,11 @@ solve_kernel(SolveParams P) {
                 if (unk1) v1 = t1;
             }
         }
+        if (nq == 0 && nr > 0) {
+            // no neighbours and nothing known: the reference factors an all-zero matrix and returns NaN
+            if (unk0) v0 = __longlong_as_double(0x7ff8000000000000LL);
+            if (unk1) v1 = __longlong_as_double(0x7ff8000000000000LL);
+        }
         if (ITER) {
             if (in0) fis[lane] = v0;
             if (in1) fis[lane + 32] = v1;
@@ -498,6 +503,8 @@ __global__ void __launch_bounds__(SOLVE_MAX_THREADS) solve_pack_kernel(SolvePara
                 ka += 8u;
             }
             v = (a0 + a1) + (a2 + a3);
+            // no neighbours and nothing known: the reference factors an all-zero matrix and returns NaN
+            if (nk + nkn == 0) v = __longlong_as_double(0x7ff8000000000000LL);
         }
         if (valid) {
             P.fi_case[c * P.fi_case_ld + o] = v;

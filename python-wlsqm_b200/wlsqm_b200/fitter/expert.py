@@ -73,6 +73,8 @@ class ExpertSolver:
                              % algorithm)
         if ntasks < 1:
             raise ValueError("ntasks must be >= 1, got %d" % ntasks)
+        if ncases < 1:     # CaseManager_new (infra.pyx:308-360) refuses an empty batch
+            raise ValueError("Must specify max_cases > 0 when creating a CaseManager.")
 
         # guest mode sanity checks (expert.pyx:163-189)
         if host is not None:

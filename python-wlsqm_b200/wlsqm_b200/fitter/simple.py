@@ -40,6 +40,8 @@ def _fit_many(dim, xk, fk, nk, xi, fi, sens, do_sens, order, knowns, weighting_m
         raise ValueError("nk, order, knowns and weighting_method must have the same length")
     if max_iter is None or do_sens is None:
         raise ValueError("do_sens and max_iter cannot be None")
+    if ncases < 1:         # CaseManager_new (infra.pyx:308-360) refuses an empty batch
+        raise ValueError("Must specify max_cases > 0 when creating a CaseManager.")
     do_sens = int(do_sens)
     if dim >= 2:
         xk_a = _lib.as_arr(xk, np.float64, 3, "xk")

@@ -1,0 +1,125 @@
+"""Edge cases of the hot path, checked against the unmodified reference's behaviour (probed in the build container,
+restated here as assertions; the oracle covers the arithmetic): empty and one-case batches, neighbourhoods without
+points, underdetermined fits next to healthy ones, large neighbourhoods, pitched / strided inputs."""
+import numpy as np
+import pytest
+
+import parity
+import oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+wlsqm = pytest.importorskip("wlsqm_b200")
+
+
+def _meta(n, k, order, knowns, wm):
+    return (np.full(n, k, np.int32), np.full(n, order, np.int32), np.full(n, knowns, np.int64), np.full(n, wm, np.int32))
+
+
+def test_empty_batch_is_refused_like_the_reference():
+    e32, e64 = np.zeros(0, np.int32), np.zeros(0, np.int64)
+    with pytest.raises(ValueError, match="max_cases > 0"):          # infra.pyx CaseManager_new
+        wlsqm.ExpertSolver(2, e32, e32, e64, e32)
+    for fn in (wlsqm.fit_2D_many, wlsqm.fit_2D_many_parallel, wlsqm.fit_2D_iterative_many):
+        with pytest.raises(ValueError, match="max_cases > 0"):
+            fn(np.zeros((0, 5, 2)), np.zeros((0, 5)), e32, np.zeros((0, 2)), np.zeros((0, 6)), None, 0, e32, e64, e32)
+
+
+def test_single_case_and_single_neighbour():
+    # order 0 with one neighbour: the fit is that neighbour's value (reference: fit_2D(...) -> fi = [3.])
+    fi = np.zeros(1)
+    assert wlsqm.fit_2D(np.array([[0.1, 0.2]]), np.array([3.0]), np.array([0.0, 0.0]), fi, None, 0, 0, 0, 1) == 0
+    assert fi[0] == 3.0
+    # a batch of one case through every entry point agrees with the oracle
+    x, hoods, f = parity.make_case(50, 2, 12)
+    xk, fk = parity.gathered(x, f, hoods)
+    m = _meta(1, 12, 2, 1, 2)
+    fi1 = np.zeros((1, 6)); fi1[0, 0] = f[0]
+    fo = fi1.copy()
+    wlsqm.fit_2D_many(xk[:1], fk[:1], m[0], x[:1], fi1, None, 0, m[1], m[2], m[3])
+    orc.fit_many(2, xk[:1], fk[:1], m[0], x[:1], fo, None, False, m[1], m[2], m[3])
+    assert np.allclose(fi1, fo, rtol=1e-10, atol=1e-12)
+
+
+def test_cases_without_neighbours_give_nan_and_leave_the_rest_alone():
+    """nk = 0: the reference's normal matrix is all zeros and every unknown comes out NaN; other cases are unaffected"""
+    n, k = 64, 12
+    x, hoods, f = parity.make_case(n, 2, k)
+    xk, fk = parity.gathered(x, f, hoods)
+    nk, od, kn, wm = _meta(n, k, 2, 0, 1)
+    nk[::8] = 0
+    fi = np.zeros((n, 6))
+    s = wlsqm.ExpertSolver(2, nk, od, kn, wm)
+    s.prepare(x, xk)
+    s.solve(fk, fi)
+    assert np.isnan(fi[::8]).all()
+    good = np.ones(n, bool); good[::8] = False
+    so = orc.OracleSolver(2, nk[good], od[good], kn[good], wm[good])
+    so.prepare(x[good], xk[good])
+    fo = np.zeros((good.sum(), 6))
+    so.solve(fk[good], fo)
+    assert np.isfinite(fi[good]).all()
+    assert np.abs(fi[good] - fo).max() <= 1e-9 * np.abs(fo).max()
+
+
+def test_underdetermined_fits_do_not_disturb_their_neighbours_in_the_batch():
+    """nk < number of unknowns: the matrix is singular, the reference returns whatever LU of round-off gives (finite
+    garbage or inf/NaN, no error).  Required here: no error, and the healthy cases of the same batch are untouched."""
+    n, k = 200, 30
+    x, hoods, f = parity.make_case(n, 2, k)
+    xk, fk = parity.gathered(x, f, hoods)
+    nk, od, kn, wm = _meta(n, k, 4, 0, 2)
+    nk[5::10] = 7                       # 7 neighbours for 15 unknowns
+    fi = np.zeros((n, 15))
+    s = wlsqm.ExpertSolver(2, nk, od, kn, wm)
+    s.prepare(x, xk)
+    s.solve(fk, fi)
+    good = np.ones(n, bool); good[5::10] = False
+    so = orc.OracleSolver(2, nk[good], od[good], kn[good], wm[good])
+    so.prepare(x[good], xk[good])
+    fo = np.zeros((good.sum(), 15))
+    so.solve(fk[good], fo)
+    rep = parity.wl.parity_report(fi[good], fo, 2, 4)
+    assert rep[0][2] < 1e-9 and rep[1][1] < 1e-9, rep
+
+
+@pytest.mark.parametrize("dim,order,k", [(2, 4, 200), (3, 4, 150), (1, 4, 300), (2, 2, 500)])
+def test_large_neighbourhoods(dim, order, k):
+    """neighbourhoods far larger than the usual 25-60 points (several 32-column blocks per fit, operator blocks of
+    tens of KB): same answers as the oracle"""
+    n = 120
+    x, hoods, f = parity.make_case(max(n, k + 50), dim, k)
+    x, hoods, f = x, hoods[:n], f
+    xi = x[:n]
+    xk, fk = np.ascontiguousarray(x[hoods]), np.ascontiguousarray(f[hoods])
+    no = wlsqm.number_of_dofs(dim, order)
+    nk, od, kn, wm = _meta(n, k, order, 1, 2)
+    fi0 = np.zeros((n, no)); fi0[:, 0] = f[:n]
+    s = wlsqm.ExpertSolver(dim, nk, od, kn, wm, do_sens=True)
+    s.prepare(xi, xk)
+    fi = fi0.copy()
+    sens = np.zeros((n, k, no))
+    s.solve(fk, fi, sens)
+    ref, sens_o, _, _ = parity.oracle_solve(dim, nk, od, kn, wm, xi, xk, fk, fi0, do_sens=True)
+    a, b = parity.permuted_self_noise(dim, nk, od, kn, wm, xi, xk, fk, fi0)
+    print(parity.check_against_floor(fi, ref, b + (ref - a), dim, order, f"k={k}"))
+    parity.check_sens(sens, sens_o, f"k={k}")
+
+
+def test_pitched_and_strided_host_inputs():
+    """the memoryview layouts of simple.pyx:149-159: leading axes arbitrarily strided, fk strided on both axes"""
+    n, k = 300, 24
+    x, hoods, f = parity.make_case(n, 2, k)
+    xk, fk = parity.gathered(x, f, hoods)
+    no = 10
+    nk, od, kn, wm = _meta(n, k, 3, 1, 1)
+    fi_ref = np.zeros((n, no)); fi_ref[:, 0] = f
+    wlsqm.fit_2D_many(xk, fk, nk, x, fi_ref, None, 0, od, kn, wm)
+    # every array embedded in a larger one
+    xk_big = np.zeros((2 * n, k + 3, 2)); xk_big[::2, :k] = xk
+    fk_big = np.zeros((n, 2 * k + 1)); fk_big[:, :2 * k:2] = fk
+    x_big = np.zeros((n, 5)); x_big[:, :2] = x
+    fi_big = np.full((n, no + 4), 7.0); fi_big[:, 0] = f
+    wlsqm.fit_2D_many(xk_big[::2, :k], fk_big[:, :2 * k:2], nk, x_big[:, :2], fi_big[:, :no], None, 0, od, kn, wm)
+    assert np.array_equal(fi_big[:, :no], fi_ref)
+    assert (fi_big[:, no:] == 7.0).all()          # columns beyond the model are not touched
