@@ -56,6 +56,16 @@ constexpr size_t SMEM_PER_CTA = 227 * 1024;
 
 inline int even(int v) { return (v + 1) & ~1; }
 
+// every element equal to the first (branch-free so that the host compiler vectorises it: ~0.1 ms per million)
+template <typename T>
+bool all_equal(const T* a, long long n) {
+    if (n < 2) return true;
+    const T v = a[0];
+    T acc = 0;
+    for (long long i = 1; i < n; ++i) acc |= (T)(a[i] ^ v);
+    return acc == 0;
+}
+
 int env_int(const char* name, int dflt) {
     const char* v = getenv(name);
     return (v && *v) ? atoi(v) : dflt;
@@ -200,7 +210,7 @@ int config_prepare(const wlsqm_solver* s, PrepareParams& P, LaunchCfg& L) {
 }
 
 // register/DMMA kernel: false if the fit does not fit its shared-memory carve-up (then the smem kernel runs)
-bool config_prepare_reg(const wlsqm_solver* s, PrepRegParams& P, LaunchCfg& L) {
+bool config_prepare_reg(const wlsqm_solver* s, PrepRegParams& P, LaunchCfg& L, bool direct = false) {
     const int nkp = (std::max(s->maxnk, 1) + 3) & ~3;
     P.nb = (std::max(nkp, s->maxnq) + 31) / 32;
     const int nkn_max = s->maxnq > 0 ? s->maxnkn : 0;
@@ -216,7 +226,7 @@ bool config_prepare_reg(const wlsqm_solver* s, PrepRegParams& P, LaunchCfg& L) {
         if (force_w > 0 && w != force_w) continue;
         if (w * per_warp > SMEM_PER_CTA) break;
         int c = 0;
-        if (prepare_reg_occupancy(s->dim, s->maxorder, w * 32, w * per_warp, &c) != cudaSuccess) {
+        if (prepare_reg_occupancy(s->dim, s->maxorder, w * 32, w * per_warp, &c, direct) != cudaSuccess) {
             cudaGetLastError();
             continue;
         }
@@ -432,9 +442,7 @@ int wlsqm_solver_create(int dimension, int64_t ncases, const int32_t* nk, const 
     s->max_iter = max_iter; s->debug = debug ? 1 : 0; s->ncases = ncases;
     // Uniform batches (every case with the same nk / order / knowns / weighting -- the usual ExpertSolver and
     // fit_*_many call) are recognised by one pass of comparisons and keep no per-case records at all.
-    bool all_same = true;
-    for (long long i = 1; i < ncases && all_same; ++i)
-        all_same = nk[i] == nk[0] && order[i] == order[0] && knowns[i] == knowns[0] && wm[i] == wm[0];
+    const bool all_same = all_equal(nk, ncases) && all_equal(order, ncases) && all_equal(knowns, ncases) && all_equal(wm, ncases);
     const long long nrec = all_same ? std::min<long long>(ncases, 1) : ncases;
     try {
         s->hmeta.resize((size_t)nrec);
@@ -1125,11 +1133,105 @@ int wlsqm_solver_interpolate_continuous(wlsqm_solver_t* s, const double* x, int6
     return WLSQM_OK;
 }
 
+// One-shot fits without sensitivities on a uniform batch: one launch of the fused kernel (assemble, equilibrate,
+// factor, solve; no operator is formed, nothing is kept).  Returns 1 if the call was handled (rc_out has the result),
+// 0 if the batch does not qualify and the general path (create + prepare + solve + destroy) must run.
+static int fit_many_direct(int dimension, int64_t ncases, const double* xk, int64_t xk_s0, int64_t xk_s1, const double* fk,
+                           int64_t fk_s0, int64_t fk_s1, const int32_t* nk, const double* xi, int64_t xi_s0, double* fi,
+                           int64_t fi_s0, const int32_t* order, const int64_t* knowns, const int32_t* wm, int device,
+                           int* rc_out) {
+    if (env_int("WLSQM_FIT_DIRECT", 1) == 0) return 0;
+    if (ncases < 1 || dimension < 1 || dimension > 3 || !nk || !order || !knowns || !wm || !xk || !fk || !xi || !fi) return 0;
+    if (!(all_equal(nk, ncases) && all_equal(order, ncases) && all_equal(knowns, ncases) && all_equal(wm, ncases))) return 0;
+    const int no = number_of_dofs(dimension, order[0]);
+    if (no < 0 || nk[0] < 0 || (wm[0] != WLSQM_WEIGHT_UNIFORM && wm[0] != WLSQM_WEIGHT_CENTER)) return 0;   // general path reports it
+    if (!prepare_reg_direct_ok(dimension, order[0])) return 0;
+    if (wlsqm_device_count() < 1 || device < 0 || device >= wlsqm_device_count()) return 0;
+    const bool xk_dev = is_device_ptr(xk), fk_dev = is_device_ptr(fk), xi_dev = is_device_ptr(xi), fi_dev = is_device_ptr(fi);
+    const int dim = dimension, k = nk[0];
+    if (!xk_dev && xk_s1 != dim && k > 1) return 0;
+    if (!fk_dev && fk_s1 != 1 && k > 1) return 0;
+    if (xk_dev && xk_s1 != dim) return 0;                      // (the kernel wants contiguous neighbour rows)
+    if (fk_dev && fi_dev) {
+        // fk may be a view of fi (the deferred write-back of expert.pyx:548-557 exists for that): general path
+        const char *a0 = (const char*)fk, *a1 = a0 + ((ncases - 1) * fk_s0 + (long long)(k - 1) * fk_s1 + 1) * 8;
+        const char *b0 = (const char*)fi, *b1 = b0 + ((ncases - 1) * fi_s0 + no) * 8;
+        if (a0 < b1 && b0 < a1) return 0;
+    }
+    // a solver shell for the launch configuration only (no device state)
+    wlsqm_solver sh;
+    sh.dim = dim; sh.device = device; sh.ncases = ncases;
+    CaseMeta m;
+    memset(&m, 0, sizeof m);
+    m.knowns = knowns[0] & ((1LL << no) - 1);
+    m.nkn = (signed char)__builtin_popcountll((unsigned long long)m.knowns);
+    m.nk = k; m.no = (short)no; m.nr = (short)(no - m.nkn); m.order = (signed char)order[0]; m.wm = (signed char)wm[0];
+    sh.uni = m;
+    sh.maxnk = k; sh.maxno = no; sh.maxnr = m.nr; sh.maxnq = k + m.nkn; sh.maxorder = m.order; sh.maxnkn = m.nkn;
+    auto run = [&]() -> int {
+        CU(cudaSetDevice(device));
+        int smc = 0;
+        if (cudaDeviceGetAttribute(&smc, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && smc > 0) sh.sm_count = smc;
+        else cudaGetLastError();
+        cudaStream_t st = nullptr;     // legacy default stream: ordered after the caller's work on it, synchronous result
+        DevBuf bxk, bfk, bxi, bfi;
+        auto done = [&](int r) { bxk.release(); bfk.release(); bxi.release(); bfi.release(); return r; };
+        int rc = WLSQM_OK;
+        PrepRegParams R{};
+        R.meta = nullptr; R.uni = m; R.op_stride = 0; R.ncases = ncases; R.geom_uniform = 1; R.op = nullptr;
+        R.xi = xi; R.xi_s0 = xi_s0; R.xk = xk; R.xk_s0 = xk_s0; R.xk_s1 = xk_s1;
+        R.fk = fk; R.fk_s0 = fk_s0; R.fk_s1 = fk_s1; R.fi = fi; R.fi_s0 = fi_s0;
+        if (!xk_dev) {
+            rc = bxk.reserve((size_t)ncases * k * dim * 8);
+            if (!rc) rc = to_dense((double*)bxk.p, xk, ncases, (long long)k * dim, xk_s0, st);
+            R.xk = (const double*)bxk.p; R.xk_s0 = (long long)k * dim; R.xk_s1 = dim;
+        }
+        if (!rc && !fk_dev) {
+            rc = bfk.reserve((size_t)ncases * k * 8);
+            if (!rc) rc = to_dense((double*)bfk.p, fk, ncases, k, fk_s0, st);
+            R.fk = (const double*)bfk.p; R.fk_s0 = k; R.fk_s1 = 1;
+        }
+        if (!rc && !xi_dev) {
+            rc = bxi.reserve((size_t)ncases * dim * 8);
+            if (!rc) rc = to_dense((double*)bxi.p, xi, ncases, dim, xi_s0, st);
+            R.xi = (const double*)bxi.p; R.xi_s0 = dim;
+        }
+        if (!rc && !fi_dev) {
+            rc = bfi.reserve((size_t)ncases * no * 8);
+            if (!rc) rc = to_dense((double*)bfi.p, fi, ncases, no, fi_s0, st);      // the known values travel in
+            R.fi = (double*)bfi.p; R.fi_s0 = no;
+        }
+        if (rc) return done(rc);
+        LaunchCfg L;
+        if (!config_prepare_reg(&sh, R, L, true)) return done(-1000);          // does not fit: general path
+        cudaError_t e = launch_prepare_reg(dim, m.order, R, L.blocks, L.threads, L.smem, st);
+        if (e == cudaSuccess && !fi_dev) {
+            rc = from_dense(fi, fi_s0, (const double*)bfi.p, no, ncases, no, st);
+            if (rc) return done(rc);
+        }
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) return done(fail(WLSQM_E_CUDA, "one-shot fit: %s", cudaGetErrorString(e)));
+        return done(WLSQM_OK);
+    };
+    const int rc = run();
+    if (rc == -1000) return 0;
+    *rc_out = rc;
+    return 1;
+}
+
 int wlsqm_fit_many(int dimension, int64_t ncases, const double* xk, int64_t xk_s0, int64_t xk_s1, const double* fk,
                    int64_t fk_s0, int64_t fk_s1, const int32_t* nk, const double* xi, int64_t xi_s0, double* fi,
                    int64_t fi_s0, double* sens, int64_t sens_s0, int64_t sens_s1, int do_sens, const int32_t* order,
                    const int64_t* knowns, const int32_t* wm, int algorithm, int max_iter, int device,
                    int32_t* iters_out) {
+    if (algorithm == WLSQM_ALGO_BASIC && !do_sens) {
+        int rc = WLSQM_OK;
+        if (fit_many_direct(dimension, ncases, xk, xk_s0, xk_s1, fk, fk_s0, fk_s1, nk, xi, xi_s0, fi, fi_s0, order, knowns,
+                            wm, device, &rc)) {
+            if (iters_out) *iters_out = 0;
+            return rc;
+        }
+    }
     wlsqm_solver_t* s = nullptr;
     int rc = wlsqm_solver_create(dimension, ncases, nk, order, knowns, wm, algorithm, do_sens, max_iter, 0, device, &s);
     if (rc) return rc;

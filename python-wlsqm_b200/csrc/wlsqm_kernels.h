@@ -39,6 +39,9 @@ struct PrepRegParams {
     int nb;                                          // 32-column blocks of the monomial table
     int fit_doubles;                                 // shared-memory doubles per fit region (prep_reg_fit_doubles)
     int warp_doubles;                                // per warp: monomial table + prep_reg_fits_per_warp() fit regions
+    // one-shot fit (no operator): data and in/out solution; fk == nullptr selects the operator-building kernel
+    const double* fk; long long fk_s0, fk_s1;        // [ncases][nk]
+    double* fi; long long fi_s0;                     // [ncases][>= no]: knowns read, unknowns written
 };
 
 struct SolveParams {
@@ -89,7 +92,8 @@ cudaError_t launch_prepare_smem(int dim, const PrepareParams& P, int blocks, int
 int prep_reg_fit_doubles(int dim, int maxorder, int nb, int nkn_max);
 int prep_reg_warp_doubles(int dim, int maxorder, int nb, int nkn_max);
 int prep_reg_fits_per_warp(int dim, int maxorder);
-cudaError_t prepare_reg_occupancy(int dim, int maxorder, int threads, size_t smem, int* ctas_per_sm);
+cudaError_t prepare_reg_occupancy(int dim, int maxorder, int threads, size_t smem, int* ctas_per_sm, bool direct = false);
+bool prepare_reg_direct_ok(int dim, int maxorder);
 cudaError_t launch_prepare_reg(int dim, int maxorder, const PrepRegParams& P, int blocks, int threads, size_t smem,
                                cudaStream_t st);
 cudaError_t launch_solve(int dim, const SolveParams& P, int blocks, int threads, size_t smem, cudaStream_t st);

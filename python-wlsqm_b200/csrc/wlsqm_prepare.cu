@@ -111,9 +111,14 @@ __device__ __forceinline__ unsigned group_min(unsigned v, int grp) {
     return r;
 }
 
-template <int DIM, int ORD>
+// DIRECT = one-shot fit (fit_*_many without sens, simple.pyx:731-1170): no operator is formed or stored.  The data
+// fk rides through the Gram phase in the unused padding slot NO of the monomial table, which makes
+// b_s = sum_k w_k f_k c[k][s] row NO of the Gram matrix; b is eliminated along with the matrix in the LU phase
+// (one extra column) and back-substituted across the lanes, and fi is written directly.
+template <int DIM, int ORD, bool DIRECT>
 __global__ void __launch_bounds__(PREP_REG_THREADS, PK<DIM, ORD>::MINB) prepare_reg_kernel(PrepRegParams P) {
     using K = PK<DIM, ORD>;
+    static_assert(!DIRECT || (K::RPL == 1 && K::NOP > K::NO), "the one-shot path needs one row per lane and a free padding slot");
     constexpr int NOP = K::NOP, NRP = K::NRP, RPL = K::RPL, T = K::T, LDA = K::LDA, CB = PREP_CB, BLK = K::BLK;
     constexpr int LPF = K::LPF, FPW = K::FPW;
     constexpr unsigned FULL = 0xffffffffu;
@@ -172,6 +177,9 @@ __global__ void __launch_bounds__(PREP_REG_THREADS, PK<DIM, ORD>::MINB) prepare_
             double v = 0.0;
             if constexpr (s < K::NO) {
                 if (in && s < no) v = monomial<DIM, s>(px, py, pz);
+            }
+            if constexpr (DIRECT && s == K::NO) {
+                if (in) v = P.fk[c * P.fk_s0 + (long long)k * P.fk_s1];
             }
             ctb[s * CB] = v;
         });
@@ -277,7 +285,7 @@ __global__ void __launch_bounds__(PREP_REG_THREADS, PK<DIM, ORD>::MINB) prepare_
             }
             __syncwarp();
             // knowns elimination: right-hand sides -A[oj, known om] (impl.pyx:792-818), weight 1
-            if (nkn) {
+            if (!DIRECT && nkn) {
                 double* KN = fb + oKN;
                 for (int t = lane; t < no * nkn; t += 32) {
                     const int s = t % no, mk = t / no;
@@ -318,12 +326,27 @@ __global__ void __launch_bounds__(PREP_REG_THREADS, PK<DIM, ORD>::MINB) prepare_
                     a[t][m] = valid ? v.x : 0.0;
                     a[t][m + 1] = valid ? v.y : 0.0;
                 }
+                // one-shot fit: the padding slot carries the right-hand side, it is not a matrix column
+                if constexpr (DIRECT && K::NO < NRP) a[t][K::NO] = 0.0;
             } else {
 #pragma unroll
                 for (int m = 0; m < NRP; ++m) {
                     const int om = m < nr ? gR2O[m] : 0;
                     const double v = g[om];
                     a[t][m] = (valid && m < nr) ? v : 0.0;
+                }
+            }
+        }
+        // one-shot fit: this row's right-hand side, knowns eliminated (impl.pyx:792-818): b_j = G[oj][NO] - sum_m fi[om] A[oj][om]
+        double bj = 0.0;
+        if constexpr (DIRECT) {
+            if (jl < nr) {
+                const double* g = gG + gR2O[jl] * LDA;
+                bj = g[K::NO];
+                const int nkn_g = __popcll(knowns);
+                for (int mk = 0; mk < nkn_g; ++mk) {
+                    const int om = gR2O[nr + mk];
+                    bj = fma(-P.fi[cg * P.fi_s0 + om], g[om], bj);
                 }
             }
         }
@@ -388,6 +411,7 @@ __global__ void __launch_bounds__(PREP_REG_THREADS, PK<DIM, ORD>::MINB) prepare_
                 a[t][m + 1] *= rj[t] * r2.y;
             }
         }
+        if constexpr (DIRECT) bj *= rj[0];
         if (P.As && nr > 0) {   // debug=True: keep the scaled matrix for conds() (impl.pyx:662-682)
             double* as = P.As + cg * (long long)P.as_stride;
 #pragma unroll
@@ -456,6 +480,7 @@ __global__ void __launch_bounds__(PREP_REG_THREADS, PK<DIM, ORD>::MINB) prepare_
                         double* row = gG + p * LDA;
 #pragma unroll
                         for (int m = 0; m < NRP; m += 2) st2(row + m, a[t][m], a[t][m + 1]);
+                        if constexpr (DIRECT) row[NOP] = bj;
                         gREC[p] = make_double2(rj[t], __hiloint2double(0, roff[t]));
                         pos[t] = p;
                         act[t] = false;
@@ -471,6 +496,9 @@ __global__ void __launch_bounds__(PREP_REG_THREADS, PK<DIM, ORD>::MINB) prepare_
                     if (piv[t]) gDINV[p] = rp;
                     l[t] = a[t][p] * rp;
                     if (act[t]) a[t][p] = l[t];
+                    if constexpr (DIRECT) {
+                        if (act[t]) bj = fma(-l[t], gG[p * LDA + NOP], bj);
+                    }
                 }
 #pragma unroll
                 for (int m = ((p + 1) & ~1); m < NRP; m += 2) {
@@ -486,6 +514,36 @@ __global__ void __launch_bounds__(PREP_REG_THREADS, PK<DIM, ORD>::MINB) prepare_
             }
         }
         __syncwarp();
+
+        if constexpr (DIRECT) {
+            // ---- U x = y across the lanes: lane jl takes row jl of the pivot order (re-read from the published LU) ----
+            double u[NRP];
+            double y = 0.0;
+            if (jl < nr) {
+#pragma unroll
+                for (int m = 0; m < NRP; m += 2) {
+                    const double2 v = ld2(gG + jl * LDA + m);
+                    u[m] = v.x;
+                    u[m + 1] = v.y;
+                }
+                y = gG[jl * LDA + NOP];
+            } else {
+#pragma unroll
+                for (int m = 0; m < NRP; ++m) u[m] = 0.0;
+            }
+#pragma unroll
+            for (int m = NRP - 1; m >= 0; --m) {
+                if (m < nrmax) {
+                    if (jl == m && m < nr) y = y / u[m];      // dgetrs divides by the pivot (exact where the data are)
+                    const double xm = __shfl_sync(FULL, y, grp * LPF + m);
+                    if (jl < m && m < nr) y = fma(-u[m], xm, y);
+                }
+            }
+            // fi[r2o[j]] = x_j * col_j; known slots and columns beyond the model are not touched
+            if (jl < nr) P.fi[cg * P.fi_s0 + gR2O[jl]] = y * gRS[jl];
+            __syncwarp();
+            continue;
+        }
 
         // ================= whole warp: P5 operator columns (dgetrs per right-hand side) =================
         // The FPW fits go through the substitution side by side (independent dependency chains).
@@ -605,15 +663,26 @@ __global__ void __launch_bounds__(PREP_REG_THREADS, PK<DIM, ORD>::MINB) prepare_
 }
 
 // ---- launch -----------------------------------------------------------------------------------------
+template <int DIM, int ORD, bool DIRECT>
+static cudaError_t launch_k(const PrepRegParams& P, int blocks, int threads, size_t smem, cudaStream_t st,
+                            int* occupancy) {
+    cudaError_t e = cudaFuncSetAttribute(prepare_reg_kernel<DIM, ORD, DIRECT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)smem);
+    if (e != cudaSuccess) return e;
+    if (occupancy)
+        return cudaOccupancyMaxActiveBlocksPerMultiprocessor(occupancy, prepare_reg_kernel<DIM, ORD, DIRECT>, threads, smem);
+    prepare_reg_kernel<DIM, ORD, DIRECT><<<blocks, threads, smem, st>>>(P);
+    return cudaGetLastError();
+}
+
 template <int DIM, int ORD>
 static cudaError_t launch_t(const PrepRegParams& P, int blocks, int threads, size_t smem, cudaStream_t st,
                             int* occupancy) {
-    cudaError_t e = cudaFuncSetAttribute(prepare_reg_kernel<DIM, ORD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)smem);
-    if (e != cudaSuccess) return e;
-    if (occupancy) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(occupancy, prepare_reg_kernel<DIM, ORD>, threads, smem);
-    prepare_reg_kernel<DIM, ORD><<<blocks, threads, smem, st>>>(P);
-    return cudaGetLastError();
+    if (P.fk) {
+        if constexpr (PK<DIM, ORD>::RPL == 1) return launch_k<DIM, ORD, true>(P, blocks, threads, smem, st, occupancy);
+        else return cudaErrorInvalidValue;      // (3D order 4: two rows per lane -- the caller takes the operator path)
+    }
+    return launch_k<DIM, ORD, false>(P, blocks, threads, smem, st, occupancy);
 }
 
 template <int DIM>
@@ -635,9 +704,15 @@ static cudaError_t dispatch(int dim, int ord, const PrepRegParams& P, int blocks
     return launch_d<3>(ord, P, blocks, threads, smem, st, occupancy);
 }
 
-cudaError_t prepare_reg_occupancy(int dim, int maxorder, int threads, size_t smem, int* ctas_per_sm) {
+cudaError_t prepare_reg_occupancy(int dim, int maxorder, int threads, size_t smem, int* ctas_per_sm, bool direct) {
     PrepRegParams P{};
+    if (direct) P.fk = reinterpret_cast<const double*>(8);    // selects the one-shot instantiation; nothing is launched
     return dispatch(dim, maxorder, P, 0, threads, smem, nullptr, ctas_per_sm);
+}
+
+bool prepare_reg_direct_ok(int dim, int maxorder) {
+    const int nrp = (prep_no(dim, maxorder) + 3) & ~3;
+    return nrp <= 32;
 }
 
 cudaError_t launch_prepare_reg(int dim, int maxorder, const PrepRegParams& P, int blocks, int threads, size_t smem,

@@ -29,7 +29,7 @@ def test_single_case_and_single_neighbour():
     # order 0 with one neighbour: the fit is that neighbour's value (reference: fit_2D(...) -> fi = [3.])
     fi = np.zeros(1)
     assert wlsqm.fit_2D(np.array([[0.1, 0.2]]), np.array([3.0]), np.array([0.0, 0.0]), fi, None, 0, 0, 0, 1) == 0
-    assert fi[0] == 3.0
+    assert abs(fi[0] - 3.0) <= 2 * np.finfo(float).eps * 3.0      # (the equilibration rounds 1 / sqrt(w))
     # a batch of one case through every entry point agrees with the oracle
     x, hoods, f = parity.make_case(50, 2, 12)
     xk, fk = parity.gathered(x, f, hoods)
