@@ -217,6 +217,28 @@ def cpu_baseline(args):
         out = {"value": n * steps / dt, "unit": UNIT, "cores": nt, "kind": "reference",
                "sample": f"{n} points x {steps} solve() steps (prepare {n / tp:.3g} fits/s at ntasks={nt})",
                "prepare_fits_per_s": n / tp}
+        try:    # configs[0]: the reference's one-shot fit_2D_many_parallel, 10k points, order 2, k=12
+            n1, k1 = 10_000, 12
+            x1 = wl.cloud(n1, 2, unit_box=True)
+            h1 = wl.hoods_knn(x1, k1)
+            f1 = wl.field(x1)
+            xk1, fk1 = np.ascontiguousarray(x1[h1]), np.ascontiguousarray(f1[h1])
+            fi1 = np.zeros((n1, 6))
+            fi1[:, 0] = f1
+            m1 = (np.full(n1, k1, np.int32), np.full(n1, 2, np.int32), np.full(n1, ref.b2_F, np.int64),
+                  np.full(n1, ref.WEIGHT_CENTER, np.int32))
+            tb = None
+            for nt1 in sorted({1, 8, cores}):
+                for _ in range(3):
+                    t0 = time.perf_counter()
+                    ref.fit_2D_many_parallel(xk1, fk1, m1[0], x1, fi1, None, 0, m1[1], m1[2], m1[3], ntasks=nt1)
+                    d = time.perf_counter() - t0
+                    if tb is None or d < tb[0]:
+                        tb = (d, nt1)
+            out["cfg1_fit_many_fits_per_s"] = n1 / tb[0]
+            out["cfg1_fit_many_ntasks"] = tb[1]
+        except Exception as exc:
+            print("cpu cfg1 leg failed: %r" % (exc,), file=sys.stderr)
     else:
         s = orc.OracleSolver(DIM, nk, od, kn, wm)
         t0 = time.perf_counter()
@@ -272,6 +294,42 @@ def run_b200(args, rank, world, local_rank):
         torch.cuda.synchronize()
         prep_ms.append(e0.elapsed_time(e1))
     prep_ms = min(prep_ms)
+
+    # ---- one-shot fits (fit_2D_many_parallel, "local fits/s"): configs[0] shape and the headline cloud ----
+    oneshot = None
+    try:
+        def wall(fn, reps=5):
+            fn()
+            torch.cuda.synchronize()
+            ts = []
+            for _ in range(reps):
+                t0 = time.perf_counter()
+                fn()
+                torch.cuda.synchronize()
+                ts.append(time.perf_counter() - t0)
+            return float(np.median(ts))
+        n1, k1 = 10_000, 12
+        x1 = wl.cloud(n1, 2, unit_box=True)
+        h1 = wl.hoods_knn(x1, k1)
+        f1 = wl.field(x1)
+        xk1, fk1 = np.ascontiguousarray(x1[h1]), np.ascontiguousarray(f1[h1])
+        fi1 = np.zeros((n1, 6))
+        fi1[:, 0] = f1
+        m1 = (np.full(n1, k1, np.int32), np.full(n1, 2, np.int32), np.full(n1, wlsqm.b2_F, np.int64),
+              np.full(n1, wlsqm.WEIGHT_CENTER, np.int32))
+        t_host = wall(lambda: wlsqm.fit_2D_many_parallel(xk1, fk1, m1[0], x1, fi1, None, 0, m1[1], m1[2], m1[3], ntasks=8))
+        d1 = [torch.from_numpy(a).to(dev) for a in (xk1, fk1, x1, fi1)]
+        t_dev = wall(lambda: wlsqm.fit_2D_many_parallel(d1[0], d1[1], m1[0], d1[2], d1[3], None, 0, m1[1], m1[2], m1[3], ntasks=8))
+        fi_big = torch.zeros((n, NO), dtype=torch.float64, device=dev)
+        t_big = wall(lambda: wlsqm.fit_2D_many_parallel(xk_d, fk_d[0], nk, x_d, fi_big, None, 0, od, kn, wm, ntasks=8), reps=3)
+        oneshot = {"cfg1": {"workload": "configs[0]: fit_2D_many_parallel, 10k points, order 2, k=12, b2_F, WEIGHT_CENTER",
+                            "host_arrays_ms": 1e3 * t_host, "host_arrays_fits_per_s": n1 / t_host,
+                            "cuda_tensors_ms": 1e3 * t_dev, "cuda_tensors_fits_per_s": n1 / t_dev},
+                   "headline_cloud": {"workload": "fit_2D_many_parallel on the 1M-point cloud (order 4, k=30), CUDA tensors, "
+                                                  "wall clock per call", "ms": 1e3 * t_big, "fits_per_s": n / t_big}}
+        del fi_big, d1
+    except Exception as exc:      # extra information must never break the headline line
+        print("one-shot leg failed: %r" % (exc,), file=sys.stderr)
     del xk_d
 
     def barrier():
@@ -372,6 +430,8 @@ def run_b200(args, rank, world, local_rank):
                                      "kernel": "wlsqm::prepare_reg_kernel<2,4>"}},
             "clocks": clocks,
         }
+        if oneshot:
+            line["one_shot_fits"] = oneshot
         if hoods_ms:
             line["e2e_hoods_extension"] = {
                 "value": world * n * e2e_steps / (hoods_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(n * 8),

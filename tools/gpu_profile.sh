@@ -14,6 +14,16 @@ timeout 900 ncu --set full --clock-control none --import-source on -k regex:prep
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:interpolate_kernel -s 2 -c 2 -o gpurun_out/interp_$TAG -f python benchmarks/run_configs.py --only cfg5 > gpurun_out/ncu_interp_$TAG.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:solve_kernel -s 2 -c 1 -o gpurun_out/solve3d_$TAG -f python benchmarks/run_configs.py --only cfg3 --scale 0.25 > gpurun_out/ncu_solve3d_$TAG.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:solve_pack_kernel -s 2 -c 2 -o gpurun_out/solvepack_$TAG -f python benchmarks/run_configs.py --only cfg4 > gpurun_out/ncu_solvepack_$TAG.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:solve_kernel -s 12 -c 1 -o gpurun_out/solveiter_$TAG -f python benchmarks/run_configs.py --only cfg2v > gpurun_out/ncu_solveiter_$TAG.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:interpolate_kernel -s 9 -c 1 -o gpurun_out/interp1_$TAG -f python benchmarks/run_configs.py --only cfg5 > gpurun_out/ncu_interp1_$TAG.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:prepare_reg_kernel -s 1 -c 1 -o gpurun_out/fitdirect_$TAG -f python tools/oneshot_1m.py > gpurun_out/ncu_fitdirect_$TAG.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:lu_reg_kernel -s 8 -c 1 -o gpurun_out/lureg_$TAG -f python benchmarks/lapack_bench.py --no-cpu > gpurun_out/ncu_lureg_$TAG.log 2>&1
+timeout 600 python benchmarks/lapack_bench.py > gpurun_out/lapack_$TAG.jsonl 2>&1
+timeout 300 python tools/oneshot_probe.py > gpurun_out/oneshot_$TAG.txt 2>&1
 timeout 1200 python benchmarks/run_configs.py > gpurun_out/configs_$TAG.jsonl 2>&1; tail -25 gpurun_out/configs_$TAG.jsonl | cut -c1-220
 timeout 600 python benchmarks/pipeline.py --host-tree > gpurun_out/pipeline_$TAG.jsonl 2>&1
 ls -la gpurun_out/*_$TAG.ncu-rep
+# the reports together exceed what gpurun copies back (64 MiB): summarise them here, keep only the headline report
+PROFILES_OUT=gpurun_out/profiles_$TAG python tools/make_profiles.py $TAG r01 2>&1 | tail -15
+for f in gpurun_out/*_$TAG.ncu-rep; do case "$f" in *solve_$TAG.ncu-rep) ;; *) rm -f "$f";; esac; done
+du -sh gpurun_out

@@ -7,7 +7,9 @@ from pathlib import Path
 ROOT = Path(__file__).resolve().parent.parent
 tag = sys.argv[1]
 rnd = sys.argv[2] if len(sys.argv) > 2 else "r01"
-OUT = ROOT / "profiles"
+import os
+OUT = Path(os.environ.get("PROFILES_OUT", str(ROOT / "profiles")))
+OUT.mkdir(parents=True, exist_ok=True)
 KEEP = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "dram__cycles_active.avg.pct_of_peak_sustained_elapsed",
         "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_bytes.sum", "sm__warps_active.avg.pct_of_peak_sustained_active",
         "smsp__issue_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum", "sm__inst_executed_pipe_fp64.sum",
@@ -43,7 +45,9 @@ def summarise(name, rep):
 
 G = ROOT / "gpurun_out"
 for name, stem in (("solve_kernel", "solve"), ("prepare_reg_kernel", "prepare"), ("interpolate_kernel", "interp"),
-                   ("solve_kernel_3d_iter_sens", "solve3d"), ("solve_pack_kernel", "solvepack")):
+                   ("solve_kernel_3d_iter_sens", "solve3d"), ("solve_pack_kernel", "solvepack"),
+                   ("solve_kernel_2d_iterative", "solveiter"), ("interpolate_kernel_one_slot", "interp1"),
+                   ("fit_direct_kernel", "fitdirect"), ("lu_reg_kernel", "lureg")):
     rep = G / f"{stem}_{tag}.ncu-rep"
     if not rep.exists():
         print("missing", rep); continue
@@ -62,7 +66,7 @@ src = G / f"launches_{tag}.csv"
 if src.exists():
     keep = [l for l in src.read_text().splitlines() if not l.startswith("==")]
     (OUT / f"{rnd}_launches.csv").write_text("\n".join(keep) + "\n")
-for stem in ("configs", "pipeline"):
+for stem in ("configs", "pipeline", "lapack"):
     p = G / f"{stem}_{tag}.jsonl"
     if p.exists():
         shutil.copy(p, OUT / f"{rnd}_{stem}.jsonl")
@@ -70,3 +74,6 @@ for stem in ("bench", "bench_ref"):
     p = G / f"{stem}_{tag}.json"
     if p.exists():
         shutil.copy(p, OUT / f"{rnd}_{stem}.json")
+p = G / f"oneshot_{tag}.txt"
+if p.exists():
+    shutil.copy(p, OUT / f"{rnd}_oneshot.txt")
