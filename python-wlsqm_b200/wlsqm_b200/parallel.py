@@ -101,6 +101,22 @@ class ShardedExpertSolver:
     def solve(self, fk, fi, sens=None, local=False):
         return self.solver.solve(self._rows(fk, local), self._rows(fi, local), self._rows(sens, local))
 
+    # -- neighbourhoods as index lists: replicated points, one all-gather of the per-point data per step --
+    def prepare_hoods(self, x, hoods, local=False):
+        """``x``: the FULL point cloud, replicated on every rank (16 MB per million 2D points; the neighbours of a
+        contiguous case range may lie anywhere in index space unless the points are spatially sorted -- the "halo");
+        ``hoods``: the global (n_total, k) int32 index lists into ``x`` (or this rank's rows with ``local=True``).
+        The origins of this rank's cases are ``x[lo:hi]``."""
+        return self.solver.prepare_hoods(x, self._rows(hoods, local), xi=x[self.lo:self.hi])
+
+    def solve_hoods(self, f, fi, sens=None, local=False, f_is_local=False, group=None):
+        """``f``: one value per point of the full cloud (replicated), or -- ``f_is_local=True`` -- only this rank's
+        slice ``f[lo:hi]`` (what a time-stepping code owns), which is all-gathered first: the one exchange of a step,
+        8 bytes per point over NCCL.  ``fi`` / ``sens``: global arrays (sliced here) or local rows (``local=True``)."""
+        if f_is_local:
+            f = all_gather_rows(f, self.n_total, self.lo, group)
+        return self.solver.solve_hoods(f, self._rows(fi, local), self._rows(sens, local))
+
     def gather(self, local_rows, group=None):
         """all-gather a per-rank result (e.g. the local fi tensor) into the global array"""
         return all_gather_rows(local_rows, self.n_total, self.lo, group)

@@ -252,3 +252,33 @@ def test_guest_mode_borrows_the_hosts_operators():
         host = wlsqm.ExpertSolver(dim, nk, od, kn, wm)
         host.prepare(x, xk)
         wlsqm.ExpertSolver(dim, nk, od, np.zeros(n, np.int64), wm, host=host)
+
+
+def test_sharded_solver_rows_equal_unsharded_bit_for_bit():
+    """the multi-GPU sharding of wlsqm_b200.parallel, exercised on one device: the ranks' contiguous case ranges,
+    solved one after the other (gathered arrays and the hoods path), concatenate to the unsharded result exactly"""
+    torch = pytest.importorskip("torch")
+    from wlsqm_b200 import parallel
+    n, k, dim, order = 3001, 30, 2, 4
+    x, hoods, f = parity.make_case(n, dim, k)
+    xk, fk = parity.gathered(x, f, hoods)
+    nk, od, kn, wm = (np.full(n, k, np.int32), np.full(n, order, np.int32), np.zeros(n, np.int64),
+                      np.full(n, 1, np.int32))
+    fi_full, _, _ = _solve_gpu(dim, nk, od, kn, wm, x, xk, fk, np.zeros((n, 15)))
+    x_d, f_d = torch.from_numpy(x).cuda(), torch.from_numpy(f).cuda()
+    hoods_d = torch.from_numpy(hoods).cuda()
+    world = 3
+    parts, parts_h = [], []
+    for rank in range(world):
+        sh = parallel.ShardedExpertSolver(dim, nk, od, kn, wm, rank=rank, world=world)
+        sh.prepare(x, xk)
+        fi = np.zeros((n, 15))
+        sh.solve(fk, fi)
+        assert not fi[:sh.lo].any() and not fi[sh.hi:].any()          # other ranks' rows are not touched
+        parts.append(fi[sh.lo:sh.hi])
+        sh.prepare_hoods(x_d, hoods_d)
+        fi_h = torch.zeros((sh.hi - sh.lo, 15), dtype=torch.float64, device="cuda")
+        sh.solve_hoods(f_d, fi_h, local=True)
+        parts_h.append(fi_h.cpu().numpy())
+    assert np.array_equal(np.concatenate(parts), fi_full)
+    assert np.array_equal(np.concatenate(parts_h), fi_full)
