@@ -77,6 +77,17 @@ __global__ void __launch_bounds__(INTERP_THREADS, MINB) interpolate_kernel(Inter
 #pragma unroll
         for (int d = 0; d < DIM; ++d) xq[j][d] = P.x[mm * P.x_s0 + d];
     }
+    // the model rows of all Q queries are requested before the first one is used: the chain index -> row is the
+    // latency that bounds this kernel, and an in-order thread would otherwise pay it once per query
+#pragma unroll
+    for (int j = 0; j < Q; ++j) {
+        const bool bad = P.nmodels > 0 && (idx[j] < 0 || idx[j] >= P.nmodels);
+        const double* fg = P.fi + (bad ? 0 : idx[j]) * P.fi_s0;
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(fg));
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(P.xi + (bad ? 0 : idx[j]) * P.xi_s0));
+        if (DIM >= 2) asm volatile("prefetch.global.L1 [%0];" ::"l"(fg + (DIM == 2 ? 14 : 16)));
+        if (DIM >= 3) asm volatile("prefetch.global.L1 [%0];" ::"l"(fg + 34));
+    }
 #pragma unroll
     for (int j = 0; j < Q; ++j) {
         const long long m = base + (long long)j * blockDim.x;
