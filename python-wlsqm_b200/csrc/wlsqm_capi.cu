@@ -16,6 +16,7 @@
 #include "wlsqm_kernels.h"
 #include "wlsqm_grid.h"
 #include "wlsqm_mem.h"
+#include "wlsqm_host.h"
 
 namespace wlsqm {
 GridView grid_view(const wlsqm_grid* g);
@@ -359,6 +360,35 @@ int to_dense(double* dst, const double* src, long long rows, long long width, lo
                          cudaMemcpyDefault, st));
     return WLSQM_OK;
 }
+// below this size the driver's own staging of pageable copies is as fast (measured: 24 MB at 25 GB/s, 240 MB at 12 GB/s)
+constexpr long long BOUNCE_MIN_BYTES = 64ll << 20;
+// to_dense / from_dense for arrays that may be ordinary pageable host memory: large ones go through the page-locked
+// rings with threaded host copies (wlsqm_host.h); the call returns when the host side is done with the array
+int stage_in(int device, double* dst, const double* src, long long rows, long long width, long long pitch, cudaStream_t st) {
+    if (rows * width * 8 >= BOUNCE_MIN_BYTES && (size_t)width * 8 <= BOUNCE_SLOT_BYTES && env_int("WLSQM_BOUNCE", 1) != 0 &&
+        !is_device_ptr(src) && is_pageable_host(src)) {
+        bounce_lock();
+        const cudaError_t e = h2d_bounced(bounce_rings(device).in, dst, src, rows, width, pitch, st);
+        bounce_unlock();
+        if (e != cudaSuccess) return fail(WLSQM_E_CUDA, "host -> device staging: %s", cudaGetErrorString(e));
+        return WLSQM_OK;
+    }
+    return to_dense(dst, src, rows, width, pitch, st);
+}
+int from_dense(double* dst, long long pitch, const double* src, long long src_pitch, long long rows, long long width,
+               cudaStream_t st);
+int stage_out(int device, double* dst, long long pitch, const double* src, long long src_pitch, long long rows, long long width,
+              cudaStream_t st) {
+    if (rows * width * 8 >= BOUNCE_MIN_BYTES && (size_t)width * 8 <= BOUNCE_SLOT_BYTES && env_int("WLSQM_BOUNCE", 1) != 0 &&
+        !is_device_ptr(dst) && is_pageable_host(dst)) {
+        bounce_lock();
+        const cudaError_t e = d2h_bounced(bounce_rings(device).out, dst, pitch, src, src_pitch, rows, width, st);
+        bounce_unlock();
+        if (e != cudaSuccess) return fail(WLSQM_E_CUDA, "device -> host staging: %s", cudaGetErrorString(e));
+        return WLSQM_OK;
+    }
+    return from_dense(dst, pitch, src, src_pitch, rows, width, st);
+}
 int from_dense(double* dst, long long pitch, const double* src, long long src_pitch, long long rows, long long width,
                cudaStream_t st) {
     if (rows == 0 || width == 0) return WLSQM_OK;
@@ -682,7 +712,7 @@ int wlsqm_solver_prepare(wlsqm_solver_t* s, const double* xi, int64_t xi_s0, con
         rc = buf.reserve((size_t)n * row * 8);
         if (rc) return rc;
         if (xk_s1 == dim) {
-            rc = to_dense((double*)buf.p, xk, n, row, xk_s0, s->stream);
+            rc = stage_in(s->device, (double*)buf.p, xk, n, row, xk_s0, s->stream);
             if (rc) return rc;
         } else if (xk_dev) {
             gather3_kernel<<<s->sm_count * 8, 256, 0, s->stream>>>((double*)buf.p, xk, n, s->maxnk, dim, xk_s0, xk_s1, 1);
@@ -814,11 +844,37 @@ int wlsqm_solver_solve(wlsqm_solver_t* s, const double* fk, int64_t fk_s0, int64
         CU(cudaEventRecord(s->events[nev - 1], st));
         CU(cudaStreamWaitEvent(s_in, s->events[nev - 1], 0));
     }
+    // ordinary (pageable) numpy arrays: host threads copy through rings of page-locked slots (wlsqm_host.h)
+    const bool fk_bounce = !fk_dev && n * s->maxnk * 8 >= BOUNCE_MIN_BYTES && is_pageable_host(fk) &&
+                           (size_t)s->maxnk * 8 <= BOUNCE_SLOT_BYTES && env_int("WLSQM_BOUNCE", 1) != 0;
+    const bool fi_bounce = !fi_dev && s->uniform_no && (fk_bounce || n * s->maxno * 8 >= BOUNCE_MIN_BYTES) &&
+                           is_pageable_host(fi) && env_int("WLSQM_BOUNCE", 1) != 0 &&
+                           (size_t)chunk * s->uni.no * 8 <= BOUNCE_SLOT_BYTES;
+    struct RingGuard {
+        bool on = false;
+        ~RingGuard() { if (on) bounce_unlock(); }
+    } ring_guard;
+    BouncePair* rings = nullptr;
+    if (fk_bounce || fi_bounce) {
+        bounce_lock();
+        ring_guard.on = true;
+        rings = &bounce_rings(s->device);
+    }
+    struct PendingOut { int slot; long long c0, rows; };
+    std::vector<PendingOut> pend;
+    auto finish_oldest = [&]() -> int {
+        const PendingOut p = pend.front();
+        pend.erase(pend.begin());
+        CU(d2h_bounced_finish(rings->out, p.slot, fi + p.c0 * fi_s0, fi_s0, p.rows, s->uni.no));
+        return WLSQM_OK;
+    };
     LaunchCfg L;
     size_t ev = 0;
     for (long long c0 = 0; c0 < n; c0 += chunk) {
         const long long c1 = std::min(n, c0 + chunk), rows = c1 - c0;
-        if (!fk_dev) {
+        if (fk_bounce) {
+            CU(h2d_bounced(rings->in, (double*)s->st_fk.p + c0 * s->maxnk, fk + c0 * fk_s0, rows, s->maxnk, fk_s0, s_in));
+        } else if (!fk_dev) {
             rc = to_dense((double*)s->st_fk.p + c0 * s->maxnk, fk + c0 * fk_s0, rows, s->maxnk, fk_s0, s_in);
             if (rc) return rc;
         }
@@ -847,7 +903,12 @@ int wlsqm_solver_solve(wlsqm_solver_t* s, const double* fk, int64_t fk_s0, int64
             CU(cudaStreamWaitEvent(s_out, s->events[ev], 0));
             ++ev;
         }
-        if (!fi_dev && s->uniform_no) {
+        if (fi_bounce) {
+            if ((int)pend.size() >= BOUNCE_SLOTS - 1) { rc = finish_oldest(); if (rc) return rc; }
+            const int slot = d2h_bounced_begin(rings->out, s->fi_case + c0 * s->maxno, s->maxno, rows, s->uni.no, s_out);
+            if (slot < 0) return fail(WLSQM_E_CUDA, "device -> host staging: %s", cudaGetErrorString((cudaError_t)(-slot)));
+            pend.push_back(PendingOut{slot, c0, rows});
+        } else if (!fi_dev && s->uniform_no) {
             rc = from_dense(fi + c0 * fi_s0, fi_s0, s->fi_case + c0 * s->maxno, s->maxno, rows, s->uni.no, s_out);
             if (rc) return rc;
         }
@@ -855,6 +916,7 @@ int wlsqm_solver_solve(wlsqm_solver_t* s, const double* fk, int64_t fk_s0, int64
             CU(cudaMemcpyAsync(sens + c0 * plane, (const double*)s->st_sens.p + c0 * plane, (size_t)rows * plane * 8,
                                cudaMemcpyDeviceToHost, s_out));
     }
+    while (!pend.empty()) { rc = finish_oldest(); if (rc) return rc; }
     if (deferred) CU(launch_scatter_fi(s->dmeta, s->uni, n, s->fi_case, s->maxno, fi, fi_s0, st));
 
     // ---- results that need a host-side scatter (heterogeneous no / nk, pitched sens) ---------------------
@@ -1183,12 +1245,12 @@ static int fit_many_direct(int dimension, int64_t ncases, const double* xk, int6
         R.fk = fk; R.fk_s0 = fk_s0; R.fk_s1 = fk_s1; R.fi = fi; R.fi_s0 = fi_s0;
         if (!xk_dev) {
             rc = bxk.reserve((size_t)ncases * k * dim * 8);
-            if (!rc) rc = to_dense((double*)bxk.p, xk, ncases, (long long)k * dim, xk_s0, st);
+            if (!rc) rc = stage_in(device, (double*)bxk.p, xk, ncases, (long long)k * dim, xk_s0, st);
             R.xk = (const double*)bxk.p; R.xk_s0 = (long long)k * dim; R.xk_s1 = dim;
         }
         if (!rc && !fk_dev) {
             rc = bfk.reserve((size_t)ncases * k * 8);
-            if (!rc) rc = to_dense((double*)bfk.p, fk, ncases, k, fk_s0, st);
+            if (!rc) rc = stage_in(device, (double*)bfk.p, fk, ncases, k, fk_s0, st);
             R.fk = (const double*)bfk.p; R.fk_s0 = k; R.fk_s1 = 1;
         }
         if (!rc && !xi_dev) {
@@ -1198,7 +1260,7 @@ static int fit_many_direct(int dimension, int64_t ncases, const double* xk, int6
         }
         if (!rc && !fi_dev) {
             rc = bfi.reserve((size_t)ncases * no * 8);
-            if (!rc) rc = to_dense((double*)bfi.p, fi, ncases, no, fi_s0, st);      // the known values travel in
+            if (!rc) rc = stage_in(device, (double*)bfi.p, fi, ncases, no, fi_s0, st);      // the known values travel in
             R.fi = (double*)bfi.p; R.fi_s0 = no;
         }
         if (rc) return done(rc);
@@ -1206,7 +1268,7 @@ static int fit_many_direct(int dimension, int64_t ncases, const double* xk, int6
         if (!config_prepare_reg(&sh, R, L, true)) return done(-1000);          // does not fit: general path
         cudaError_t e = launch_prepare_reg(dim, m.order, R, L.blocks, L.threads, L.smem, st);
         if (e == cudaSuccess && !fi_dev) {
-            rc = from_dense(fi, fi_s0, (const double*)bfi.p, no, ncases, no, st);
+            rc = stage_out(device, fi, fi_s0, (const double*)bfi.p, no, ncases, no, st);
             if (rc) return done(rc);
         }
         if (e == cudaSuccess) e = cudaStreamSynchronize(st);

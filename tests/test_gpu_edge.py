@@ -123,3 +123,37 @@ def test_pitched_and_strided_host_inputs():
     wlsqm.fit_2D_many(xk_big[::2, :k], fk_big[:, :2 * k:2], nk, x_big[:, :2], fi_big[:, :no], None, 0, od, kn, wm)
     assert np.array_equal(fi_big[:, :no], fi_ref)
     assert (fi_big[:, no:] == 7.0).all()          # columns beyond the model are not touched
+
+
+def test_large_pageable_arrays_take_the_threaded_staging_path():
+    """ordinary numpy arrays above 64 MB go through the page-locked rings with threaded host copies
+    (csrc/wlsqm_host.cu): same bits as page-locked arrays and as CUDA tensors, pitched fi rows left intact"""
+    torch = pytest.importorskip("torch")
+    n, k, no = 320_000, 30, 15            # fk = 76.8 MB
+    g = torch.Generator(device="cuda").manual_seed(3)
+    xi_d = 20.0 * torch.rand((n, 2), dtype=torch.float64, device="cuda", generator=g)
+    xk_d = xi_d[:, None, :] + 0.015 * (2 * torch.rand((n, k, 2), dtype=torch.float64, device="cuda", generator=g) - 1)
+    fk_d = torch.sin(xk_d[..., 0]) * torch.cos(xk_d[..., 1])
+    nk, od, kn, wm = _meta(n, k, 4, 0, 1)
+    s = wlsqm.ExpertSolver(2, nk, od, kn, wm)
+    xk_h = xk_d.cpu().numpy()             # 153.6 MB pageable: prepare stages it through the rings too
+    s.prepare(xi_d.cpu().numpy(), xk_h)
+    fi_d = torch.zeros((n, no), dtype=torch.float64, device="cuda")
+    s.solve(fk_d, fi_d)
+    ref = fi_d.cpu().numpy()
+    fk_h = fk_d.cpu().numpy()
+    fi_big = np.full((n, no + 3), 5.0)    # pitched rows: columns beyond the model must survive
+    s.solve(fk_h, fi_big[:, :no])
+    assert np.array_equal(fi_big[:, :no], ref)
+    assert (fi_big[:, no:] == 5.0).all()
+    fk_p, fi_p = wlsqm.pinned_empty((n, k)), wlsqm.pinned_empty((n, no))
+    fk_p[...] = fk_h
+    fi_p[...] = 0.0
+    s.solve(fk_p, fi_p)
+    assert np.array_equal(fi_p, ref)
+    # the same prepared state from device arrays gives the same operators
+    s2 = wlsqm.ExpertSolver(2, nk, od, kn, wm)
+    s2.prepare(xi_d, xk_d)
+    fi2 = torch.zeros_like(fi_d)
+    s2.solve(fk_d, fi2)
+    assert torch.equal(fi2, fi_d)
