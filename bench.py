@@ -373,6 +373,20 @@ def run_b200(args, rank, world, local_rank):
     barrier()
     e2e_ms = e0.elapsed_time(e1)
     chk = float(np.abs(fi_h - fi_d.cpu().numpy()).max()) if (e2e_steps - 1) % 2 == (args.steps - 1) % NBUF % 2 else None
+    # the same call with ORDINARY (pageable) numpy arrays, what a reference user passes without thinking about it
+    page_ms = None
+    try:
+        fk_pg = [np.array(fk_h[t]) for t in range(2)]
+        fi_pg = np.zeros((n, NO))
+        s.solve(fk_pg[0], fi_pg)
+        barrier()
+        t0 = time.perf_counter()
+        for t in range(3):
+            s.solve(fk_pg[t % 2], fi_pg)
+        page_ms = 1e3 * (time.perf_counter() - t0) / 3
+        del fk_pg, fi_pg
+    except Exception as exc:
+        print("pageable leg failed: %r" % (exc,), file=sys.stderr)
 
     # ---- extension: the same step fed per point (solve_hoods): f (n,) in, fi out; the gather f[hoods] runs on the GPU ----
     hoods_ms = None
@@ -430,6 +444,10 @@ def run_b200(args, rank, world, local_rank):
                                      "kernel": "wlsqm::prepare_reg_kernel<2,4>"}},
             "clocks": clocks,
         }
+        if page_ms:
+            line["e2e_pageable_numpy"] = {"value": n / (page_ms * 1e-3), "unit": UNIT, "ms_per_step": page_ms,
+                                          "note": "rank 0, ordinary numpy arrays: host threads copy through page-locked rings "
+                                                  "(csrc/wlsqm_host.cu); cudaMemcpy from pageable memory gave 29 ms per step"}
         if oneshot:
             line["one_shot_fits"] = oneshot
         if hoods_ms:
