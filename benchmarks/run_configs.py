@@ -134,7 +134,8 @@ def main():
         run_expert("cfg2 variant 2D o4 k30 b2_F UNIFORM BASIC", int(1_000_000 * sc), 2, 4, 30, 1, 1, 1, False)
         run_expert("cfg2 2D o4 k30 knowns=0 CENTER ITERATIVE(3)", int(1_000_000 * sc), 2, 4, 30, 0, 2, 2, False)
     if want("cfg3"):
-        run_expert("cfg3 3D o4 k60 b3_F ITERATIVE(3) do_sens (2M of 4M points on one GPU)", int(2_000_000 * sc), 3, 4, 60,
+        n3 = int(2_000_000 * sc)     # --scale 2.0 = the full 4M-point configuration (140 GB: fits one B200)
+        run_expert("cfg3 3D o4 k60 b3_F ITERATIVE(3) do_sens (%.3gM of 4M points on one GPU)" % (n3 / 1e6), n3, 3, 4, 60,
                    1, 2, 2, True)
         torch.cuda.empty_cache()
         run_expert("cfg3-basic 3D o4 k60 b3_F BASIC no sens", int(2_000_000 * sc), 3, 4, 60, 1, 2, 1, False)
