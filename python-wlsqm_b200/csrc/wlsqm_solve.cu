@@ -66,8 +66,13 @@ __device__ __forceinline__ void warp_matvec_t(uint32_t op_s, uint32_t v_s, int n
         int cnt = (n - g + G - 1) / G;      // rows of this group
         for (; cnt >= 4; cnt -= 4) {
             const double x0 = lds_f64(pa), x1 = lds_f64(pa + sp), x2 = lds_f64(pa + sp2), x3 = lds_f64(pa + sp3);
-            const double y0 = lds_f64(va), y1 = lds_f64(va + G * 8), y2 = lds_f64(va + 2 * G * 8),
-                         y3 = lds_f64(va + 3 * G * 8);
+            double y0, y1, y2, y3;
+            if constexpr (G == 1) {       // one group: the four vector entries are consecutive -> two broadcast LDS.128
+                asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(y0), "=d"(y1) : "r"(va) : "memory");
+                asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(y2), "=d"(y3) : "r"(va + 16u) : "memory");
+            } else {
+                y0 = lds_f64(va); y1 = lds_f64(va + G * 8); y2 = lds_f64(va + 2 * G * 8); y3 = lds_f64(va + 3 * G * 8);
+            }
             a0 = fma(x0, y0, a0);
             a1 = fma(x1, y1, a1);
             a2 = fma(x2, y2, a2);
@@ -302,6 +307,7 @@ solve_kernel(SolveParams P) {
                 // the tails of TR = 32 / nt rows per store instead of one nearly empty store per row
                 double* sp = sn + lane;
                 const double* opp = op;
+#pragma unroll 4
                 for (int k = 0; k < nk; ++k) {
                     st_stream(sp, unk0 ? opp[j0] : qnan);
                     sp += P.sens_s1;
