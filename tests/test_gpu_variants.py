@@ -282,3 +282,60 @@ def test_sharded_solver_rows_equal_unsharded_bit_for_bit():
         parts_h.append(fi_h.cpu().numpy())
     assert np.array_equal(np.concatenate(parts), fi_full)
     assert np.array_equal(np.concatenate(parts_h), fi_full)
+
+
+_SWITCH_SCRIPT = r"""
+import sys, numpy as np
+sys.path[:0] = [%(root)r, %(root)r + "/python-wlsqm_b200", %(root)r + "/tests", %(root)r + "/oracle"]
+import wlsqm_b200 as wlsqm, parity
+from wlsqm_b200.utils import lapackdrivers as ld
+n, k = 1500, 24
+x, hoods, f = parity.make_case(n, 2, k)
+xk, fk = parity.gathered(x, f, hoods)
+m = (np.full(n, k, np.int32), np.full(n, 3, np.int32), np.full(n, 1, np.int64), np.full(n, 2, np.int32))
+fi = np.zeros((n, 10)); fi[:, 0] = f
+wlsqm.fit_2D_many_parallel(xk, fk, m[0], x, fi, None, 0, m[1], m[2], m[3])
+s = wlsqm.ExpertSolver(2, *m)
+s.prepare(x, xk)
+fe = np.zeros((n, 10)); fe[:, 0] = f
+s.solve(fk, fe)
+rng = np.random.default_rng(0)
+A = np.asfortranarray(rng.standard_normal((15, 15, 400))); b = np.asfortranarray(rng.standard_normal((15, 400)))
+ip = np.zeros((15, 400), np.int32, order="F")
+LU = A.copy(order="F"); ld.mgeneralfactor(LU, ip)
+xs = b.copy(order="F"); ld.mgeneralfactored(LU, ip, xs)
+np.savez(sys.argv[1], fit=fi, expert=fe, LU=LU, ipiv=ip, x=xs)
+"""
+
+
+def test_ab_switches_give_the_same_answers(tmp_path):
+    """the A/B switches of the library (memory pool off, one-shot fits through the general path, shared-memory LU,
+    no threaded staging) are run in subprocesses and compared with the default configuration"""
+    import os
+    import subprocess
+    import sys
+    from pathlib import Path
+    root = str(Path(__file__).resolve().parent.parent)
+    script = tmp_path / "switch.py"
+    script.write_text(_SWITCH_SCRIPT % {"root": root})
+
+    def run(env_extra, name):
+        env = dict(os.environ)
+        env.update(env_extra)
+        out = tmp_path / (name + ".npz")
+        subprocess.check_call([sys.executable, str(script), str(out)], env=env)
+        return np.load(out)
+    base = run({}, "base")
+    # fused one-shot kernel vs operator path: two orders of the same arithmetic, cond * eps apart
+    err = np.abs(base["fit"] - base["expert"]) / np.abs(base["expert"]).max(axis=0)
+    assert err.max() <= 1e-7 and np.median(err) <= 1e-12, (err.max(), np.median(err))
+    nopool = run({"WLSQM_POOL": "0", "WLSQM_BOUNCE": "0"}, "nopool")
+    for key in ("fit", "expert", "LU", "ipiv", "x"):
+        assert np.array_equal(base[key], nopool[key]), key
+    general = run({"WLSQM_FIT_DIRECT": "0"}, "general")
+    assert np.array_equal(general["fit"], general["expert"])          # general one-shot path == ExpertSolver, bit for bit
+    assert np.array_equal(general["expert"], base["expert"])
+    smem = run({"WLSQM_LU_SMEM": "1"}, "smem")
+    assert np.array_equal(smem["ipiv"], base["ipiv"])
+    assert np.allclose(smem["LU"], base["LU"], rtol=1e-10, atol=1e-12)
+    assert np.allclose(smem["x"], base["x"], rtol=1e-9, atol=1e-11)
