@@ -546,116 +546,86 @@ __global__ void __launch_bounds__(PREP_REG_THREADS, PK<DIM, ORD>::MINB) prepare_
         }
 
         // ================= whole warp: P5 operator columns (dgetrs per right-hand side) =================
-        // The FPW fits go through the substitution side by side (independent dependency chains).
-        int f_nr[FPW], f_nk[FPW], f_nq[FPW], f_no[FPW];
-        long long f_off[FPW];
-        int qblk = 0;
-#pragma unroll
+        // One fit after the other (a runtime loop: the unrolled substitution code exists once, not FPW times).
+#pragma unroll 1
         for (int f = 0; f < FPW; ++f) {
-            f_nr[f] = f_nk[f] = f_nq[f] = f_no[f] = 0;
-            f_off[f] = 0;
-            if (c0 + f < P.ncases) {
-                const CaseMeta mt = get_meta(c0 + f);
-                if (mt.nr > 0) {
-                    f_nr[f] = mt.nr; f_nk[f] = mt.nk; f_nq[f] = mt.nk + mt.nkn; f_no[f] = mt.no;
-                    f_off[f] = mt.op_off;
-                    qblk = max(qblk, (f_nq[f] + 31) >> 5);
+            if (c0 + f >= P.ncases) break;
+            const CaseMeta mt = get_meta(c0 + f);
+            if (mt.nr < 1) continue;
+            const int nrf = mt.nr, nkf = mt.nk, nqf = mt.nk + mt.nkn, nof = mt.no;
+            const double* fb = fits + f * P.fit_doubles;
+            const double* G = fb + oG;
+            const double* DI = fb + oDINV;
+            const double* RS = fb + oRS;
+            const double2* REC = reinterpret_cast<const double2*>(fb + oREC);
+            const int qblk = (nqf + 31) >> 5;
+            for (int b = 0; b < qblk; ++b) {
+                const int q = b * 32 + lane;
+                double y[NRP];
+                // y = P (row o (w_q c_q)): right-hand side row_j w_q c[q,oj] (impl.pyx:769-779), in pivot order.
+                // The lane recomputes its column of monomials into its own CT column and reads it back through
+                // the pivot-order row offsets (no other lane touches that column: no barrier needed).
+                double* ctq = CT + lane;
+                if (pending) {
+                    if (lane == 0) tma_store_wait_read();
+                    __syncwarp();
+                    pending = false;
                 }
-            }
-        }
-        for (int b = 0; b < qblk; ++b) {
-            const int q = b * 32 + lane;
-            double y[FPW][NRP];
-            // y = P (row o (w_q c_q)): right-hand side row_j w_q c[q,oj] (impl.pyx:769-779), in pivot order.
-            // The lane recomputes its column of monomials into its own CT column and reads it back through
-            // the pivot-order row offsets (no other lane touches that column: no barrier needed).
-            double* ctq = CT + lane;
+                monomial_column(c0 + f, q, nkf, nof, ctq);
+                if (q >= nkf && q < nqf) {
+                    const double* kn = fb + oKN + (q - nkf) * NOP;
+                    for (int s2 = 0; s2 < nof; ++s2) ctq[s2 * CB] = kn[s2];
+                }
+                const double wq = q < nqf ? fb[oW + q] : 0.0;
 #pragma unroll
-            for (int f = 0; f < FPW; ++f) {
-#pragma unroll
-                for (int i = 0; i < NRP; ++i) y[f][i] = 0.0;
-                if (b * 32 < f_nq[f]) {
-                    const double* fb = fits + f * P.fit_doubles;
-                    const double2* REC = reinterpret_cast<const double2*>(fb + oREC);
-                    if (pending) {
-                        if (lane == 0) tma_store_wait_read();
-                        __syncwarp();
-                        pending = false;
-                    }
-                    monomial_column(c0 + f, q, f_nk[f], f_no[f], ctq);
-                    if (q >= f_nk[f] && q < f_nq[f]) {
-                        const double* kn = fb + oKN + (q - f_nk[f]) * NOP;
-                        for (int s2 = 0; s2 < f_no[f]; ++s2) ctq[s2 * CB] = kn[s2];
-                    }
-                    const double wq = q < f_nq[f] ? fb[oW + q] : 0.0;
-#pragma unroll
-                    for (int i = 0; i < NRP; ++i) {
-                        if (i < f_nr[f]) {
-                            const double2 rec = REC[i];
-                            y[f][i] = rec.x * (wq * ctq[__double2loint(rec.y)]);
-                        }
+                for (int i = 0; i < NRP; ++i) {
+                    y[i] = 0.0;
+                    if (i < nrf) {
+                        const double2 rec = REC[i];
+                        y[i] = rec.x * (wq * ctq[__double2loint(rec.y)]);
                     }
                 }
-            }
-            // unit-lower forward substitution
+                // unit-lower forward substitution
 #pragma unroll
-            for (int i = 1; i < NRP; ++i) {
-#pragma unroll
-                for (int f = 0; f < FPW; ++f) {
-                    if (i < f_nr[f]) {
-                        const double* G = fits + f * P.fit_doubles + oG;
+                for (int i = 1; i < NRP; ++i) {
+                    if (i < nrf) {
 #pragma unroll
                         for (int p = 0; p < i; p += 2) {
                             const double2 l2 = ld2(G + i * LDA + p);
-                            y[f][i] = fma(-l2.x, y[f][p], y[f][i]);
-                            if (p + 1 < i) y[f][i] = fma(-l2.y, y[f][p + 1], y[f][i]);
+                            y[i] = fma(-l2.x, y[p], y[i]);
+                            if (p + 1 < i) y[i] = fma(-l2.y, y[p + 1], y[i]);
                         }
                     }
                 }
-            }
-            // upper backward substitution (padded columns hold zeros)
+                // upper backward substitution (padded columns hold zeros)
 #pragma unroll
-            for (int i = NRP - 1; i >= 0; --i) {
-#pragma unroll
-                for (int f = 0; f < FPW; ++f) {
-                    if (i < f_nr[f]) {
-                        const double* G = fits + f * P.fit_doubles + oG;
+                for (int i = NRP - 1; i >= 0; --i) {
+                    if (i < nrf) {
 #pragma unroll
                         for (int m = ((i + 1) & ~1); m < NRP; m += 2) {
                             const double2 u2 = ld2(G + i * LDA + m);
-                            if (m > i) y[f][i] = fma(-u2.x, y[f][m], y[f][i]);
-                            y[f][i] = fma(-u2.y, y[f][m + 1], y[f][i]);
+                            if (m > i) y[i] = fma(-u2.x, y[m], y[i]);
+                            y[i] = fma(-u2.y, y[m + 1], y[i]);
                         }
-                        y[f][i] *= fits[f * P.fit_doubles + oDINV + i];
+                        y[i] *= DI[i];
                     }
                 }
-            }
-            // Op[q][j] = x_j * col_j: 32 consecutive operator rows staged in CT, one bulk store per fit
+                // Op[q][j] = x_j * col_j: 32 consecutive operator rows staged in CT, one bulk store per block
+                const int rows = min(32, nqf - b * 32);
+                __syncwarp();    // gathers done
+                if (lane < rows) {
 #pragma unroll
-            for (int f = 0; f < FPW; ++f) {
-                const int nrf = f_nr[f];
-                const int rows = min(32, f_nq[f] - b * 32);
-                if (rows > 0) {
-                    if (pending) {
-                        if (lane == 0) tma_store_wait_read();
-                        pending = false;
-                    }
-                    __syncwarp();    // gathers done / previous store has finished reading
-                    const double* RS = fits + f * P.fit_doubles + oRS;
-                    if (lane < rows) {
-#pragma unroll
-                        for (int i = 0; i < NRP; ++i)
-                            if (i < nrf) CT[lane * nrf + i] = y[f][i] * RS[i];
-                    }
-                    if (lane == 0 && ((rows * nrf) & 1)) CT[rows * nrf] = 0.0;
-                    fence_proxy_async();
-                    __syncwarp();
-                    if (lane == 0) {
-                        tma_store_1d(P.op + f_off[f] + (long long)b * 32 * nrf, CT, (uint32_t)(((rows * nrf + 1) & ~1) * 8));
-                        tma_store_commit();
-                    }
-                    pending = true;
+                    for (int i = 0; i < NRP; ++i)
+                        if (i < nrf) CT[lane * nrf + i] = y[i] * RS[i];
                 }
+                if (lane == 0 && ((rows * nrf) & 1)) CT[rows * nrf] = 0.0;
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) {
+                    tma_store_1d(P.op + mt.op_off + (long long)b * 32 * nrf, CT, (uint32_t)(((rows * nrf + 1) & ~1) * 8));
+                    tma_store_commit();
+                }
+                pending = true;
             }
         }
     }
