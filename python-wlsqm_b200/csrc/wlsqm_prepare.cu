@@ -505,10 +505,10 @@ __global__ void __launch_bounds__(PREP_REG_THREADS, PK<DIM, ORD>::MINB) prepare_
                     const double2 u2 = ld2(gG + p * LDA + m);
 #pragma unroll
                     for (int t = 0; t < RPL; ++t) {
-                        if (act[t]) {
-                            if (m > p) a[t][m] = fma(-l[t], u2.x, a[t][m]);
-                            a[t][m + 1] = fma(-l[t], u2.y, a[t][m + 1]);
-                        }
+                        // unconditional: a row that has been the pivot lives in shared memory from then on, its
+                        // registers are never read again (no predicate / branch per update keeps the code small)
+                        if (m > p) a[t][m] = fma(-l[t], u2.x, a[t][m]);
+                        a[t][m + 1] = fma(-l[t], u2.y, a[t][m + 1]);
                     }
                 }
             }
