@@ -215,6 +215,7 @@ __global__ void __launch_bounds__(PREP_REG_THREADS, PK<DIM, ORD>::MINB) prepare_
 
             // ---- P1. monomials and squared distances (lane = neighbour) ----------------------------
             double max_d2 = 0.0;
+#pragma unroll 1
             for (int b = 0; b < nblk; ++b) {
                 const int k = b * 32 + lane;
                 const double d2 = monomial_column(c, k, nk, no, CT + b * BLK + lane);
@@ -224,7 +225,8 @@ __global__ void __launch_bounds__(PREP_REG_THREADS, PK<DIM, ORD>::MINB) prepare_
             // ---- weights (infra.pyx:679-702); columns >= nk carry weight 0 through the Gram phase ----
             if (mt.wm == WLSQM_WEIGHT_CENTER) {
                 max_d2 = warp_max(max_d2);
-                for (int b = 0; b < nblk; ++b) {
+    #pragma unroll 1
+            for (int b = 0; b < nblk; ++b) {
                     const int k = b * 32 + lane;
                     double w = 0.0;
                     if (k < nk) {
@@ -234,7 +236,8 @@ __global__ void __launch_bounds__(PREP_REG_THREADS, PK<DIM, ORD>::MINB) prepare_
                     W[k] = w;
                 }
             } else {
-                for (int b = 0; b < nblk; ++b) {
+    #pragma unroll 1
+            for (int b = 0; b < nblk; ++b) {
                     const int k = b * 32 + lane;
                     W[k] = k < nk ? 1.0 : 0.0;
                 }
