@@ -70,7 +70,7 @@ WLSQM_API void* wlsqm_pinned_alloc(int64_t bytes);
 WLSQM_API void wlsqm_pinned_free(void* p);
 
 /* Device memory of the library comes from one stream-ordered CUDA memory pool per device: what a destroyed solver or
- * a finished one-shot fit gives back stays cached (up to WLSQM_POOL_KEEP_MB, default 2048; WLSQM_POOL=0 disables the
+ * a finished one-shot fit gives back stays cached (up to WLSQM_POOL_KEEP_MB, default 8192; WLSQM_POOL=0 disables the
  * pool) so that the next call does not pay cudaMalloc / cudaFree -- the counterpart of the reference building its
  * per-call arena with one malloc (CaseManager_commit, wlsqm/fitter/infra.pyx:545-632).  stats: bytes reserved from
  * the driver / in use (-1 before the first allocation on that device); trim: return the cached blocks. */

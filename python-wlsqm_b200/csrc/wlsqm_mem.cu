@@ -15,6 +15,7 @@ struct DevPool {
     cudaMemPool_t pool = nullptr;
     cudaStream_t stream = nullptr;   // the allocations' own stream: alloc and free are ordered on it
     bool ok = false;
+    uint64_t keep = 0;              // free bytes the pool may hold on to
     std::atomic<bool> tried{false};
 };
 DevPool g_pools[MAX_DEVICES];
@@ -35,8 +36,12 @@ DevPool* pool_of(int device) {
         props.location.id = device;
         if (cudaMemPoolCreate(&d.pool, &props) == cudaSuccess &&
             cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking) == cudaSuccess) {
+            // The pool never gives memory back on its own (the built-in release threshold counts live blocks too: a
+            // solver holding 3.6 GB of operators would make every freed staging block go back to the driver at the
+            // next synchronisation).  dev_free() trims it instead, keeping up to WLSQM_POOL_KEEP_MB of FREE blocks.
             const char* keep = getenv("WLSQM_POOL_KEEP_MB");
-            uint64_t thr = (uint64_t)((keep && *keep) ? atoll(keep) : 2048) << 20;
+            d.keep = (uint64_t)((keep && *keep) ? atoll(keep) : 8192) << 20;
+            uint64_t thr = UINT64_MAX;
             cudaMemPoolSetAttribute(d.pool, cudaMemPoolAttrReleaseThreshold, &thr);
             d.ok = true;
         } else {
@@ -81,6 +86,18 @@ void dev_free(void* p) {
     if (!d || cudaFreeAsync(p, d->stream) != cudaSuccess) {
         cudaGetLastError();
         cudaFree(p);
+        cudaGetLastError();
+        return;
+    }
+    // keep at most d->keep bytes of free blocks cached
+    uint64_t reserved = 0, used = 0;
+    if (cudaMemPoolGetAttribute(d->pool, cudaMemPoolAttrReservedMemCurrent, &reserved) == cudaSuccess &&
+        cudaMemPoolGetAttribute(d->pool, cudaMemPoolAttrUsedMemCurrent, &used) == cudaSuccess) {
+        if (reserved > used && reserved - used > d->keep) {
+            cudaStreamSynchronize(d->stream);          // the frees queued so far are complete
+            cudaMemPoolTrimTo(d->pool, (size_t)(used + d->keep));
+        }
+    } else {
         cudaGetLastError();
     }
 }

@@ -4,8 +4,8 @@
 // reference allocates its whole per-solver arena with one malloc in CaseManager_commit (wlsqm/fitter/infra.pyx:
 // 545-632) and the one-shot drivers build and drop such an arena on every call (simple.pyx:731-1170); on a GPU a
 // cudaMalloc / cudaFree pair per call costs more than the fits themselves (10k fits: 0.1 ms of kernels, 0.8-20 ms
-// of allocation calls), so freed blocks are kept in the pool (up to WLSQM_POOL_KEEP_MB, default 2048) and the next
-// call reuses them.
+// of allocation calls), so freed blocks are kept in the pool (up to WLSQM_POOL_KEEP_MB of FREE memory, default 8192;
+// anything beyond that goes back to the driver when it is freed) and the next call reuses them.
 #pragma once
 #include <cstddef>
 #include <cuda_runtime.h>
