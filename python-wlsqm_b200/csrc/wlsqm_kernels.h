@@ -6,7 +6,7 @@
 namespace wlsqm {
 
 constexpr int PREP_MAX_THREADS = 512;        // shared-memory variant (wlsqm_prepare_smem.cu)
-constexpr int PREP_REG_THREADS = 256;        // register/DMMA variant (wlsqm_prepare.cu): launch bound; the host picks the CTA size
+constexpr int PREP_REG_THREADS = 512;        // register/DMMA variant (wlsqm_prepare.cu): launch bound; the host picks the CTA size
 constexpr int PREP_CB = 36;                  // row stride (doubles) inside a 32-column block of the monomial table
 constexpr int SOLVE_MAX_THREADS = 1024;       // ALGO_BASIC variants (<= 64 registers per thread)
 constexpr int SOLVE_MAX_THREADS_ITER = 512;   // ALGO_ITERATIVE variants carry the Taylor evaluator
@@ -42,6 +42,7 @@ struct PrepRegParams {
     // one-shot fit (no operator): data and in/out solution; fk == nullptr selects the operator-building kernel
     const double* fk; long long fk_s0, fk_s1;        // [ncases][nk]
     double* fi; long long fi_s0;                     // [ncases][>= no]: knowns read, unknowns written
+    int phase_sync;                                  // CTA barrier at every phase boundary (instruction-cache sharing)
 };
 
 struct SolveParams {

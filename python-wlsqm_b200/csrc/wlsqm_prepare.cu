@@ -47,7 +47,8 @@ struct PK {
     static constexpr int T = NOP / 8;
     static constexpr int LDA = NOP + 2;             // row stride of G / LU: LDS.128 by lane = row is conflict free
     static constexpr int BLK = NOP * PREP_CB;       // doubles per 32-column block of CT
-    static constexpr int MINB = RPL == 2 ? 1 : 2;   // CTAs of PREP_REG_THREADS per SM the register budget must allow
+    static constexpr int MAXT = RPL == 2 ? 256 : PREP_REG_THREADS;   // launch bound: 128 registers (RPL == 2: 255)
+    static constexpr int MINB = 1;
 };
 
 __host__ __device__ constexpr int prep_no(int dim, int ord) {
@@ -116,7 +117,7 @@ __device__ __forceinline__ unsigned group_min(unsigned v, int grp) {
 // b_s = sum_k w_k f_k c[k][s] row NO of the Gram matrix; b is eliminated along with the matrix in the LU phase
 // (one extra column) and back-substituted across the lanes, and fi is written directly.
 template <int DIM, int ORD, bool DIRECT>
-__global__ void __launch_bounds__(PREP_REG_THREADS, PK<DIM, ORD>::MINB) prepare_reg_kernel(PrepRegParams P) {
+__global__ void __launch_bounds__(PK<DIM, ORD>::MAXT, PK<DIM, ORD>::MINB) prepare_reg_kernel(PrepRegParams P) {
     using K = PK<DIM, ORD>;
     static_assert(!DIRECT || (K::RPL == 1 && K::NOP > K::NO), "the one-shot path needs one row per lane and a free padding slot");
     constexpr int NOP = K::NOP, NRP = K::NRP, RPL = K::RPL, T = K::T, LDA = K::LDA, CB = PREP_CB, BLK = K::BLK;
@@ -190,7 +191,21 @@ __global__ void __launch_bounds__(PREP_REG_THREADS, PK<DIM, ORD>::MINB) prepare_
     const long long WS = (long long)gridDim.x * nwarps * FPW;
     bool pending = false;    // a bulk store may still be reading CT
 
-    for (long long c0 = w0; c0 < P.ncases; c0 += WS) {
+    // Phase-synchronous mode (P.phase_sync): the warps of a CTA walk through the phases together (a CTA barrier at
+    // every phase boundary), so that they execute the same few KB of this kernel's ~75 KB of straight-line code at
+    // any time and share instruction-cache lines.  Every warp of the CTA runs the same number of iterations; a
+    // warp past the end of the batch recomputes the last fits (identical values are stored twice).
+    const long long cta_w0 = (long long)blockIdx.x * nwarps * FPW;
+    const long long n_it = cta_w0 < P.ncases ? (P.ncases - cta_w0 + WS - 1) / WS : 0;
+    const long long c_last = ((P.ncases - 1) / FPW) * FPW;
+    auto phase_barrier = [&]() { if (P.phase_sync == 1) __syncthreads(); };
+    for (long long it = 0; it < n_it; ++it) {
+        long long c0 = w0 + it * WS;
+        if (c0 >= P.ncases) {
+            if (!P.phase_sync) break;
+            c0 = c_last;
+        }
+        if (P.phase_sync) __syncthreads();      // (mode 2: once per iteration only)
         if (pending) {
             if (lane == 0) tma_store_wait_read();
             __syncwarp();
@@ -310,7 +325,8 @@ __global__ void __launch_bounds__(PREP_REG_THREADS, PK<DIM, ORD>::MINB) prepare_
             knowns = mg.knowns;
         }
         const int nrmax = FPW == 1 ? nr : (int)__reduce_max_sync(FULL, (unsigned)nr);
-        if (nrmax < 1) continue;
+        phase_barrier();
+        if (nrmax < 1) { phase_barrier(); phase_barrier(); continue; }
         double a[RPL][NRP];
         double rj[RPL];
         int roff[RPL];
@@ -426,6 +442,7 @@ __global__ void __launch_bounds__(PREP_REG_THREADS, PK<DIM, ORD>::MINB) prepare_
             }
         }
 
+        phase_barrier();
         // ---- P4. LU with partial pivoting; rows stay in their lanes ----------------------------------
         bool act[RPL];
         int pos[RPL];
@@ -518,6 +535,7 @@ __global__ void __launch_bounds__(PREP_REG_THREADS, PK<DIM, ORD>::MINB) prepare_
         }
         __syncwarp();
 
+        phase_barrier();
         if constexpr (DIRECT) {
             // ---- U x = y across the lanes: lane jl takes row jl of the pivot order (re-read from the published LU) ----
             double u[NRP];
