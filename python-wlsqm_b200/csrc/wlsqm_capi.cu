@@ -265,11 +265,11 @@ int config_solve(const wlsqm_solver* s, SolveParams& P, LaunchCfg& L, long long 
     // each) beat prefetch depth there (measured: 3D order 4 k=60 with sens, 16.7 -> 9.6 ms per 1M points).
     int S = env_int("WLSQM_SOLVE_STAGES", (iter && stage_bytes >= 8192) ? 1 : 2);
     S = std::max(1, std::min(S, 8));
-    // ALGO_ITERATIVE in 1D / 2D: 12-warp CTAs at 80 registers, two per SM (the refinement loop is latency-bound:
-    // 24 resident warps beat 16)
+    // ALGO_ITERATIVE in 1D / 2D: one 24-warp CTA per SM at 80 registers (the refinement loop is latency-bound: 24 resident
+    // warps beat 16, and one CTA whose warps start together beats two 12-warp CTAs: 1.59 -> 1.54 ms)
     const bool iter_small = iter && s->dim < 3;
     const int max_warps = (iter ? (iter_small ? SOLVE_ITER12_THREADS : SOLVE_MAX_THREADS_ITER) : SOLVE_MAX_THREADS) / 32;
-    int warps = env_int("WLSQM_SOLVE_WARPS", 16);
+    int warps = env_int("WLSQM_SOLVE_WARPS", iter_small ? 24 : 16);
     warps = std::max(1, std::min(warps, max_warps));
     size_t per_warp = 0;
     int off_fi, off_r, wd;

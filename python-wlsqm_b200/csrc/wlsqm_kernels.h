@@ -10,7 +10,7 @@ constexpr int PREP_REG_THREADS = 512;        // register/DMMA variant (wlsqm_pre
 constexpr int PREP_CB = 36;                  // row stride (doubles) inside a 32-column block of the monomial table
 constexpr int SOLVE_MAX_THREADS = 1024;       // ALGO_BASIC variants (<= 64 registers per thread)
 constexpr int SOLVE_MAX_THREADS_ITER = 512;   // ALGO_ITERATIVE variants carry the Taylor evaluator
-constexpr int SOLVE_ITER12_THREADS = 384;     // ... in 1D / 2D: two 12-warp CTAs per SM (80 registers)
+constexpr int SOLVE_ITER12_THREADS = 768;     // ... in 1D / 2D: one 24-warp CTA per SM (80 registers)
 
 // All strides are in elements (doubles), all offsets into per-warp shared memory in doubles.
 struct PrepareParams {

@@ -140,7 +140,7 @@ __device__ __forceinline__ double fetch_reduced(double lo, double hi, int j) {
 // UNI = the whole batch shares one CaseMeta (passed by value): everything derived from it is loop
 // invariant and hoisted by the compiler, which is what keeps the per-case instruction count low.
 template <int DIM, bool ITER, bool SENS, bool UNI>
-__global__ void __launch_bounds__(ITER ? (DIM == 3 ? SOLVE_MAX_THREADS_ITER : SOLVE_ITER12_THREADS) : SOLVE_MAX_THREADS, (ITER && DIM < 3) ? 2 : 1)
+__global__ void __launch_bounds__(ITER ? (DIM == 3 ? SOLVE_MAX_THREADS_ITER : SOLVE_ITER12_THREADS) : SOLVE_MAX_THREADS, 1)
 solve_kernel(SolveParams P) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31;
