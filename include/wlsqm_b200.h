@@ -65,6 +65,12 @@ WLSQM_API int wlsqm_device_count(void);                       /* CUDA devices vi
  * Returns -1 for a bad dimension, -2 for a bad order (no error state is set). */
 WLSQM_API int wlsqm_number_of_dofs(int dimension, int order);
 
+/* max nk, min / max order and "every case alike" of the per-case metadata arrays (host memory), in one pass: what the
+ * Python mirror needs for the shape checks of simple.pyx:149-159 / expert.pyx:131-159 without several array reductions */
+WLSQM_API int wlsqm_meta_summary(int64_t ncases, const int32_t* nk, const int32_t* order, const int64_t* knowns,
+                       const int32_t* weighting_method, int32_t* max_nk, int32_t* min_order, int32_t* max_order,
+                       int32_t* uniform);
+
 /* page-locked host buffers for the staged (host-pointer) path */
 WLSQM_API void* wlsqm_pinned_alloc(int64_t bytes);
 WLSQM_API void wlsqm_pinned_free(void* p);

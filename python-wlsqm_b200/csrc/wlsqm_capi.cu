@@ -442,6 +442,25 @@ void wlsqm_pinned_free(void* p) {
     if (p) cudaFreeHost(p);
 }
 
+// max nk, min / max order and whether every case has the same (nk, order, knowns, weighting), in one vectorised pass
+// (the Python mirror needs them for its shape checks; three numpy reductions over 1M cases cost ~1 ms per call)
+int wlsqm_meta_summary(int64_t ncases, const int32_t* nk, const int32_t* order, const int64_t* knowns, const int32_t* wm,
+                       int32_t* max_nk, int32_t* min_order, int32_t* max_order, int32_t* uniform) {
+    if (ncases < 0 || (ncases > 0 && (!nk || !order || !knowns || !wm))) return fail(WLSQM_E_VALUE, "NULL metadata array");
+    int32_t mk = 0, lo = 0, hi = 0;
+    if (ncases > 0) {
+        mk = nk[0]; lo = hi = order[0];
+        for (int64_t i = 1; i < ncases; ++i) mk = nk[i] > mk ? nk[i] : mk;
+        for (int64_t i = 1; i < ncases; ++i) { lo = order[i] < lo ? order[i] : lo; hi = order[i] > hi ? order[i] : hi; }
+    }
+    if (max_nk) *max_nk = mk;
+    if (min_order) *min_order = lo;
+    if (max_order) *max_order = hi;
+    if (uniform)
+        *uniform = (all_equal(nk, ncases) && all_equal(order, ncases) && all_equal(knowns, ncases) && all_equal(wm, ncases)) ? 1 : 0;
+    return WLSQM_OK;
+}
+
 int wlsqm_pool_stats(int device, int64_t* reserved, int64_t* used) {
     long long r = -1, u = -1;
     dev_pool_stats(device, &r, &u);

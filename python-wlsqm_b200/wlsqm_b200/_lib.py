@@ -33,6 +33,7 @@ SIGNATURES = {
     "wlsqm_last_error": (C.c_char_p, []),
     "wlsqm_device_count": (_int, []),
     "wlsqm_number_of_dofs": (_int, [_int, _int]),
+    "wlsqm_meta_summary": (_int, [_i64, _vp, _vp, _vp, _vp, _i32p, _i32p, _i32p, _i32p]),
     "wlsqm_pinned_alloc": (_vp, [_i64]),
     "wlsqm_pinned_free": (None, [_vp]),
     "wlsqm_pool_stats": (_int, [_int, _i64p, _i64p]),
@@ -222,6 +223,14 @@ def pinned_free(arr: np.ndarray):
     ent = _PINNED.pop(arr.ctypes.data, None)
     if ent is not None:
         lib().wlsqm_pinned_free(ent[1])
+
+
+def meta_summary(nk_a, order_a, knowns_a, wm_a):
+    """(max nk, min order, max order, uniform) of the metadata arrays in one C pass (``wlsqm_meta_summary``)"""
+    mk, lo, hi, un = C.c_int32(0), C.c_int32(0), C.c_int32(0), C.c_int32(0)
+    check(lib().wlsqm_meta_summary(nk_a.shape[0], nk_a.ctypes.data, order_a.ctypes.data, knowns_a.ctypes.data,
+                                   wm_a.ctypes.data, C.byref(mk), C.byref(lo), C.byref(hi), C.byref(un)))
+    return int(mk.value), int(lo.value), int(hi.value), bool(un.value)
 
 
 def pool_stats(device=None):

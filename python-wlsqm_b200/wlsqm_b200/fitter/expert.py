@@ -119,10 +119,10 @@ class ExpertSolver:
         if device is None:
             device = host.device if host is not None else _lib.default_device()
         self.device = int(device)
-        self._maxnk = int(nk_a.max()) if ncases else 0
-        self._maxno = number_of_dofs(dimension, int(order_a.max())) if ncases else 1
-        if ncases and (order_a.min() < 0 or order_a.max() > 4):
+        self._maxnk, min_order, max_order, _ = _lib.meta_summary(nk_a, order_a, knowns_a, wm_a)
+        if ncases and (min_order < 0 or max_order > 4):
             raise ValueError("order must be 0, 1, 2, 3 or 4")
+        self._maxno = number_of_dofs(dimension, max_order) if ncases else 1
 
         h = C.c_void_p()
         # guest mode: borrow the host's operators (one set of operators for several fields on one geometry);

@@ -59,10 +59,10 @@ def _fit_many(dim, xk, fk, nk, xi, fi, sens, do_sens, order, knowns, weighting_m
     if not fk_a.is_cuda and fk_a.shape[1] > 1 and fk_a.strides[1] != 1:
         fk_a = _lib.as_arr(np.ascontiguousarray(fk_a.np), np.float64, 2, "fk")
     fi_a = _lib.as_arr(fi, np.float64, 2, "fi", writable=True)
-    maxnk = int(nk_a.max()) if ncases else 0
-    if ncases and (order_a.min() < 0 or order_a.max() > 4):
+    maxnk, min_order, max_order, _ = _lib.meta_summary(nk_a, order_a, knowns_a, wm_a)
+    if ncases and (min_order < 0 or max_order > 4):
         raise ValueError("order must be 0, 1, 2, 3 or 4")
-    maxno = defs.NUMBER_OF_DOFS[dim][int(order_a.max())] if ncases else 1
+    maxno = defs.NUMBER_OF_DOFS[dim][max_order] if ncases else 1
     for nm, a in (("xk", xk_a), ("fk", fk_a), ("xi", xi_a), ("fi", fi_a)):
         if a.shape[0] < ncases:
             raise ValueError("%s must have at least ncases = %d rows" % (nm, ncases))
