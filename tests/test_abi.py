@@ -119,3 +119,21 @@ def test_as_arr_mirrors_memoryview_checks():
     with pytest.raises(ValueError, match="read-only"):
         _lib.as_arr(ro, np.float64, 2, "a", writable=True)
     assert _lib.as_arr(a[::2], np.float64, 2, "a").strides == (12, 1)      # pitched rows are fine
+
+
+def test_meta_summary_needs_no_device():
+    """wlsqm_meta_summary (host-only): max nk, order range and uniformity of the metadata arrays in one pass"""
+    from wlsqm_b200 import _lib
+    rng = np.random.default_rng(1)
+    n = 100_003
+    nk = rng.integers(5, 60, n).astype(np.int32)
+    od = rng.integers(0, 5, n).astype(np.int32)
+    kn = rng.integers(0, 4, n).astype(np.int64)
+    wm = rng.integers(1, 3, n).astype(np.int32)
+    assert _lib.meta_summary(nk, od, kn, wm) == (int(nk.max()), int(od.min()), int(od.max()), False)
+    u = (np.full(n, 30, np.int32), np.full(n, 4, np.int32), np.zeros(n, np.int64), np.full(n, 1, np.int32))
+    assert _lib.meta_summary(*u) == (30, 4, 4, True)
+    u[2][-1] = 1                      # one case differs in its knowns only
+    assert _lib.meta_summary(*u) == (30, 4, 4, False)
+    e = (np.zeros(0, np.int32), np.zeros(0, np.int32), np.zeros(0, np.int64), np.zeros(0, np.int32))
+    assert _lib.meta_summary(*e) == (0, 0, 0, True)
