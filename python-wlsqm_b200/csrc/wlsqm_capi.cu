@@ -1004,7 +1004,7 @@ int wlsqm_solver_interpolate(wlsqm_solver_t* s, const double* x, int64_t x_s0, c
     else {
         rc = s->st_x.reserve((size_t)nx * s->dim * 8);
         if (rc) return rc;
-        rc = to_dense((double*)s->st_x.p, x, nx, s->dim, x_s0, st);
+        rc = stage_in(s->device, (double*)s->st_x.p, x, nx, s->dim, x_s0, st);
         if (rc) return rc;
         P.x = (const double*)s->st_x.p; P.x_s0 = s->dim;
     }
@@ -1012,7 +1012,8 @@ int wlsqm_solver_interpolate(wlsqm_solver_t* s, const double* x, int64_t x_s0, c
     else {
         rc = s->st_I.reserve((size_t)nx * 8);
         if (rc) return rc;
-        CU(cudaMemcpyAsync(s->st_I.p, I, (size_t)nx * 8, cudaMemcpyHostToDevice, st));
+        rc = stage_in(s->device, (double*)s->st_I.p, reinterpret_cast<const double*>(I), nx, 1, 1, st);   // (8-byte items)
+        if (rc) return rc;
         P.I = (const long long*)s->st_I.p;
     }
     if (out_dev) { P.out = out; P.out_s0 = diff == WLSQM_DIFF_ALL ? out_s0 : 1; }
@@ -1025,8 +1026,8 @@ int wlsqm_solver_interpolate(wlsqm_solver_t* s, const double* x, int64_t x_s0, c
     P.stage_no = (diff == WLSQM_DIFF_ALL && s->uniform_no && P.out_s0 == s->uni.no) ? s->uni.no : 0;
     CU(launch_interpolate(P, st));
     if (!out_dev) {
-        if (diff == WLSQM_DIFF_ALL) rc = from_dense(out, out_s0, (const double*)s->st_out.p, ow, nx, ow, st);
-        else { CU(cudaMemcpyAsync(out, s->st_out.p, (size_t)nx * 8, cudaMemcpyDeviceToHost, st)); }
+        if (diff == WLSQM_DIFF_ALL) rc = stage_out(s->device, out, out_s0, (const double*)s->st_out.p, ow, nx, ow, st);
+        else rc = stage_out(s->device, out, 1, (const double*)s->st_out.p, 1, nx, 1, st);
         if (rc) return rc;
     }
     if (!x_dev || !I_dev || !out_dev) CU(cudaStreamSynchronize(st));
@@ -1201,7 +1202,7 @@ int wlsqm_solver_interpolate_continuous(wlsqm_solver_t* s, const double* x, int6
     else {
         rc = s->st_x.reserve((size_t)nx * s->dim * 8);
         if (rc) return rc;
-        rc = to_dense((double*)s->st_x.p, x, nx, s->dim, x_s0, st);
+        rc = stage_in(s->device, (double*)s->st_x.p, x, nx, s->dim, x_s0, st);
         if (rc) return rc;
         P.x = (const double*)s->st_x.p; P.x_s0 = s->dim;
     }

@@ -151,6 +151,15 @@ def test_large_pageable_arrays_take_the_threaded_staging_path():
     fi_p[...] = 0.0
     s.solve(fk_p, fi_p)
     assert np.array_equal(fi_p, ref)
+    # interpolate with large pageable query arrays (x 144 MB, I 72 MB, out 72 MB) == the device-tensor path
+    nq = 9_000_000
+    I_d = torch.randint(0, n, (nq,), device="cuda", generator=g)
+    xq_d = xi_d[I_d] + 0.004 * (2 * torch.rand((nq, 2), dtype=torch.float64, device="cuda", generator=g) - 1)
+    s.tree = object()
+    out_d, _ = s.interpolate(xq_d, diff=wlsqm.i2_XY, I=I_d)
+    out_h, I_back = s.interpolate(xq_d.cpu().numpy(), diff=wlsqm.i2_XY, I=I_d.cpu().numpy())
+    assert isinstance(out_h, np.ndarray) and np.array_equal(out_h, out_d.cpu().numpy())
+    del I_d, xq_d, out_d, out_h
     # the same prepared state from device arrays gives the same operators
     s2 = wlsqm.ExpertSolver(2, nk, od, kn, wm)
     s2.prepare(xi_d, xk_d)
