@@ -137,3 +137,27 @@ def test_meta_summary_needs_no_device():
     assert _lib.meta_summary(*u) == (30, 4, 4, False)
     e = (np.zeros(0, np.int32), np.zeros(0, np.int32), np.zeros(0, np.int64), np.zeros(0, np.int32))
     assert _lib.meta_summary(*e) == (0, 0, 0, True)
+
+
+def test_batched_driver_argument_checks_need_no_device():
+    """shape / dtype / layout validation of the batched drivers mirrors the memoryview signatures of
+    lapackdrivers.pyx (double[::1,:,:] etc.) and happens before any device work"""
+    from wlsqm_b200.utils import lapackdrivers as ld
+    A = np.zeros((4, 4, 3), order="F")
+    b = np.zeros((4, 3), order="F")
+    ip = np.zeros((4, 3), dtype=np.int32, order="F")
+    for fn, args in ((ld.mgeneralfactor, (np.zeros((4, 4, 3)), ip)),            # C order
+                     (ld.msymmetricfactor, (np.zeros((4, 4, 3)), ip)),
+                     (ld.msymmetricfactored, (A, ip.astype(np.int64), b)),     # wrong ipiv dtype
+                     (ld.mgeneral, (A.astype(np.float32), b)),                   # wrong data dtype
+                     (ld.msymmetrize, (np.zeros((4, 4)),))):                     # wrong rank
+        with pytest.raises(ValueError):
+            fn(*args)
+    for fn, args in ((ld.msymmetricfactor, (A, np.zeros((5, 3), dtype=np.int32, order="F"))),
+                     (ld.msymmetric, (A, np.zeros((4, 2), order="F"))),
+                     (ld.mgeneralfactored, (A, ip, np.zeros((3, 3), order="F"))),
+                     (ld.msymmetrize, (np.zeros((4, 5, 3), order="F"),))):
+        with pytest.raises(ValueError, match="shape mismatch"):
+            fn(*args)
+    assert set(ld.__all__) >= {"mgeneral", "mgeneralp", "msymmetric", "msymmetricp", "msymmetricfactor",
+                               "msymmetricfactored", "msymmetrize", "msymmetrizep"}
