@@ -269,7 +269,12 @@ int config_solve(const wlsqm_solver* s, SolveParams& P, LaunchCfg& L, long long 
     // warps beat 16, and one CTA whose warps start together beats two 12-warp CTAs: 1.59 -> 1.54 ms)
     const bool iter_small = iter && s->dim < 3;
     const int max_warps = (iter ? (iter_small ? SOLVE_ITER12_THREADS : SOLVE_MAX_THREADS_ITER) : SOLVE_MAX_THREADS) / 32;
-    int warps = env_int("WLSQM_SOLVE_WARPS", iter_small ? 24 : 16);
+    // Batches whose cases differ in size: the ring is sized for the largest block but the typical block is smaller, so the
+    // pass is bound by per-case issue overhead and bytes in flight like any small-block batch -- as many resident warps as
+    // shared memory holds (measured, 1M cases 2D orders 2-4 nk 22-30: 16 warps 0.770 ms, 24 warps 0.589 ms)
+    const size_t mean_block_bytes = s->ncases > 0 ? (size_t)(s->op_total * 8 / s->ncases) : stage_bytes;
+    const bool small_mean = !iter && !s->geom_uniform && mean_block_bytes < 3072;
+    int warps = env_int("WLSQM_SOLVE_WARPS", iter_small ? 24 : (small_mean ? 32 : 16));
     warps = std::max(1, std::min(warps, max_warps));
     size_t per_warp = 0;
     int off_fi, off_r, wd;
@@ -299,7 +304,7 @@ int config_solve(const wlsqm_solver* s, SolveParams& P, LaunchCfg& L, long long 
     L.threads = warps * 32;
     L.smem = (size_t)P.bar_off_bytes + (size_t)warps * S * 8;
     int ctas = (int)(SMEM_PER_SM / (L.smem + 1024));
-    ctas = std::max(1, std::min(ctas, std::max(1, env_int("WLSQM_SOLVE_MAXWARPS_SM", iter_small ? 24 : (stage_bytes >= 3072 ? 16 : 32)) / warps)));
+    ctas = std::max(1, std::min(ctas, std::max(1, env_int("WLSQM_SOLVE_MAXWARPS_SM", iter_small ? 24 : ((stage_bytes >= 3072 && !small_mean) ? 16 : 32)) / warps)));
     long long need = (ncases_launch + warps - 1) / warps;
     L.blocks = (int)std::max<long long>(1, std::min<long long>((long long)s->sm_count * ctas, need));
     return WLSQM_OK;
