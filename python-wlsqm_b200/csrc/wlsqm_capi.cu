@@ -263,7 +263,12 @@ int config_solve(const wlsqm_solver* s, SolveParams& P, LaunchCfg& L, long long 
     // per-case issue overhead instead and want two such CTAs per SM.
     // ALGO_ITERATIVE keeps a warp busy on one block for thousands of cycles: more resident warps (one stage
     // each) beat prefetch depth there (measured: 3D order 4 k=60 with sens, 16.7 -> 9.6 ms per 1M points).
-    int S = env_int("WLSQM_SOLVE_STAGES", (iter && stage_bytes >= 8192) ? 1 : 2);
+    // Batches whose cases differ in size (ALGO_BASIC): when two stages of the LARGEST block leave room for fewer than
+    // 16 warps, one stage and twice the warps win -- the typical block is smaller than the stage, so resident warps put
+    // more bytes in flight than a prefetch slot sized for the worst case (measured, 400k cases 3D orders 2-4 nk 40-60:
+    // 2 stages x 6 warps 1.21 ms, 1 stage x 12 warps 0.73 ms = 0.78 of the HBM peak)
+    const bool hetero_shallow = !iter && !s->geom_uniform && 16 * (2 * stage_bytes + 512) > SMEM_PER_CTA;
+    int S = env_int("WLSQM_SOLVE_STAGES", ((iter && stage_bytes >= 8192) || hetero_shallow) ? 1 : 2);
     S = std::max(1, std::min(S, 8));
     // ALGO_ITERATIVE in 1D / 2D: one 24-warp CTA per SM at 80 registers (the refinement loop is latency-bound: 24 resident
     // warps beat 16, and one CTA whose warps start together beats two 12-warp CTAs: 1.59 -> 1.54 ms)
@@ -273,7 +278,7 @@ int config_solve(const wlsqm_solver* s, SolveParams& P, LaunchCfg& L, long long 
     // pass is bound by per-case issue overhead and bytes in flight like any small-block batch -- as many resident warps as
     // shared memory holds (measured, 1M cases 2D orders 2-4 nk 22-30: 16 warps 0.770 ms, 24 warps 0.589 ms)
     const size_t mean_block_bytes = s->ncases > 0 ? (size_t)(s->op_total * 8 / s->ncases) : stage_bytes;
-    const bool small_mean = !iter && !s->geom_uniform && mean_block_bytes < 3072;
+    const bool small_mean = !iter && !s->geom_uniform && (mean_block_bytes < 3072 || hetero_shallow);
     int warps = env_int("WLSQM_SOLVE_WARPS", iter_small ? 24 : (small_mean ? 32 : 16));
     warps = std::max(1, std::min(warps, max_warps));
     size_t per_warp = 0;
