@@ -3,6 +3,7 @@
 // wlsqm_interp.cu / wlsqm_lapack.cu.  There is deliberately no CPU code path: every compute entry
 // point needs a CUDA device and fails with WLSQM_E_CUDA otherwise.
 #include <algorithm>
+#include <atomic>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -57,19 +58,61 @@ constexpr size_t SMEM_PER_CTA = 227 * 1024;
 
 inline int even(int v) { return (v + 1) & ~1; }
 
-// every element equal to the first (branch-free so that the host compiler vectorises it: ~0.1 ms per million)
-template <typename T>
-bool all_equal(const T* a, long long n) {
-    if (n < 2) return true;
-    const T v = a[0];
-    T acc = 0;
-    for (long long i = 1; i < n; ++i) acc |= (T)(a[i] ^ v);
-    return acc == 0;
-}
-
 int env_int(const char* name, int dflt) {
     const char* v = getenv(name);
     return (v && *v) ? atoi(v) : dflt;
+}
+
+// One look at the four metadata arrays of a batch (20 bytes per case): which of them hold one value throughout, and --
+// only for those that do not -- the reductions the callers need.  The pass is bound by host memory bandwidth (about
+// 1 ms per million cases on one thread), so large batches are split over the library's host threads.
+struct MetaScan {
+    bool same_nk = true, same_order = true, same_knowns = true, same_wm = true;
+    int32_t max_nk = 0, min_order = 0, max_order = 0;
+    bool uniform() const { return same_nk && same_order && same_knowns && same_wm; }
+};
+MetaScan scan_meta(long long n, const int32_t* nk, const int32_t* order, const int64_t* knowns, const int32_t* wm) {
+    MetaScan r;
+    if (n < 1) return r;
+    r.max_nk = nk[0]; r.min_order = r.max_order = order[0];
+    if (n < 2) return r;
+    const int32_t nk0 = nk[0], od0 = order[0], wm0 = wm[0];
+    const int64_t kn0 = knowns[0];
+    std::atomic<uint32_t> d_nk{0}, d_od{0}, d_wm{0};
+    std::atomic<uint64_t> d_kn{0};
+    auto piece = [&](size_t lo, size_t hi) {
+        uint32_t a = 0, b = 0, c = 0;
+        uint64_t d = 0;
+        for (size_t i = lo; i < hi; ++i) a |= (uint32_t)(nk[i] ^ nk0);
+        for (size_t i = lo; i < hi; ++i) b |= (uint32_t)(order[i] ^ od0);
+        for (size_t i = lo; i < hi; ++i) c |= (uint32_t)(wm[i] ^ wm0);
+        for (size_t i = lo; i < hi; ++i) d |= (uint64_t)(knowns[i] ^ kn0);
+        if (a) d_nk.fetch_or(a, std::memory_order_relaxed);
+        if (b) d_od.fetch_or(b, std::memory_order_relaxed);
+        if (c) d_wm.fetch_or(c, std::memory_order_relaxed);
+        if (d) d_kn.fetch_or(d, std::memory_order_relaxed);
+    };
+    const bool par = n >= 262144 && env_int("WLSQM_META_THREADS", 1) != 0;
+    if (par) par_for((size_t)n, piece);
+    else piece(0, (size_t)n);
+    r.same_nk = d_nk.load() == 0; r.same_order = d_od.load() == 0; r.same_wm = d_wm.load() == 0; r.same_knowns = d_kn.load() == 0;
+    if (!r.same_nk || !r.same_order) {
+        std::atomic<int32_t> mk{nk0}, lo_o{od0}, hi_o{od0};
+        auto atomic_max = [](std::atomic<int32_t>& t, int32_t v) { int32_t c = t.load(); while (v > c && !t.compare_exchange_weak(c, v)) {} };
+        auto atomic_min = [](std::atomic<int32_t>& t, int32_t v) { int32_t c = t.load(); while (v < c && !t.compare_exchange_weak(c, v)) {} };
+        auto red = [&](size_t lo, size_t hi) {
+            int32_t m = nk0, l = od0, h = od0;
+            if (!r.same_nk)
+                for (size_t i = lo; i < hi; ++i) m = nk[i] > m ? nk[i] : m;
+            if (!r.same_order)
+                for (size_t i = lo; i < hi; ++i) { l = order[i] < l ? order[i] : l; h = order[i] > h ? order[i] : h; }
+            atomic_max(mk, m); atomic_min(lo_o, l); atomic_max(hi_o, h);
+        };
+        if (par) par_for((size_t)n, red);
+        else red(0, (size_t)n);
+        r.max_nk = mk.load(); r.min_order = lo_o.load(); r.max_order = hi_o.load();
+    }
+    return r;
 }
 
 // 1 = device-accessible (device or managed), 0 = host (pinned or pageable)
@@ -457,17 +500,11 @@ void wlsqm_pinned_free(void* p) {
 int wlsqm_meta_summary(int64_t ncases, const int32_t* nk, const int32_t* order, const int64_t* knowns, const int32_t* wm,
                        int32_t* max_nk, int32_t* min_order, int32_t* max_order, int32_t* uniform) {
     if (ncases < 0 || (ncases > 0 && (!nk || !order || !knowns || !wm))) return fail(WLSQM_E_VALUE, "NULL metadata array");
-    int32_t mk = 0, lo = 0, hi = 0;
-    if (ncases > 0) {
-        mk = nk[0]; lo = hi = order[0];
-        for (int64_t i = 1; i < ncases; ++i) mk = nk[i] > mk ? nk[i] : mk;
-        for (int64_t i = 1; i < ncases; ++i) { lo = order[i] < lo ? order[i] : lo; hi = order[i] > hi ? order[i] : hi; }
-    }
-    if (max_nk) *max_nk = mk;
-    if (min_order) *min_order = lo;
-    if (max_order) *max_order = hi;
-    if (uniform)
-        *uniform = (all_equal(nk, ncases) && all_equal(order, ncases) && all_equal(knowns, ncases) && all_equal(wm, ncases)) ? 1 : 0;
+    const MetaScan m = scan_meta(ncases, nk, order, knowns, wm);
+    if (max_nk) *max_nk = m.max_nk;
+    if (min_order) *min_order = m.min_order;
+    if (max_order) *max_order = m.max_order;
+    if (uniform) *uniform = m.uniform() ? 1 : 0;
     return WLSQM_OK;
 }
 
@@ -505,7 +542,7 @@ int wlsqm_solver_create(int dimension, int64_t ncases, const int32_t* nk, const 
     s->max_iter = max_iter; s->debug = debug ? 1 : 0; s->ncases = ncases;
     // Uniform batches (every case with the same nk / order / knowns / weighting -- the usual ExpertSolver and
     // fit_*_many call) are recognised by one pass of comparisons and keep no per-case records at all.
-    const bool all_same = all_equal(nk, ncases) && all_equal(order, ncases) && all_equal(knowns, ncases) && all_equal(wm, ncases);
+    const bool all_same = scan_meta(ncases, nk, order, knowns, wm).uniform();
     const long long nrec = all_same ? std::min<long long>(ncases, 1) : ncases;
     try {
         s->hmeta.resize((size_t)nrec);
@@ -1238,7 +1275,7 @@ static int fit_many_direct(int dimension, int64_t ncases, const double* xk, int6
                            int* rc_out) {
     if (env_int("WLSQM_FIT_DIRECT", 1) == 0) return 0;
     if (ncases < 1 || dimension < 1 || dimension > 3 || !nk || !order || !knowns || !wm || !xk || !fk || !xi || !fi) return 0;
-    if (!(all_equal(nk, ncases) && all_equal(order, ncases) && all_equal(knowns, ncases) && all_equal(wm, ncases))) return 0;
+    if (!scan_meta(ncases, nk, order, knowns, wm).uniform()) return 0;
     const int no = number_of_dofs(dimension, order[0]);
     if (no < 0 || nk[0] < 0 || (wm[0] != WLSQM_WEIGHT_UNIFORM && wm[0] != WLSQM_WEIGHT_CENTER)) return 0;   // general path reports it
     if (!prepare_reg_direct_ok(dimension, order[0])) return 0;

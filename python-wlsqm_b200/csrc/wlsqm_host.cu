@@ -99,6 +99,8 @@ private:
 
 }  // namespace
 
+void par_for(size_t n, const std::function<void(size_t, size_t)>& fn) { HostPool::get().parallel_for(n, fn); }
+
 void par_copy_rows(void* dst, size_t dst_pitch, const void* src, size_t src_pitch, size_t row_bytes, size_t rows) {
     if (rows == 0 || row_bytes == 0) return;
     char* d = (char*)dst;

@@ -6,12 +6,17 @@
 // a ring of page-locked slots and go to the device with asynchronous copies, and results come back the same way.
 #pragma once
 #include <cstddef>
+#include <functional>
 #include <cuda_runtime.h>
 
 namespace wlsqm {
 
 // 1 = ordinary pageable host memory (neither device memory nor page-locked / registered)
 bool is_pageable_host(const void* p);
+
+// fn(lo, hi) over contiguous pieces of [0, n) on the library's host threads (the caller's thread takes one piece);
+// pieces run concurrently: fn must only touch its own range or synchronise
+void par_for(size_t n, const std::function<void(size_t, size_t)>& fn);
 
 // dst[r][0..row_bytes) = src[r][0..row_bytes) for r < rows (pitches in bytes), split over the library's host threads
 void par_copy_rows(void* dst, size_t dst_pitch, const void* src, size_t src_pitch, size_t row_bytes, size_t rows);

@@ -137,6 +137,14 @@ def test_meta_summary_needs_no_device():
     assert _lib.meta_summary(*u) == (30, 4, 4, False)
     e = (np.zeros(0, np.int32), np.zeros(0, np.int32), np.zeros(0, np.int64), np.zeros(0, np.int32))
     assert _lib.meta_summary(*e) == (0, 0, 0, True)
+    # batches of 262144 cases and more are scanned in pieces on the library's host threads
+    for m in (1, 2, 262143, 262144, 600_001):
+        a, b = rng.integers(5, 31, m).astype(np.int32), rng.integers(0, 5, m).astype(np.int32)
+        same = bool((a == a[0]).all() and (b == b[0]).all())
+        assert _lib.meta_summary(a, b, np.zeros(m, np.int64), np.ones(m, np.int32)) == (int(a.max()), int(b.min()), int(b.max()), same)
+        w = np.ones(m, np.int32)
+        w[m // 2] = 1 if m == 1 else 2          # a single case in the middle differs in its weighting only
+        assert _lib.meta_summary(np.full(m, 7, np.int32), np.full(m, 2, np.int32), np.zeros(m, np.int64), w) == (7, 2, 2, m == 1)
 
 
 def test_batched_driver_argument_checks_need_no_device():
