@@ -210,6 +210,10 @@ struct wlsqm_solver {
     wlsqm_grid* models_grid = nullptr;           // search grid over the model origins (index_models)
     wlsqm_solver* lender = nullptr;              // guest mode: op / dmeta / dorder / xi_dev / As / xk_keep belong to this solver
     long long bytes_state = 0;
+    // batches of mixed orders: case lists per order (device, ascending case index inside an order), so that prepare()
+    // runs one kernel instantiation per order instead of the maximum order's for every case
+    int* order_perm = nullptr;
+    long long order_lo[6] = {0, 0, 0, 0, 0, 0};
 };
 
 namespace {
@@ -254,13 +258,17 @@ int config_prepare(const wlsqm_solver* s, PrepareParams& P, LaunchCfg& L) {
 }
 
 // register/DMMA kernel: false if the fit does not fit its shared-memory carve-up (then the smem kernel runs)
-bool config_prepare_reg(const wlsqm_solver* s, PrepRegParams& P, LaunchCfg& L, bool direct = false) {
+// (order_sel / count: the launch covers `count` cases of order `order_sel` only -- batches of mixed orders)
+bool config_prepare_reg(const wlsqm_solver* s, PrepRegParams& P, LaunchCfg& L, bool direct = false, int order_sel = -1,
+                        long long count = -1) {
+    const int kord = order_sel >= 0 ? order_sel : s->maxorder;
+    const long long ncases = count >= 0 ? count : s->ncases;
     const int nkp = (std::max(s->maxnk, 1) + 3) & ~3;
     P.nb = (std::max(nkp, s->maxnq) + 31) / 32;
     const int nkn_max = s->maxnq > 0 ? s->maxnkn : 0;
-    P.fit_doubles = prep_reg_fit_doubles(s->dim, s->maxorder, P.nb, nkn_max);
-    P.warp_doubles = prep_reg_warp_doubles(s->dim, s->maxorder, P.nb, nkn_max);
-    const int fpw = prep_reg_fits_per_warp(s->dim, s->maxorder);
+    P.fit_doubles = prep_reg_fit_doubles(s->dim, kord, P.nb, nkn_max);
+    P.warp_doubles = prep_reg_warp_doubles(s->dim, kord, P.nb, nkn_max);
+    const int fpw = prep_reg_fits_per_warp(s->dim, kord);
     const size_t per_warp = (size_t)P.warp_doubles * 8;
     if (per_warp > SMEM_PER_CTA) return false;
     // CTA size: the one that keeps most warps resident (shared memory and registers both limit it)
@@ -270,7 +278,7 @@ bool config_prepare_reg(const wlsqm_solver* s, PrepRegParams& P, LaunchCfg& L, b
         if (force_w > 0 && w != force_w) continue;
         if (w * per_warp > SMEM_PER_CTA) break;
         int c = 0;
-        if (prepare_reg_occupancy(s->dim, s->maxorder, w * 32, w * per_warp, &c, direct) != cudaSuccess) {
+        if (prepare_reg_occupancy(s->dim, kord, w * 32, w * per_warp, &c, direct) != cudaSuccess) {
             cudaGetLastError();
             continue;
         }
@@ -287,7 +295,7 @@ bool config_prepare_reg(const wlsqm_solver* s, PrepRegParams& P, LaunchCfg& L, b
     P.phase_sync = env_int("WLSQM_PREP_PHASE_SYNC", 0);
     const int cap = env_int("WLSQM_PREP_CTAS", 0);
     if (cap > 0) ctas = std::min(ctas, cap);
-    long long need = (s->ncases + (long long)warps * fpw - 1) / ((long long)warps * fpw);
+    long long need = (ncases + (long long)warps * fpw - 1) / ((long long)warps * fpw);
     L.blocks = (int)std::max<long long>(1, std::min<long long>((long long)s->sm_count * ctas, need));
     return true;
 }
@@ -622,7 +630,19 @@ int wlsqm_solver_create(int dimension, int64_t ncases, const int32_t* nk, const 
         rc = alloc((void**)&s->As, (size_t)ncases * s->as_stride * 8);
     }
     if (!rc && algorithm == WLSQM_ALGO_ITERATIVE) rc = alloc((void**)&s->iters_dev, ((size_t)ncases + 1) * 4);
+    std::vector<int> perm;
+    if (!rc && !s->uniform_no && ncases >= env_int("WLSQM_PREP_BUCKET_MIN", 8192) && ncases < (1LL << 31)) {
+        long long cnt[5] = {0, 0, 0, 0, 0};
+        for (long long i = 0; i < ncases; ++i) ++cnt[s->hmeta[(size_t)i].order];
+        for (int o = 0; o < 5; ++o) s->order_lo[o + 1] = s->order_lo[o] + cnt[o];
+        long long at[5];
+        for (int o = 0; o < 5; ++o) at[o] = s->order_lo[o];
+        perm.resize((size_t)ncases);
+        for (long long i = 0; i < ncases; ++i) perm[(size_t)at[s->hmeta[(size_t)i].order]++] = (int)i;
+        rc = alloc((void**)&s->order_perm, (size_t)ncases * 4);
+    }
     if (rc) { wlsqm_solver_destroy(s); return rc; }
+    if (s->order_perm) cudaMemcpyAsync(s->order_perm, perm.data(), (size_t)ncases * 4, cudaMemcpyHostToDevice, s->stream);
     if (s->dmeta)
         cudaMemcpyAsync(s->dmeta, s->hmeta.data(), sizeof(CaseMeta) * (size_t)ncases, cudaMemcpyHostToDevice, s->stream);
     if (s->dorder) {
@@ -649,7 +669,7 @@ int wlsqm_solver_destroy(wlsqm_solver_t* s) {
     if (s->s_in) cudaStreamSynchronize(s->s_in);
     if (s->s_out) cudaStreamSynchronize(s->s_out);
     if (!s->lender) {
-        dev_free(s->dmeta); dev_free(s->dorder); dev_free(s->op); dev_free(s->xi_dev); dev_free(s->As);
+        dev_free(s->dmeta); dev_free(s->dorder); dev_free(s->op); dev_free(s->xi_dev); dev_free(s->As); dev_free(s->order_perm);
         s->xk_keep.release();
     } else {
         s->xk_keep.p = nullptr; s->xk_keep.cap = 0;
@@ -805,7 +825,22 @@ int wlsqm_solver_prepare(wlsqm_solver_t* s, const double* xi, int64_t xi_s0, con
     const char* ksel = getenv("WLSQM_PREP_KERNEL");
     const bool want_smem = ksel && !strcmp(ksel, "smem");
     if (!want_smem && config_prepare_reg(s, R, L)) {
-        CU(launch_prepare_reg(dim, s->maxorder, R, L.blocks, L.threads, L.smem, s->stream));
+        if (s->order_perm && env_int("WLSQM_PREP_BUCKETS", 1) != 0) {
+            // mixed orders: one launch per order over its case list, each with the kernel instantiated for that order
+            // (an order-2 fit in the order-4 kernel pays for 16-wide rows; measured in profiles/README.md)
+            for (int o = 0; o < 5; ++o) {
+                const long long cnt = s->order_lo[o + 1] - s->order_lo[o];
+                if (cnt < 1) continue;
+                PrepRegParams Ro = R;
+                LaunchCfg Lo;
+                Ro.perm = s->order_perm + s->order_lo[o];
+                Ro.ncases = cnt;
+                if (!config_prepare_reg(s, Ro, Lo, false, o, cnt)) return fail(WLSQM_E_VALUE, "prepare: no launch shape for order %d", o);
+                CU(launch_prepare_reg(dim, o, Ro, Lo.blocks, Lo.threads, Lo.smem, s->stream));
+            }
+        } else {
+            CU(launch_prepare_reg(dim, s->maxorder, R, L.blocks, L.threads, L.smem, s->stream));
+        }
     } else {
         PrepareParams P{};
         P.meta = s->dmeta; P.uni = s->uni; P.op_stride = s->op_stride; P.ncases = n;

@@ -43,6 +43,7 @@ struct PrepRegParams {
     const double* fk; long long fk_s0, fk_s1;        // [ncases][nk]
     double* fi; long long fi_s0;                     // [ncases][>= no]: knowns read, unknowns written
     int phase_sync;                                  // CTA barrier at every phase boundary (instruction-cache sharing)
+    const int* perm;                                 // launch over a case list: entry v of [0, ncases) is case perm[v] (nullptr: v)
 };
 
 struct SolveParams {

@@ -147,6 +147,8 @@ __global__ void __launch_bounds__(PK<DIM, ORD>::MAXT, PK<DIM, ORD>::MINB) prepar
     double2* gREC = reinterpret_cast<double2*>(gb + oREC);
     const int* gR2O = reinterpret_cast<const int*>(gb + oR2O);
 
+    // launches over a case list (batches of mixed orders run one instantiation per order): entry -> case
+    auto case_of = [&](long long v) -> long long { return P.perm ? (long long)P.perm[v] : v; };
     auto get_meta = [&](long long c) {
         CaseMeta m;
         if (P.meta && !P.geom_uniform) {
@@ -215,8 +217,8 @@ __global__ void __launch_bounds__(PK<DIM, ORD>::MAXT, PK<DIM, ORD>::MINB) prepar
         // ================= per fit, whole warp: P1 monomials + weights, P2 Gram matrix =================
 #pragma unroll 1
         for (int f = 0; f < FPW; ++f) {
-            const long long c = c0 + f;
-            if (c >= P.ncases) break;
+            if (c0 + f >= P.ncases) break;
+            const long long c = case_of(c0 + f);
             const CaseMeta mt = get_meta(c);
             const int nk = mt.nk, no = mt.no, nr = mt.nr, nkn = mt.nkn, nq = nk + nkn;
             const long long knowns = mt.knowns;
@@ -316,10 +318,11 @@ __global__ void __launch_bounds__(PK<DIM, ORD>::MAXT, PK<DIM, ORD>::MINB) prepar
 
         // ================= row phases: LPF lanes per fit, FPW fits side by side ========================
         // ---- P3. reduced matrix rows -> registers; Ruiz equilibration ------------------------------
-        const long long cg = c0 + grp;
+        long long cg = c0 + grp;
         int nr = 0;
         long long knowns = 0;
         if (cg < P.ncases) {
+            cg = case_of(cg);
             const CaseMeta mg = get_meta(cg);
             nr = mg.nr;
             knowns = mg.knowns;
@@ -571,7 +574,8 @@ __global__ void __launch_bounds__(PK<DIM, ORD>::MAXT, PK<DIM, ORD>::MINB) prepar
 #pragma unroll 1
         for (int f = 0; f < FPW; ++f) {
             if (c0 + f >= P.ncases) break;
-            const CaseMeta mt = get_meta(c0 + f);
+            const long long cf = case_of(c0 + f);
+            const CaseMeta mt = get_meta(cf);
             if (mt.nr < 1) continue;
             const int nrf = mt.nr, nkf = mt.nk, nqf = mt.nk + mt.nkn, nof = mt.no;
             const double* fb = fits + f * P.fit_doubles;
@@ -592,7 +596,7 @@ __global__ void __launch_bounds__(PK<DIM, ORD>::MAXT, PK<DIM, ORD>::MINB) prepar
                     __syncwarp();
                     pending = false;
                 }
-                monomial_column(c0 + f, q, nkf, nof, ctq);
+                monomial_column(cf, q, nkf, nof, ctq);
                 if (q >= nkf && q < nqf) {
                     const double* kn = fb + oKN + (q - nkf) * NOP;
                     for (int s2 = 0; s2 < nof; ++s2) ctq[s2 * CB] = kn[s2];

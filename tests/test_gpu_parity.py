@@ -78,31 +78,36 @@ def test_differential_vs_oracle(dim, order, k, knowns, wm, algo, n, do_sens):
         assert np.median(err) < 1e-12
 
 
-def test_heterogeneous_batch():
-    """per-case nk / order / knowns / weighting in one batch (expert.pyx:92-104)"""
-    n, dim, kmax = 3000, 2, 30
+@pytest.mark.parametrize("dim,bucketed", [(2, False), (2, True), (3, True)])
+def test_heterogeneous_batch(dim, bucketed, monkeypatch):
+    """per-case nk / order / knowns / weighting in one batch (expert.pyx:92-104); `bucketed`: prepare() runs one launch
+    per order over that order's case list (the default from 8192 cases on) instead of the maximum order's kernel for all"""
+    monkeypatch.setenv("WLSQM_PREP_BUCKET_MIN", "1000" if bucketed else "1000000000")
+    n, kmax = 3000, (30 if dim == 2 else 60)
+    nomax = wlsqm.number_of_dofs(dim, 4)
+    b_xy = wlsqm.b2_XY if dim == 2 else wlsqm.b3_XY
     x, hoods, f = parity.make_case(n, dim, kmax)
     rng = np.random.default_rng(3)
     od = rng.integers(0, 5, n).astype(np.int32)
-    nk = np.array([rng.integers(min(kmax, (3 * wlsqm.number_of_dofs(2, int(o))) // 2 + 2), kmax + 1) for o in od], np.int32)
+    nk = np.array([rng.integers(min(kmax, (3 * wlsqm.number_of_dofs(dim, int(o))) // 2 + 2), kmax + 1) for o in od], np.int32)
     kn = np.where(rng.random(n) < 0.5, 1, 0).astype(np.int64)
-    kn[od >= 2] |= np.where(rng.random((od >= 2).sum()) < 0.3, wlsqm.b2_XY, 0)
+    kn[od >= 2] |= np.where(rng.random((od >= 2).sum()) < 0.3, b_xy, 0)
     wm = rng.integers(1, 3, n).astype(np.int32)
     xk, fk = parity.gathered(x, f, hoods)
-    fi0 = rng.standard_normal((n, 15))
+    fi0 = rng.standard_normal((n, nomax))
     fi0[:, 0] = f
     fi_g, sens_g, _, _ = _run_gpu(dim, nk, od, kn, wm, x, xk, fk, fi0, 1, True)
     fi_o, sens_o, _, _ = parity.oracle_solve(dim, nk, od, kn, wm, x, xk, fk, fi0, 1, True)
     # untouched: columns >= no_j, and known slots
     for j in range(n):
-        no = wlsqm.number_of_dofs(2, int(od[j]))
+        no = wlsqm.number_of_dofs(dim, int(od[j]))
         assert np.array_equal(fi_g[j, no:], fi0[j, no:])
         for o in range(no):
             if kn[j] >> o & 1:
                 assert fi_g[j, o] == fi0[j, o]
     for order in range(5):
         m = od == order
-        no = wlsqm.number_of_dofs(2, order)
+        no = wlsqm.number_of_dofs(dim, order)
         sc = np.abs(fi_o[m][:, :no]).max(axis=0)
         sc[sc == 0] = 1
         e = np.abs(fi_g[m][:, :no] - fi_o[m][:, :no]) / sc
@@ -111,6 +116,16 @@ def test_heterogeneous_batch():
     # sens rows k >= nk_j and columns o >= no_j stay untouched (zeros here)
     for j in range(0, n, 97):
         assert (sens_g[j, nk[j]:, :] == 0).all()
+    if bucketed:
+        # same arithmetic per fit in the per-order kernels as in the maximum order's: compare the two launch plans
+        monkeypatch.setenv("WLSQM_PREP_BUCKETS", "0")
+        fi_u, sens_u, _, _ = _run_gpu(dim, nk, od, kn, wm, x, xk, fk, fi0, 1, True)
+        sc = np.abs(fi_u).max(axis=0)
+        sc[sc == 0] = 1
+        d = np.abs(fi_g - fi_u) / sc
+        print("per-order launches vs one launch: max scaled difference %.3g, identical: %s" % (d.max(), np.array_equal(fi_g, fi_u)))
+        assert np.median(d) < 1e-9 and np.quantile(d, 0.99) < 1e-6
+        assert np.array_equal(np.isnan(sens_g), np.isnan(sens_u))
 
 
 def test_fk_alias_of_fi_on_device():
