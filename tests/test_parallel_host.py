@@ -68,3 +68,68 @@ def test_all_gather_rows_gloo_world2():
     for p in procs:
         p.join(timeout=60)
     assert res == [(0, True), (1, True)]
+
+
+class _RecordingSolver:
+    """stands in for ExpertSolver (which needs a GPU): records what the sharding layer hands to it"""
+    def __init__(self, dimension, nk, order, knowns, weighting_method, device=None, **kwargs):
+        self.dimension, self.nk, self.order, self.knowns, self.wm = dimension, nk, order, knowns, weighting_method
+        self.device, self.kwargs, self.calls = device, kwargs, []
+
+    def prepare(self, xi, xk):
+        self.calls.append(("prepare", xi, xk))
+
+    def solve(self, fk, fi, sens=None):
+        self.calls.append(("solve", fk, fi, sens))
+        fi[:, 0] = fk[:, 0]          # in-place semantics of the real solve: the caller's rows are updated
+        return 0
+
+    def prepare_hoods(self, x, hoods, xi=None):
+        self.calls.append(("prepare_hoods", x, hoods, xi))
+
+
+def test_sharded_solver_slices_global_arrays(monkeypatch):
+    """ShardedExpertSolver: every rank builds its solver from its contiguous slice of the GLOBAL metadata and hands it
+    views (no copies) of its rows of the global arrays, so that in-place results land in the caller's arrays; the
+    slices of all ranks tile the batch"""
+    monkeypatch.setattr(parallel, "ExpertSolver", _RecordingSolver)
+    n, k, world = 1001, 6, 4
+    rng = np.random.default_rng(0)
+    nk = rng.integers(3, k + 1, n).astype(np.int32)
+    od = rng.integers(0, 5, n).astype(np.int32)
+    kn = rng.integers(0, 2, n).astype(np.int64)
+    wm = rng.integers(1, 3, n).astype(np.int32)
+    xi, xk = rng.random((n, 2)), rng.random((n, k, 2))
+    fk, fi = rng.random((n, k)), np.zeros((n, 15))
+    covered = np.zeros(n, dtype=int)
+    for balance in (False, True):
+        fi[:] = 0.0
+        covered[:] = 0
+        for rank in range(world):
+            s = parallel.ShardedExpertSolver(2, nk, od, kn, wm, rank=rank, world=world, device=rank, balance=balance,
+                                             algorithm=1, do_sens=False)
+            lo, hi = s.lo, s.hi
+            covered[lo:hi] += 1
+            assert s.solver.device == rank and s.solver.kwargs == {"algorithm": 1, "do_sens": False}
+            assert np.array_equal(s.solver.nk, nk[lo:hi]) and np.array_equal(s.solver.order, od[lo:hi])
+            assert np.array_equal(s.solver.knowns, kn[lo:hi]) and np.array_equal(s.solver.wm, wm[lo:hi])
+            s.prepare(xi, xk)
+            s.solve(fk, fi)
+            (_, pxi, pxk), (_, sfk, sfi, ssens) = s.solver.calls
+            assert np.shares_memory(pxi, xi) and np.shares_memory(pxk, xk) and np.shares_memory(sfi, fi)
+            assert pxi.shape[0] == hi - lo and sfk.shape[0] == hi - lo and ssens is None
+            # rows that already are local pass through untouched
+            s.solve(fk[lo:hi], fi[lo:hi], local=True)
+            assert s.solver.calls[-1][1].shape[0] == hi - lo
+            # neighbourhoods as index lists: the cloud is replicated, the lists and the origins are this rank's rows
+            hoods = rng.integers(0, n, (n, k)).astype(np.int32)
+            s.prepare_hoods(xi, hoods)
+            _, hx, hh, hxi = s.solver.calls[-1]
+            assert hx is xi and hh.shape[0] == hi - lo and np.array_equal(hxi, xi[lo:hi])
+        assert (covered == 1).all()
+        assert np.array_equal(fi[:, 0], fk[:, 0])       # every rank wrote its rows of the global array in place
+    # the work balancer moves the cuts towards the expensive cases
+    cost = parallel.case_cost(2, nk, od, kn)
+    cuts = parallel.balanced_shards(cost, world)
+    work = np.array([cost[lo:hi].sum() for lo, hi in cuts])
+    assert work.max() / work.mean() < 1.1
