@@ -30,6 +30,35 @@ def gathered(x, f, hoods):
     return xk, fk
 
 
+def hetero_case(dim, n=3000):
+    """a batch with per-case nk / order / knowns / weighting (expert.pyx:92-104), seeded: the inputs of
+    test_gpu_parity.test_heterogeneous_batch and of the golden vectors tests/golden/golden_hetero.npz"""
+    import wlsqm_b200 as wlsqm
+    kmax = 30 if dim == 2 else 60
+    nomax = wlsqm.number_of_dofs(dim, 4)
+    b_xy = wlsqm.b2_XY if dim == 2 else wlsqm.b3_XY
+    x, hoods, f = make_case(n, dim, kmax)
+    rng = np.random.default_rng(3)
+    od = rng.integers(0, 5, n).astype(np.int32)
+    nk = np.array([rng.integers(min(kmax, (3 * wlsqm.number_of_dofs(dim, int(o))) // 2 + 2), kmax + 1) for o in od], np.int32)
+    kn = np.where(rng.random(n) < 0.5, 1, 0).astype(np.int64)
+    kn[od >= 2] |= np.where(rng.random((od >= 2).sum()) < 0.3, b_xy, 0)
+    wm = rng.integers(1, 3, n).astype(np.int32)
+    xk, fk = gathered(x, f, hoods)
+    fi0 = rng.standard_normal((n, nomax))
+    fi0[:, 0] = f
+    return dict(dim=dim, n=n, kmax=kmax, x=x, xk=xk, fk=fk, nk=nk, od=od, kn=kn, wm=wm, fi0=fi0)
+
+
+def golden_hetero(dim):
+    """the unmodified reference's fi (and the NaN pattern / a checksum of sens) for hetero_case(dim), or None"""
+    path = GOLDEN_DIR / "golden_hetero.npz"
+    if not path.exists():
+        return None
+    z = np.load(path)
+    return {k.split("/", 1)[1]: z[k] for k in z.files if k.startswith("d%d/" % dim)}
+
+
 def oracle_solve(dim, nk, order, knowns, wm, xi, xk, fk, fi0, algorithm=1, do_sens=False, max_iter=10):
     s = orc.OracleSolver(dim, nk, order, knowns, wm, algorithm, do_sens, max_iter)
     s.prepare(xi, xk)

@@ -83,19 +83,8 @@ def test_heterogeneous_batch(dim, bucketed, monkeypatch):
     """per-case nk / order / knowns / weighting in one batch (expert.pyx:92-104); `bucketed`: prepare() runs one launch
     per order over that order's case list (the default from 8192 cases on) instead of the maximum order's kernel for all"""
     monkeypatch.setenv("WLSQM_PREP_BUCKET_MIN", "1000" if bucketed else "1000000000")
-    n, kmax = 3000, (30 if dim == 2 else 60)
-    nomax = wlsqm.number_of_dofs(dim, 4)
-    b_xy = wlsqm.b2_XY if dim == 2 else wlsqm.b3_XY
-    x, hoods, f = parity.make_case(n, dim, kmax)
-    rng = np.random.default_rng(3)
-    od = rng.integers(0, 5, n).astype(np.int32)
-    nk = np.array([rng.integers(min(kmax, (3 * wlsqm.number_of_dofs(dim, int(o))) // 2 + 2), kmax + 1) for o in od], np.int32)
-    kn = np.where(rng.random(n) < 0.5, 1, 0).astype(np.int64)
-    kn[od >= 2] |= np.where(rng.random((od >= 2).sum()) < 0.3, b_xy, 0)
-    wm = rng.integers(1, 3, n).astype(np.int32)
-    xk, fk = parity.gathered(x, f, hoods)
-    fi0 = rng.standard_normal((n, nomax))
-    fi0[:, 0] = f
+    c = parity.hetero_case(dim)
+    n, x, xk, fk, nk, od, kn, wm, fi0 = (c[k] for k in ("n", "x", "xk", "fk", "nk", "od", "kn", "wm", "fi0"))
     fi_g, sens_g, _, _ = _run_gpu(dim, nk, od, kn, wm, x, xk, fk, fi0, 1, True)
     fi_o, sens_o, _, _ = parity.oracle_solve(dim, nk, od, kn, wm, x, xk, fk, fi0, 1, True)
     # untouched: columns >= no_j, and known slots
@@ -116,6 +105,17 @@ def test_heterogeneous_batch(dim, bucketed, monkeypatch):
     # sens rows k >= nk_j and columns o >= no_j stay untouched (zeros here)
     for j in range(0, n, 97):
         assert (sens_g[j, nk[j]:, :] == 0).all()
+    # the unmodified reference on the same inputs (tests/golden/make_golden_hetero.py)
+    g = parity.golden_hetero(dim)
+    assert g is not None, "tests/golden/golden_hetero.npz is missing"
+    for order in range(5):
+        m = od == order
+        no = wlsqm.number_of_dofs(dim, order)
+        sc = np.abs(g["fi_ref"][m][:, :no]).max(axis=0)
+        sc[sc == 0] = 1
+        e = np.abs(fi_g[m][:, :no] - g["fi_ref"][m][:, :no]) / sc
+        assert np.median(e) < 1e-9 and np.quantile(e, 0.99) < 1e-6, ("reference", order, np.median(e), e.max())
+    assert np.array_equal(np.packbits(np.isnan(sens_g).ravel()), g["sens_nan_bits"])
     if bucketed:
         # same arithmetic per fit in the per-order kernels as in the maximum order's: compare the two launch plans
         monkeypatch.setenv("WLSQM_PREP_BUCKETS", "0")
