@@ -36,9 +36,15 @@ def number_of_dofs(dimension, order):
     return defs.NUMBER_OF_DOFS[dimension][order]
 
 
+class NoneIntegerError(TypeError, ValueError):
+    """``None`` where a C int is expected.  The reference's source raises ``ValueError("... cannot be None")``
+    (``expert.pyx:140-149``), but its typed signature (``int algorithm=...``, ``expert.pyx:92-93``) makes Cython refuse the
+    call first with ``TypeError("an integer is required")``; code written against either catches this."""
+
+
 def _as_c_int(v, name):
     if v is None:
-        raise ValueError(f"{name} cannot be None")
+        raise NoneIntegerError(f"{name} cannot be None (an integer is required)")
     return int(v)
 
 

@@ -38,8 +38,9 @@ def _fit_many(dim, xk, fk, nk, xi, fi, sens, do_sens, order, knowns, weighting_m
     ncases = nk_a.shape[0]
     if order_a.shape[0] != ncases or knowns_a.shape[0] != ncases or wm_a.shape[0] != ncases:
         raise ValueError("nk, order, knowns and weighting_method must have the same length")
-    if max_iter is None or do_sens is None:
-        raise ValueError("do_sens and max_iter cannot be None")
+    if max_iter is None or do_sens is None:      # typed `int` arguments of the reference: Cython raises TypeError
+        from .expert import NoneIntegerError
+        raise NoneIntegerError("do_sens and max_iter cannot be None (an integer is required)")
     if ncases < 1:         # CaseManager_new (infra.pyx:308-360) refuses an empty batch
         raise ValueError("Must specify max_cases > 0 when creating a CaseManager.")
     do_sens = int(do_sens)

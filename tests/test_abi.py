@@ -3,6 +3,7 @@ include/wlsqm_b200.h declares; the ctypes table covers them; the product never t
 without a CUDA device the compute entry points fail loudly instead of falling back."""
 import ctypes
 import re
+import sys
 from pathlib import Path
 
 import numpy as np
@@ -169,3 +170,43 @@ def test_batched_driver_argument_checks_need_no_device():
             fn(*args)
     assert set(ld.__all__) >= {"mgeneral", "mgeneralp", "msymmetric", "msymmetricp", "msymmetricfactor",
                                "msymmetricfactored", "msymmetrize", "msymmetrizep"}
+
+
+def test_constructor_errors_match_the_live_reference():
+    """the same bad arguments to the unmodified reference (oracle/_ref, where it is built) and to the drop-in:
+    same exception type for every check ExpertSolver makes before it touches its native state (expert.pyx:131-159)"""
+    sys.path.insert(0, str(ROOT / "oracle"))
+    import oracle as orc
+    ref = orc.load_reference()
+    if ref is None:
+        pytest.skip("oracle/_ref is not built here")
+    import wlsqm_b200 as w
+    nk, od, kn, wm = np.full(2, 6, np.int32), np.full(2, 1, np.int32), np.zeros(2, np.int64), np.ones(2, np.int32)
+    table = [
+        ("length mismatch", (2, nk, od[:1], kn, wm), {}),
+        ("bad dimension", (5, nk, od, kn, wm), {}),
+        ("algorithm None", (2, nk, od, kn, wm), {"algorithm": None}),
+        ("unknown algorithm", (2, nk, od, kn, wm), {"algorithm": 3}),
+        ("ntasks 0", (2, nk, od, kn, wm), {"ntasks": 0}),
+        ("max_iter None", (2, nk, od, kn, wm), {"max_iter": None}),
+        ("do_sens None", (2, nk, od, kn, wm), {"do_sens": None}),
+        ("nk int64", (2, nk.astype(np.int64), od, kn, wm), {}),
+        ("knowns int32", (2, nk, od, kn.astype(np.int32), wm), {}),
+        ("empty batch", (2, nk[:0], od[:0], kn[:0], wm[:0]), {}),
+        ("nk 2-D", (2, nk.reshape(1, 2), od, kn, wm), {}),
+        ("dimension None", (None, nk, od, kn, wm), {}),
+    ]
+    import warnings
+    for what, args, kw in table:
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")      # (the reference's __del__ complains about its half-built object)
+            with pytest.raises(Exception) as e_ref:
+                ref.ExpertSolver(*args, **kw)
+        with pytest.raises(Exception) as e_new:
+            w.ExpertSolver(*args, **kw)
+        assert issubclass(e_new.type, e_ref.type), (what, e_ref.type, e_new.type, str(e_ref.value), str(e_new.value))
+    # None for a typed int: the reference's source says ValueError, its compiled signature raises TypeError -- both are caught
+    with pytest.raises(ValueError, match="cannot be None"):
+        w.ExpertSolver(2, nk, od, kn, wm, max_iter=None)
+    with pytest.raises(TypeError, match="an integer is required"):
+        w.fit_2D_many(np.zeros((2, 6, 2)), np.zeros((2, 6)), nk, np.zeros((2, 2)), np.zeros((2, 3)), None, None, od, kn, wm)
