@@ -12,13 +12,27 @@ The ``*p`` variants take ``ntasks`` for signature compatibility; on the GPU ever
 """
 from __future__ import annotations
 
+from enum import IntEnum
+
 import numpy as np
 
 from .. import _lib
 
-__all__ = ["mgeneral", "mgeneralp", "mgeneralfactor", "mgeneralfactorp", "mgeneralfactored", "mgeneralfactoredp",
+__all__ = ["ScalingAlgo", "mgeneral", "mgeneralp", "mgeneralfactor", "mgeneralfactorp", "mgeneralfactored", "mgeneralfactoredp",
            "msymmetric", "msymmetricp", "msymmetricfactor", "msymmetricfactorp", "msymmetricfactored",
            "msymmetricfactoredp", "msymmetrize", "msymmetrizep"]
+
+
+class ScalingAlgo(IntEnum):
+    """The reference's enum of matrix-scaling algorithms (``lapackdrivers.pyx:305-317``; plain ints, so comparisons with
+    int literals work).  The fitter's ``prepare`` stage uses ``ALGO_RUIZ2001`` (``impl.pyx:620-689``) -- here phase P3 of
+    ``prepare_reg_kernel``; the single-matrix ``do_rescale`` / ``rescale_*`` wrappers themselves are not served."""
+    ALGO_COLS_EUCL = 1
+    ALGO_ROWS_EUCL = 2
+    ALGO_TWOPASS = 3
+    ALGO_RUIZ2001 = 4
+    ALGO_SCALGM = 5
+    ALGO_DGEEQU = 6
 
 
 def _f3(a, name, dtype, ndim):
