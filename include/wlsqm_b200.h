@@ -102,9 +102,14 @@ WLSQM_API int wlsqm_solver_prepare_guest(wlsqm_solver_t* s);
 /* ExpertSolver.__del__ (expert.pyx:267-286) / CaseManager_del (infra.pyx:497) */
 WLSQM_API int wlsqm_solver_destroy(wlsqm_solver_t* s);
 
-/* Enqueue the solver's work on a caller-owned CUDA stream (cudaStream_t) instead of its own. */
+/* Enqueue the solver's work on a caller-owned CUDA stream (cudaStream_t) instead of its own.  Work already queued on the
+ * previous stream is ordered before whatever follows on the new one. */
 WLSQM_API int wlsqm_solver_set_stream(wlsqm_solver_t* s, void* cuda_stream);
 WLSQM_API int wlsqm_solver_synchronize(wlsqm_solver_t* s);
+/* The calling thread's CUDA stream for the entry points WITHOUT a handle (wlsqm_fit_many, wlsqm_interpolate_fit,
+ * wlsqm_grid_*, wlsqm_m*): their work runs on it or is ordered after it.  Thread-local; default NULL = the legacy
+ * default stream.  A binding that accepts device arrays sets it to the framework's current stream before each call. */
+WLSQM_API int wlsqm_set_caller_stream(void* cuda_stream);
 
 /* ExpertSolver.prepare (expert.pyx:309-426) -> expert_prepare_one_{1,2,3}D (expert.pyx:788-817):
  * make_c_*D, make_A, preprocess_A (impl.pyx:70-689).  xi: [ncases][dim] (row stride xi_s0),
@@ -174,13 +179,16 @@ WLSQM_API int wlsqm_grid_knn(wlsqm_grid_t* g, const double* xq, int64_t xq_s0, i
                    int32_t* idx32, int64_t* idx64, double* d2);
 
 /* x[hoods] / f[hoods]: dst[i][k][0..w) = src[idx[i][k]][0..w)  (the caller-side gathers of the examples).
- * src [nsrc][w] (row stride src_s0), idx int32 [n][k] (row stride idx_s0), dst [n][k][w] dense. */
-WLSQM_API int wlsqm_gather_hoods(const double* src, int64_t src_s0, int w, const int32_t* idx, int64_t idx_s0, int64_t n,
-                       int k, double* dst, int device, void* cuda_stream);
+ * src [nsrc][w] (row stride src_s0), idx int32 [n][k] (row stride idx_s0), dst [n][k][w] dense.  Asynchronous on
+ * cuda_stream; an index outside [0, nsrc) -- where numpy raises IndexError -- yields NaN, nothing is read out of bounds. */
+WLSQM_API int wlsqm_gather_hoods(const double* src, int64_t src_s0, int w, int64_t nsrc, const int32_t* idx, int64_t idx_s0,
+                       int64_t n, int k, double* dst, int device, void* cuda_stream);
 
 /* prepare / solve with the neighbourhoods given as index lists (extension): hoods int32 [ncases][>= max nk] into the
  * point array x [npoints][dim] / the per-point data f [npoints]; xk = x[hoods] and fk = f[hoods] are gathered on
- * the device.  xi == NULL: the origins are the first ncases points of x.  solve_hoods takes fi / sens like solve. */
+ * the device.  xi == NULL: the origins are the first ncases points of x.  solve_hoods takes fi / sens like solve.
+ * Only the first nk[i] indices of row i are used (the padding of ragged hoods is never dereferenced); a used index
+ * outside [0, npoints) fails with WLSQM_E_VALUE, as x[hoods] raises IndexError in the reference's caller code. */
 WLSQM_API int wlsqm_solver_prepare_hoods(wlsqm_solver_t* s, const double* x, int64_t x_s0, int64_t npoints,
                                const int32_t* hoods, int64_t hoods_s0, const double* xi, int64_t xi_s0);
 WLSQM_API int wlsqm_solver_solve_hoods(wlsqm_solver_t* s, const double* f, int64_t f_s0, double* fi, int64_t fi_s0,

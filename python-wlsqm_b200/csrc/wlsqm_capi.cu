@@ -152,16 +152,30 @@ struct DevBuf {
     }
 };
 
-// dst[i][k][0..w) = src[idx[i][k]][0..w)
+// dst[i][k][0..w) = src[idx[i][k]][0..w).  Only the first nk_i neighbours of case i are read (nk_i from the per-case
+// records, else nk_uni; negative: all k columns): the padding of a ragged hood array (cKDTree and wlsqm_grid_knn both
+// report missing neighbours as the index n) is never dereferenced and its slots are zero-filled.  An index outside
+// [0, nsrc) among the USED slots -- where the reference's x[hoods] raises IndexError -- gives NaN and raises *err.
 __global__ void gather_hoods_kernel(const double* __restrict__ src, long long src_s0, int w, const int32_t* __restrict__ idx,
-                                    long long idx_s0, long long n, int k, double* __restrict__ dst) {
+                                    long long idx_s0, long long n, int k, double* __restrict__ dst, long long nsrc,
+                                    const CaseMeta* __restrict__ meta, int nk_uni, int* __restrict__ err) {
     const long long per = (long long)k * w;
     for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n * per;
          t += (long long)gridDim.x * blockDim.x) {
         const long long i = t / per;
         const int r = (int)(t - i * per);
         const int kk = r / w, d = r - kk * w;
-        dst[t] = src[(long long)idx[i * idx_s0 + kk] * src_s0 + d];
+        const int nki = meta ? meta[i].nk : (nk_uni >= 0 ? nk_uni : k);
+        double v = 0.0;
+        if (kk < nki) {
+            const long long j = idx[i * idx_s0 + kk];
+            if (j >= 0 && j < nsrc) v = src[j * src_s0 + d];
+            else {
+                v = __longlong_as_double(0x7ff8000000000000LL);
+                if (err) *err = 1;
+            }
+        }
+        dst[t] = v;
     }
 }
 
@@ -207,6 +221,7 @@ struct wlsqm_solver {
     DevBuf st_xk, st_fk, st_fi, st_sens, st_x, st_I, st_out;
     DevBuf hoods_dev, hood_x, hood_f, hood_fk;   // prepare_hoods / solve_hoods: neighbour lists and gathered data
     long long hood_points = 0;
+    int* hood_err = nullptr;                     // device flag: a used hood index fell outside [0, npoints)
     wlsqm_grid* models_grid = nullptr;           // search grid over the model origins (index_models)
     wlsqm_solver* lender = nullptr;              // guest mode: op / dmeta / dorder / xi_dev / As / xk_keep belong to this solver
     long long bytes_state = 0;
@@ -677,6 +692,7 @@ int wlsqm_solver_destroy(wlsqm_solver_t* s) {
     dev_free(s->fi_case); dev_free(s->iters_dev); s->st_xk.release(); s->st_fk.release(); s->st_fi.release(); s->st_sens.release();
     s->st_x.release(); s->st_I.release(); s->st_out.release();
     s->hoods_dev.release(); s->hood_x.release(); s->hood_f.release(); s->hood_fk.release();
+    dev_free(s->hood_err);
     if (s->models_grid) { wlsqm_grid_destroy(s->models_grid); s->models_grid = nullptr; }
     if (s->own_stream && s->stream) cudaStreamDestroy(s->stream);
     if (s->s_in) cudaStreamDestroy(s->s_in);
@@ -757,13 +773,23 @@ int wlsqm_solver_prepare_guest(wlsqm_solver_t* s) {
 
 int wlsqm_solver_set_stream(wlsqm_solver_t* s, void* cuda_stream) {
     if (!s) return fail(WLSQM_E_VALUE, "NULL solver");
+    cudaStream_t next = (cudaStream_t)cuda_stream;
+    if (!s->own_stream && s->stream == next) return WLSQM_OK;
+    cudaSetDevice(s->device);
     if (s->own_stream && s->stream) {
-        cudaSetDevice(s->device);
         cudaStreamSynchronize(s->stream);
         cudaStreamDestroy(s->stream);
+    } else {
+        // work queued on the previous caller stream (a prepare, say) must be visible to what follows on the new one
+        CU(order_streams(s->stream, next));
     }
-    s->stream = (cudaStream_t)cuda_stream;
+    s->stream = next;
     s->own_stream = false;
+    return WLSQM_OK;
+}
+
+int wlsqm_set_caller_stream(void* cuda_stream) {
+    set_caller_stream((cudaStream_t)cuda_stream);
     return WLSQM_OK;
 }
 
@@ -1154,8 +1180,8 @@ int wlsqm_solver_get_fi(wlsqm_solver_t* s, double* out, int64_t out_s0) {
     return WLSQM_OK;
 }
 
-int wlsqm_gather_hoods(const double* src, int64_t src_s0, int w, const int32_t* idx, int64_t idx_s0, int64_t n, int k,
-                       double* dst, int device, void* cuda_stream) {
+int wlsqm_gather_hoods(const double* src, int64_t src_s0, int w, int64_t nsrc, const int32_t* idx, int64_t idx_s0, int64_t n,
+                       int k, double* dst, int device, void* cuda_stream) {
     if (n == 0 || k == 0 || w == 0) return WLSQM_OK;
     if (!src || !idx || !dst) return fail(WLSQM_E_VALUE, "NULL argument");
     if (!is_device_ptr(src) || !is_device_ptr(idx) || !is_device_ptr(dst))
@@ -1163,7 +1189,9 @@ int wlsqm_gather_hoods(const double* src, int64_t src_s0, int w, const int32_t* 
     CU(cudaSetDevice(device));
     const long long total = (long long)n * k * w;
     const unsigned blocks = (unsigned)std::min<long long>((total + 255) / 256, 148LL * 32);
-    gather_hoods_kernel<<<blocks, 256, 0, (cudaStream_t)cuda_stream>>>(src, src_s0, w, idx, idx_s0, n, k, dst);
+    // asynchronous on the caller's stream: an index outside [0, nsrc) yields NaN (no flag can be reported without a sync)
+    gather_hoods_kernel<<<blocks, 256, 0, (cudaStream_t)cuda_stream>>>(src, src_s0, w, idx, idx_s0, n, k, dst, nsrc, nullptr,
+                                                                      -1, nullptr);
     CU(cudaGetLastError());
     return WLSQM_OK;
 }
@@ -1199,14 +1227,27 @@ int wlsqm_solver_prepare_hoods(wlsqm_solver_t* s, const double* x, int64_t x_s0,
     rc = s->st_xk.reserve((size_t)n * s->maxnk * dim * 8);
     if (rc) return rc;
     const long long total = n * s->maxnk * dim;
+    if (!s->hood_err) {
+        if (dev_alloc((void**)&s->hood_err, 4) != cudaSuccess) { cudaGetLastError(); return fail(WLSQM_E_MEMORY, "device allocation failed"); }
+    }
+    CU(cudaMemsetAsync(s->hood_err, 0, 4, st));
     gather_hoods_kernel<<<(unsigned)std::min<long long>((total + 255) / 256, (long long)s->sm_count * 32), 256, 0, st>>>(
-        xd, xs0, dim, (const int32_t*)s->hoods_dev.p, s->maxnk, n, s->maxnk, (double*)s->st_xk.p);
+        xd, xs0, dim, (const int32_t*)s->hoods_dev.p, s->maxnk, n, s->maxnk, (double*)s->st_xk.p, npoints, s->dmeta,
+        s->uni.nk, s->hood_err);
     CU(cudaGetLastError());
     const double* xi_use = xi ? xi : xd;
     const long long xi_use_s0 = xi ? xi_s0 : xs0;
     rc = wlsqm_solver_prepare(s, xi_use, xi_use_s0, (const double*)s->st_xk.p, (long long)s->maxnk * dim, dim);
     if (rc) return rc;
+    int herr = 0;
+    CU(cudaMemcpyAsync(&herr, s->hood_err, 4, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
+    if (herr) {
+        // the reference's caller-side gather x[hoods] raises IndexError here (examples/expertsolver_example.py:66)
+        s->ready = false;
+        s->hoods_dev.release();
+        return fail(WLSQM_E_VALUE, "hoods: a neighbour index among the first nk[i] of some case lies outside [0, %lld)", (long long)npoints);
+    }
     s->st_xk.release();      // (ALGO_ITERATIVE keeps its own copy of the geometry)
     s->hood_x.release();
     return WLSQM_OK;
@@ -1238,8 +1279,10 @@ int wlsqm_solver_solve_hoods(wlsqm_solver_t* s, const double* f, int64_t f_s0, d
     rc = s->hood_fk.reserve((size_t)n * s->maxnk * 8);
     if (rc) return rc;
     const long long total = n * s->maxnk;
+    // (the indices were validated against [0, hood_points) by prepare_hoods; padding slots are not read)
     gather_hoods_kernel<<<(unsigned)std::min<long long>((total + 255) / 256, (long long)s->sm_count * 32), 256, 0, st>>>(
-        fd, fs0, 1, (const int32_t*)s->hoods_dev.p, s->maxnk, n, s->maxnk, (double*)s->hood_fk.p);
+        fd, fs0, 1, (const int32_t*)s->hoods_dev.p, s->maxnk, n, s->maxnk, (double*)s->hood_fk.p, s->hood_points, s->dmeta,
+        s->uni.nk, nullptr);
     CU(cudaGetLastError());
     return wlsqm_solver_solve(s, (const double*)s->hood_fk.p, s->maxnk, 1, fi, fi_s0, sens, sens_s0, sens_s1, iters_out);
 }
@@ -1341,7 +1384,7 @@ static int fit_many_direct(int dimension, int64_t ncases, const double* xk, int6
         int smc = 0;
         if (cudaDeviceGetAttribute(&smc, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && smc > 0) sh.sm_count = smc;
         else cudaGetLastError();
-        cudaStream_t st = nullptr;     // legacy default stream: ordered after the caller's work on it, synchronous result
+        cudaStream_t st = caller_stream();   // the caller's stream (default: the legacy default stream); synchronous result
         DevBuf bxk, bfk, bxi, bfi;
         auto done = [&](int r) { bxk.release(); bfk.release(); bxi.release(); bfi.release(); return r; };
         int rc = WLSQM_OK;
@@ -1403,6 +1446,9 @@ int wlsqm_fit_many(int dimension, int64_t ncases, const double* xk, int64_t xk_s
     wlsqm_solver_t* s = nullptr;
     int rc = wlsqm_solver_create(dimension, ncases, nk, order, knowns, wm, algorithm, do_sens, max_iter, 0, device, &s);
     if (rc) return rc;
+    // the temporary solver works on its own stream: order it after what the caller has queued (device-array arguments
+    // may still be being produced, or their blocks still be in use, on the caller's stream)
+    if (order_after_caller(s->stream) != cudaSuccess) { cudaGetLastError(); cudaStreamSynchronize(caller_stream()); }
     rc = wlsqm_solver_prepare(s, xi, xi_s0, xk, xk_s0, xk_s1);
     if (!rc) rc = wlsqm_solver_solve(s, fk, fk_s0, fk_s1, fi, fi_s0, sens, sens_s0, sens_s1, iters_out);
     if (!rc) rc = wlsqm_solver_synchronize(s);
@@ -1430,7 +1476,7 @@ int wlsqm_interpolate_fit(int dimension, int order, const double* xi, const doub
     if (!rc && !is_device_ptr(out)) rc = bo.reserve((size_t)nx * ow * 8);
     auto done = [&](int r) { bm.release(); bx.release(); bo.release(); return r; };
     if (rc) return done(rc);
-    cudaStream_t st = nullptr;
+    cudaStream_t st = caller_stream();
     double* dm = (double*)bm.p;
     cudaError_t e = cudaMemcpyAsync(dm, xi, (size_t)dimension * 8, cudaMemcpyDefault, st);
     if (e == cudaSuccess) e = cudaMemcpyAsync(dm + dimension, fi, (size_t)no * 8, cudaMemcpyDefault, st);
@@ -1468,7 +1514,7 @@ static int lapack_common(int n, int64_t nlhs, double* A, int32_t* ipiv, double* 
     if (!rc && !b_dev) rc = bb.reserve(nb);
     auto done = [&](int r) { ba.release(); bp.release(); bb.release(); return r; };
     if (rc) return done(rc);
-    cudaStream_t st = nullptr;
+    cudaStream_t st = caller_stream();
     double* dA = a_dev ? A : (double*)ba.p;
     int* dP = p_dev ? ipiv : (int*)bp.p;
     double* dB = b_dev ? b : (double*)bb.p;
@@ -1527,7 +1573,7 @@ int wlsqm_msymmetrize(int n, int64_t nlhs, double* A, int device) {
     const bool a_dev = is_device_ptr(A);
     DevBuf ba;
     if (!a_dev) { int rc = ba.reserve(na); if (rc) return rc; }
-    cudaStream_t st = nullptr;
+    cudaStream_t st = caller_stream();
     double* dA = a_dev ? A : (double*)ba.p;
     cudaError_t e = cudaSuccess;
     if (!a_dev) e = cudaMemcpyAsync(dA, A, na, cudaMemcpyHostToDevice, st);

@@ -76,7 +76,7 @@ __global__ void bbox_kernel(const double* __restrict__ x, long long s0, long lon
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
         for (int d = 0; d < dim; ++d) {
             const double v = x[i * s0 + d];
-            if (v == v) {     // NaN coordinates do not shape the box
+            if (fabs(v) <= 1.79769313486231570e308) {     // NaN and +/-inf coordinates do not shape the box
                 lo[d] = fmin(lo[d], v);
                 hi[d] = fmax(hi[d], v);
             }
@@ -171,7 +171,7 @@ __global__ void __launch_bounds__(128) knn_kernel(GridView g, const double* __re
                             d2 += dd * dd;
                         }
                         const int id = g.sorted_idx[p];
-                        if (id == self || !(d2 == d2)) continue;
+                        if (id == self || !(d2 < INFINITY)) continue;     // (points with NaN / inf coordinates are nobody's neighbour)
                         if (cnt == k && !(d2 < worst || (d2 == worst && id < worst_i))) continue;
                         int j = cnt < k ? cnt : k - 1;
                         while (j > 0 && (bd[j - 1] > d2 || (bd[j - 1] == d2 && bi[j - 1] > id))) {
@@ -266,6 +266,8 @@ int wlsqm_grid_create(int dimension, int64_t n, const double* x, int64_t x_s0, i
     if (e != cudaSuccess) { delete g; return gfail(WLSQM_E_CUDA, cudaGetErrorString(e)); }
     cudaStream_t st = g->stream;
     auto bail = [&](int rc) { wlsqm_grid_destroy(g); return rc; };
+    // the points may still be being produced on the caller's stream (device arrays)
+    if (order_after_caller(st) != cudaSuccess) { cudaGetLastError(); cudaStreamSynchronize(caller_stream()); }
 
     // the points on the device (a host array is staged; only the sorted copy is kept)
     double* xd = nullptr;
@@ -312,7 +314,11 @@ int wlsqm_grid_create(int dimension, int64_t n, const double* x, int64_t x_s0, i
     double h = 1.0;
     if (deff > 0) {
         h = std::pow(vol / std::max(1.0, (double)n / ppc), 1.0 / deff);
-        for (;;) {
+        // (a product of huge finite extents overflows: without this check the loop below never ends)
+        if (!std::isfinite(vol) || !std::isfinite(h) || !(h > 0.0))
+            return fail_here(WLSQM_E_VALUE, "the extent of the point set is too large for a search grid (overflow)");
+        for (int guard = 0;; ++guard) {
+            if (guard > 4096) return fail_here(WLSQM_E_VALUE, "no cell size found for the search grid");
             double total = 1.0;
             bool ok = true;
             for (int d = 0; d < dimension; ++d) {
@@ -372,6 +378,8 @@ int wlsqm_grid_knn(wlsqm_grid_t* g, const double* xq, int64_t xq_s0, int64_t nq,
     if (!idx32 && !idx64 && !d2) return gfail(WLSQM_E_VALUE, "no output array given");
     GCU(cudaSetDevice(g->device));
     cudaStream_t st = g->stream;
+    // queries / freshly allocated output tensors of the caller: order after what is queued on the caller's stream
+    if (order_after_caller(st) != cudaSuccess) { cudaGetLastError(); cudaStreamSynchronize(caller_stream()); }
     const size_t cnt = (size_t)nq * k;
     // host arrays are staged
     double* xqd = nullptr;
@@ -382,7 +390,8 @@ int wlsqm_grid_knn(wlsqm_grid_t* g, const double* xq, int64_t xq_s0, int64_t nq,
     long long s0 = xq_s0;
     if (xq && !is_dev(xq)) {
         if (dev_alloc((void**)&xqd, (size_t)nq * g->dim * 8) != cudaSuccess) return done(gfail(WLSQM_E_MEMORY, "cudaMalloc failed (queries)"));
-        GCU(cudaMemcpy2DAsync(xqd, (size_t)g->dim * 8, xq, (size_t)xq_s0 * 8, (size_t)g->dim * 8, (size_t)nq, cudaMemcpyHostToDevice, st));
+        cudaError_t ec = cudaMemcpy2DAsync(xqd, (size_t)g->dim * 8, xq, (size_t)xq_s0 * 8, (size_t)g->dim * 8, (size_t)nq, cudaMemcpyHostToDevice, st);
+        if (ec != cudaSuccess) return done(gfail(WLSQM_E_CUDA, cudaGetErrorString(ec)));
         xqv = xqd; s0 = g->dim;
     }
     if (idx32 && !is_dev(idx32)) { if (dev_alloc((void**)&b32, cnt * 4) != cudaSuccess) return done(gfail(WLSQM_E_MEMORY, "cudaMalloc failed")); o32 = (int32_t*)b32; }

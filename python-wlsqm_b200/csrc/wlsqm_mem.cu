@@ -119,6 +119,24 @@ void dev_pool_stats(int device, long long* reserved, long long* used) {
     if (used) *used = (long long)u;
 }
 
+namespace {
+thread_local cudaStream_t g_caller_stream = nullptr;
+}
+void set_caller_stream(cudaStream_t s) { g_caller_stream = s; }
+cudaStream_t caller_stream() { return g_caller_stream; }
+
+cudaError_t order_streams(cudaStream_t earlier, cudaStream_t later) {
+    if (earlier == later) return cudaSuccess;
+    cudaEvent_t ev = nullptr;
+    cudaError_t e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+    if (e != cudaSuccess) return e;
+    e = cudaEventRecord(ev, earlier);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(later, ev, 0);
+    cudaEventDestroy(ev);      // (released by the runtime once the recorded work has completed)
+    return e;
+}
+cudaError_t order_after_caller(cudaStream_t priv) { return order_streams(g_caller_stream, priv); }
+
 void dev_pool_trim(int device) {
     if (device < 0 || device >= MAX_DEVICES || !g_pools[device].ok) return;
     cudaStreamSynchronize(g_pools[device].stream);

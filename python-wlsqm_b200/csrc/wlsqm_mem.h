@@ -24,4 +24,16 @@ void dev_pool_stats(int device, long long* reserved, long long* used);
 // Give cached blocks back to the driver.
 void dev_pool_trim(int device);
 
+// The CUDA stream of the CALLER, for entry points that have no handle to carry one (one-shot fits, interpolate_fit,
+// the search grid, the batched dense drivers): thread-local, set through wlsqm_set_caller_stream(); the default is the
+// legacy default stream (which is torch's default stream).  Work of such a call runs on that stream, or -- where the
+// library uses a private stream -- is ordered after everything already queued on it (order_after_caller), so that a
+// kernel never reads an input before the torch op producing it has run, nor writes into a freshly allocated torch
+// tensor whose block the caching allocator still has in use on the caller's stream.
+void set_caller_stream(cudaStream_t s);
+cudaStream_t caller_stream();
+cudaError_t order_after_caller(cudaStream_t priv);
+// make `later` wait for everything queued so far on `earlier` (no-op when they are the same stream)
+cudaError_t order_streams(cudaStream_t earlier, cudaStream_t later);
+
 }  // namespace wlsqm

@@ -44,6 +44,7 @@ SIGNATURES = {
     "wlsqm_solver_destroy": (_int, [_vp]),
     "wlsqm_solver_set_stream": (_int, [_vp, _vp]),
     "wlsqm_solver_synchronize": (_int, [_vp]),
+    "wlsqm_set_caller_stream": (_int, [_vp]),
     "wlsqm_solver_prepare": (_int, [_vp, _vp, _i64, _vp, _i64, _i64]),
     "wlsqm_solver_solve": (_int, [_vp, _vp, _i64, _i64, _vp, _i64, _vp, _i64, _i64, _i32p]),
     "wlsqm_solver_iterations": (_int, [_vp, _vp]),
@@ -58,7 +59,7 @@ SIGNATURES = {
     "wlsqm_grid_destroy": (_int, [_vp]),
     "wlsqm_grid_info": (_int, [_vp, _i64p, C.POINTER(C.c_double), _i64p]),
     "wlsqm_grid_knn": (_int, [_vp, _vp, _i64, _i64, _int, _int, _vp, _vp, _vp]),
-    "wlsqm_gather_hoods": (_int, [_vp, _i64, _int, _vp, _i64, _i64, _int, _vp, _int, _vp]),
+    "wlsqm_gather_hoods": (_int, [_vp, _i64, _int, _i64, _vp, _i64, _i64, _int, _vp, _int, _vp]),
     "wlsqm_solver_prepare_hoods": (_int, [_vp, _vp, _i64, _i64, _vp, _i64, _vp, _i64]),
     "wlsqm_solver_solve_hoods": (_int, [_vp, _vp, _i64, _vp, _i64, _vp, _i64, _i64, _i32p]),
     "wlsqm_solver_index_models": (_int, [_vp]),
@@ -129,6 +130,12 @@ def current_stream_ptr(device: int):
     return None
 
 
+def announce_stream(device: int):
+    """Tell the library which CUDA stream the handle-less entry points (one-shot fits, interpolate_fit, search grid,
+    batched dense drivers) must order their work after: torch's current stream on `device`, else the default stream."""
+    lib().wlsqm_set_caller_stream(current_stream_ptr(int(device)))
+
+
 def _is_torch_tensor(a) -> bool:
     t = sys.modules.get("torch")
     return t is not None and isinstance(a, t.Tensor)
@@ -167,6 +174,15 @@ def as_arr(a, dtype, ndim, name, *, writable=False, last_contig=True, allow_copy
             return Arr(int(a.data_ptr()), a.shape, st, True, a.device.index, a)
         a = a.detach().numpy()
     if not isinstance(a, np.ndarray):
+        if writable:
+            # the reference's typed memoryviews refuse objects without a writable buffer; a silently copied list would
+            # swallow the results
+            try:
+                mv = memoryview(a)
+            except TypeError:
+                raise TypeError(f"{name}: a writable float64 buffer is required (got {type(a).__name__})") from None
+            if mv.readonly:
+                raise ValueError(f"{name}: buffer source array is read-only")
         try:
             a = np.asarray(a)
         except Exception as e:  # pragma: no cover

@@ -204,8 +204,10 @@ class ExpertSolver:
             raise ValueError("xi and xk must have at least ncases = %d rows" % self.ncases)
         if self.ncases and xk_a.shape[1] < self._maxnk:
             raise ValueError("xk must hold at least max(nk) = %d neighbours per case" % self._maxnk)
-        if not xk_a.is_cuda and dim >= 2 and self._maxnk > 1 and xk_s1 != xk_a.shape[2]:
-            xk_a = _lib.as_arr(np.ascontiguousarray(xk_a.np), np.float64, 3, "xk")
+        if not xk_a.is_cuda and dim >= 2 and self._maxnk > 1 and (xk_s1 != dim or xk_a.shape[2] != dim):
+            # host rows must be dense with exactly `dim` coordinates; the reference's double[:,:,::contiguous] view also
+            # accepts pitched rows / a longer last axis and reads only the first dim columns
+            xk_a = _lib.as_arr(np.ascontiguousarray(xk_a.np[:, :, :dim]), np.float64, 3, "xk")
             xk_s0, xk_s1 = xk_a.strides[0], xk_a.strides[1]
         if not xk_a.is_cuda and dim == 1 and self._maxnk > 1 and xk_s1 != 1:
             xk_a = _lib.as_arr(np.ascontiguousarray(xk_a.np), np.float64, 2, "xk", last_contig=False)

@@ -47,10 +47,12 @@ def _fit_many(dim, xk, fk, nk, xi, fi, sens, do_sens, order, knowns, weighting_m
     if dim >= 2:
         xk_a = _lib.as_arr(xk, np.float64, 3, "xk")
         xi_a = _lib.as_arr(xi, np.float64, 2, "xi")
-        if not xk_a.is_cuda and xk_a.shape[1] > 1 and xk_a.strides[1] != xk_a.shape[2]:
-            xk_a = _lib.as_arr(np.ascontiguousarray(xk_a.np), np.float64, 3, "xk")
         if xi_a.shape[1] < dim or xk_a.shape[2] < dim:
             raise ValueError("xi and xk must have %d coordinates on their last axis" % dim)
+        # the library wants dense neighbour rows of exactly `dim` coordinates from host memory; the reference's
+        # double[:,:,::contiguous] view also takes pitched rows and longer last axes (only the first dim columns are read)
+        if not xk_a.is_cuda and xk_a.shape[1] > 1 and (xk_a.strides[1] != dim or xk_a.shape[2] != dim):
+            xk_a = _lib.as_arr(np.ascontiguousarray(xk_a.np[:, :, :dim]), np.float64, 3, "xk")
     else:
         xk_a = _lib.as_arr(xk, np.float64, 2, "xk", last_contig=False, allow_copy=True)
         xi_a = _lib.as_arr(xi, np.float64, 1, "xi", last_contig=False)
@@ -82,6 +84,7 @@ def _fit_many(dim, xk, fk, nk, xi, fi, sens, do_sens, order, knowns, weighting_m
         if device is None:
             device = _lib.default_device()
     it = C.c_int32(0)
+    _lib.announce_stream(device)
     _lib.check(_lib.lib().wlsqm_fit_many(
         dim, ncases, xk_a.ptr, xk_a.strides[0], xk_a.strides[1], fk_a.ptr, fk_a.strides[0], fk_a.strides[1],
         nk_a.ctypes.data, xi_a.ptr, xi_a.strides[0], fi_a.ptr, fi_a.strides[0], sens_p, s0, s1, do_sens,

@@ -50,6 +50,7 @@ class PointGrid:
         self._on_device = a.is_cuda
         self._torch_device = x.device if a.is_cuda else None
         h = C.c_void_p()
+        _lib.announce_stream(self.device)
         _lib.check(_lib.lib().wlsqm_grid_create(dim, n, a.ptr, s0, self.device, C.byref(h)))
         self._handle = h
 
@@ -84,6 +85,7 @@ class PointGrid:
         k = int(k)
         idx, ip = self._out((self.n, k), np.int32, self._on_device)
         d2, dp = (self._out((self.n, k), np.float64, self._on_device) if return_distance else (None, None))
+        _lib.announce_stream(self.device)
         _lib.check(_lib.lib().wlsqm_grid_knn(self._handle, None, 0, self.n, k, 1 if exclude_self else 0, ip, None, dp))
         if return_distance:
             return (d2.sqrt() if self._on_device else np.sqrt(d2)), idx
@@ -98,6 +100,7 @@ class PointGrid:
         idx, ip = self._out((nq, k), np.int64, a.is_cuda)
         d2, dp = self._out((nq, k), np.float64, a.is_cuda)
         if nq:
+            _lib.announce_stream(self.device)
             _lib.check(_lib.lib().wlsqm_grid_knn(self._handle, a.ptr, s0, nq, k, 0, None, ip, dp))
         d = d2.sqrt() if a.is_cuda else np.sqrt(d2)
         if k == 1:
@@ -130,6 +133,6 @@ def gather(src, hoods):
     n, k = hoods.shape
     out = torch.empty((n, k) if src.dim() == 1 else (n, k, w), dtype=torch.float64, device=src.device)
     sp = _lib.current_stream_ptr(src.device.index)
-    _lib.check(_lib.lib().wlsqm_gather_hoods(int(src.data_ptr()), src.stride(0), w, int(hoods.data_ptr()), hoods.stride(0),
-                                             n, k, int(out.data_ptr()), src.device.index, sp))
+    _lib.check(_lib.lib().wlsqm_gather_hoods(int(src.data_ptr()), src.stride(0), w, src.shape[0], int(hoods.data_ptr()),
+                                             hoods.stride(0), n, k, int(out.data_ptr()), src.device.index, sp))
     return out

@@ -68,10 +68,12 @@ def _f3(a, name, dtype, ndim):
 
 
 def _dev(*devs):
-    for d in devs:
-        if d is not None:
-            return d
-    return _lib.default_device()
+    """device of the call (first one named), announcing the caller's CUDA stream on it to the library"""
+    dev = next((d for d in devs if d is not None), None)
+    if dev is None:
+        dev = _lib.default_device()
+    _lib.announce_stream(dev)
+    return dev
 
 
 def mgeneralfactor(A, ipiv, device=None):
