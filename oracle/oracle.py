@@ -146,6 +146,35 @@ class OracleSolver:
         return out
 
 
+    def interpolate_continuous(self, x, r, diff=0):
+        """mode='continuous' (expert_interpolate_continuous, wlsqm/fitter/expert.pyx:898-985): for every query, the
+        weighted average over all local models whose origin lies within r (cKDTree.query_ball_tree, :902-911), each
+        model evaluated by interpolate_nD (:958-972), weights alpha + beta (1 - sqrt(d2 / r^2))^2 with alpha = 0,
+        beta = 1 (:45-46, :979-980), accumulated in the order of the ball query's lists (:955-983); cdivision is on
+        (:11), so a query with no model within r yields 0/0 = NaN."""
+        from scipy.spatial import cKDTree
+        x = np.ascontiguousarray(np.asarray(x, np.float64).reshape(-1, self.dim))
+        lists = cKDTree(x).query_ball_tree(cKDTree(self.xi), r=r)
+        cnt = np.array([len(L) for L in lists], np.int64)
+        qm = np.repeat(np.arange(len(x)), cnt)
+        li = np.array([i for L in lists for i in L], np.int64)
+        out = np.full(len(x), np.nan)
+        if len(li) == 0:
+            return out
+        vals = self.interpolate(x[qm], li, diff)
+        d2 = ((x[qm] - self.xi[li]) ** 2).sum(axis=1) if self.dim > 1 else ((x[qm, 0] - self.xi[li, 0]) ** 2)
+        tmp = 1.0 - np.sqrt(d2 / (r * r))
+        w = 0.0 + 1.0 * tmp * tmp
+        acc = np.zeros(len(x))
+        sw = np.zeros(len(x))
+        # sequential accumulation per query, in list order (np.add.at applies the updates in index order)
+        np.add.at(acc, qm, w * vals)
+        np.add.at(sw, qm, w)
+        with np.errstate(invalid="ignore", divide="ignore"):
+            out = acc / sw
+        return out
+
+
 def fit_many(dimension, xk, fk, nk, xi, fi, sens, do_sens, order, knowns, weighting_method,
              algorithm=ALGO_BASIC, max_iter=10):
     """fit_?D[_iterative]_many[_parallel] (wlsqm/fitter/simple.pyx:731-1170): prepare+solve."""

@@ -79,6 +79,59 @@ def permuted_self_noise(dim, nk, order, knowns, wm, xi, xk, fk, fi0, algorithm=1
     return a, b
 
 
+def permute_within_hoods(nk, xk, fk, seed=7):
+    """per-case random permutation of the first nk[j] neighbours (the rest of the row stays where it is): the same
+    neighbourhoods in another summation order, for batches whose cases use different numbers of neighbours"""
+    rng = np.random.default_rng(seed)
+    n, kmax = fk.shape
+    keys = rng.random((n, kmax))
+    keys[np.arange(kmax)[None, :] >= np.asarray(nk)[:, None]] = 2.0 + np.arange(kmax)[None, :].repeat(n, 0)[
+        np.arange(kmax)[None, :] >= np.asarray(nk)[:, None]]
+    perm = np.argsort(keys, axis=1, kind="stable")
+    rows = np.arange(n)[:, None]
+    return np.ascontiguousarray(xk[rows, perm]), np.ascontiguousarray(fk[rows, perm])
+
+
+def hetero_self_noise(dim, nk, order, knowns, wm, xi, xk, fk, fi0, algorithm=1, max_iter=10, seed=7):
+    """oracle vs oracle with every case's own neighbours permuted (heterogeneous batches)"""
+    a, _, _, _ = oracle_solve(dim, nk, order, knowns, wm, xi, xk, fk, fi0, algorithm, False, max_iter)
+    xkp, fkp = permute_within_hoods(nk, xk, fk, seed)
+    b, _, _, _ = oracle_solve(dim, nk, order, knowns, wm, xi, xkp, fkp, fi0, algorithm, False, max_iter)
+    return a, b
+
+
+def check_hetero_against_floor(got, ref, ref_perm, dim, od, label="", min_cases=20):
+    """check_against_floor per ORDER GROUP of a batch with per-case orders: the cases of order o, their first no(o)
+    columns, grouped by derivative order.  Returns the report."""
+    lines = []
+    for order in sorted(set(int(o) for o in od)):
+        m = np.asarray(od) == order
+        if m.sum() < min_cases:
+            continue
+        no = orc.number_of_dofs(dim, order)
+        lines.append(check_against_floor(got[m][:, :no], ref[m][:, :no], ref_perm[m][:, :no], dim, order,
+                                         "%s order %d (%d cases)" % (label, order, int(m.sum()))))
+    return "\n".join(lines)
+
+
+def golden_hetero_iter(dim):
+    """the unmodified reference's ALGO_ITERATIVE(3) results for hetero_case(dim) (tests/golden/golden_hetero_iter.npz)"""
+    path = GOLDEN_DIR / "golden_hetero_iter.npz"
+    if not path.exists():
+        return None
+    z = np.load(path)
+    return {k.split("/", 1)[1]: z[k] for k in z.files if k.startswith("d%d/" % dim)}
+
+
+def golden_continuous(dim):
+    """the unmodified reference's ExpertSolver.interpolate outputs, both modes (tests/golden/golden_continuous.npz)"""
+    path = GOLDEN_DIR / "golden_continuous.npz"
+    if not path.exists():
+        return None
+    z = np.load(path)
+    return {k.split("/", 1)[1]: z[k] for k in z.files if k.startswith("d%d/" % dim)}
+
+
 def check_against_floor(got, ref, ref_perm, dim, order, label=""):
     """assert got ~ ref within FLOOR_FACTOR x |ref - ref_perm| per derivative order; returns the report"""
     rep = wl.parity_report(got, ref, dim, order)
@@ -140,3 +193,51 @@ def check_sens(sens_got, sens_ref, label=""):
     err = np.abs(np.nan_to_num(sens_got) - r) / sc
     assert err.max() < 1e-7 and np.median(err) < 1e-11, (label, err.max(), np.median(err))
     return err.max()
+
+
+def cfg4_problem(dim, n, k, order=3):
+    """BASELINE.json configs[3] as SURVEY.md 8d builds it (needs a GPU: the neighbour search runs on the device):
+    order-3 fits with WEIGHT_UNIFORM; interior points know F; boundary points (2D: the 4 sqrt(n) points nearest the box
+    edges; 1D: the two end points and every 1000th point) know dF/dy (dF/dx in 1D) from the analytic field instead and
+    take their k neighbours from the INTERIOR points only (defs.pyx:199-207); an interior point's neighbours are its k
+    nearest interior points.  Returns host metadata and device tensors (x_d, hoods_d, f_d, fi_in_d)."""
+    import torch
+    import wlsqm_b200 as wlsqm
+    no = orc.number_of_dofs(dim, order)
+    x = wl.cloud(n, dim)
+    x2 = x.reshape(n, -1)
+    L = wl.H0 * n ** (1.0 / dim)
+    bnd = np.zeros(n, bool)
+    if dim == 2:
+        edge = np.minimum(np.minimum(x2[:, 0], L - x2[:, 0]), np.minimum(x2[:, 1], L - x2[:, 1]))
+        bnd[np.argsort(edge, kind="stable")[: int(4 * np.sqrt(n))]] = True
+        iB, bB, bF = wlsqm.i2_Y, wlsqm.b2_Y, wlsqm.b2_F
+        dfd = -np.pi * np.sin(np.pi * x2[:, 0]) * np.sin(np.pi * x2[:, 1])       # d/dy of sin(pi x) cos(pi y)
+    elif dim == 1:
+        bnd[[int(np.argmin(x)), int(np.argmax(x))]] = True
+        bnd[::1000] = True
+        iB, bB, bF = wlsqm.i1_X, wlsqm.b1_X, wlsqm.b1_F
+        dfd = np.pi * np.cos(np.pi * x)
+    else:
+        raise ValueError("configs[3] is 1D / 2D")
+    interior = np.nonzero(~bnd)[0]
+    boundary = np.nonzero(bnd)[0]
+    xin_d = torch.from_numpy(np.ascontiguousarray(x2[interior])).cuda()
+    grid = wlsqm.PointGrid(xin_d)
+    h_in = grid.knn(k)                                                            # (n_int, k) into the interior array
+    _, h_b = grid.query(torch.from_numpy(np.ascontiguousarray(x2[boundary])).cuda(), k=k)
+    int_d = torch.from_numpy(interior).cuda()
+    hoods_d = torch.empty((n, k), dtype=torch.int32, device="cuda")
+    hoods_d[int_d] = int_d[h_in.long()].int()
+    hoods_d[torch.from_numpy(boundary).cuda()] = int_d[h_b.reshape(len(boundary), k)].int()
+    grid.close()
+    nk, od, wm = np.full(n, k, np.int32), np.full(n, order, np.int32), np.full(n, 1, np.int32)     # WEIGHT_UNIFORM
+    kn = np.full(n, bF, np.int64)
+    kn[bnd] = bB
+    f = wl.field(x)
+    fi_in = np.full((n, no), 123.0)                    # sentinel in every unknown slot
+    fi_in[~bnd, 0] = f[~bnd]
+    fi_in[bnd, iB] = dfd[bnd]
+    return dict(dim=dim, n=n, k=k, order=order, no=no, x=x, x2=x2, bnd=bnd, interior=interior, boundary=boundary, iB=iB,
+                meta=(nk, od, kn, wm), f=f, hoods_d=hoods_d, x_d=torch.from_numpy(x).cuda(), f_d=torch.from_numpy(f).cuda(),
+                fi_in_d=torch.from_numpy(fi_in).cuda())

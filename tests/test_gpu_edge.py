@@ -166,3 +166,133 @@ def test_large_pageable_arrays_take_the_threaded_staging_path():
     fi2 = torch.zeros_like(fi_d)
     s2.solve(fk_d, fi2)
     assert torch.equal(fi2, fi_d)
+
+
+# ---- robustness of the extension entry points (hood index lists, search grid, CUDA streams) --------------------
+def test_ragged_hoods_padding_is_never_dereferenced_and_bad_indices_raise():
+    """hoods rows with nk[i] < max nk carry padding (cKDTree and the device search both report a missing neighbour as
+    the index n): only the first nk[i] entries are used; a USED index outside [0, npoints) raises ValueError where the
+    reference's caller-side gather x[hoods] raises IndexError."""
+    n, k, dim, order = 600, 14, 2, 2
+    x, hoods, f = parity.make_case(n, dim, k)
+    rng = np.random.default_rng(4)
+    nk = rng.integers(8, k + 1, n).astype(np.int32)
+    nk[0] = k
+    od, kn, wm = np.full(n, order, np.int32), np.full(n, 1, np.int64), np.full(n, 2, np.int32)
+    ragged = hoods.copy()
+    pad = np.array([n, -1, 2 ** 31 - 1, n + 12345], np.int32)
+    for i in range(n):
+        ragged[i, nk[i]:] = pad[rng.integers(0, 4, k - nk[i])]
+    s = wlsqm.ExpertSolver(dim, nk, od, kn, wm)
+    s.prepare_hoods(x, ragged)
+    fi = np.zeros((n, 6)); fi[:, 0] = f
+    s.solve_hoods(f, fi)
+    # == the pre-gathered path on the same neighbourhoods (padding slots hold anything there, too)
+    xk, fk = parity.gathered(x, f, hoods)
+    s2 = wlsqm.ExpertSolver(dim, nk, od, kn, wm)
+    s2.prepare(x, xk)
+    fi2 = np.zeros((n, 6)); fi2[:, 0] = f
+    s2.solve(fk, fi2)
+    assert np.array_equal(fi, fi2)
+    bad = hoods.copy()
+    bad[17, 3] = n                      # a used slot
+    s3 = wlsqm.ExpertSolver(dim, nk, od, kn, wm)
+    with pytest.raises(ValueError, match="hoods"):
+        s3.prepare_hoods(x, bad)
+    assert not s3.ready
+    bad[17, 3] = -2
+    with pytest.raises(ValueError, match="hoods"):
+        s3.prepare_hoods(x, bad)
+    s3.prepare_hoods(x, hoods)          # and the solver is still usable afterwards
+    torch = pytest.importorskip("torch")
+    g = wlsqm.gather(torch.from_numpy(f).cuda(), torch.from_numpy(bad).cuda())
+    torch.cuda.synchronize()
+    gh = g.cpu().numpy()
+    assert np.isnan(gh[17, 3]) and np.isfinite(np.delete(gh.ravel(), 17 * k + 3)).all()
+
+
+def test_search_grid_with_non_finite_coordinates_does_not_hang():
+    """+/-inf coordinates are treated like NaN ones (nobody's neighbour, they do not shape the cell grid); a cloud with
+    no finite point, or an extent whose volume overflows, is a ValueError -- not an endless loop (run with a timeout)."""
+    x, hoods, f = parity.make_case(2000, 2, 8)
+    xb = x.copy()
+    xb[5, 0] = np.inf
+    xb[9, 1] = -np.inf
+    xb[11, 0] = np.nan
+    h = wlsqm.knn_hoods(xb, 8)
+    good = np.ones(2000, bool); good[[5, 9, 11]] = False
+    assert not np.isin(h[good], [5, 9, 11]).any()
+    from scipy.spatial import cKDTree
+    idx = np.nonzero(good)[0]
+    ref = idx[cKDTree(x[good]).query(x[good], 9)[1][:, 1:]]
+    assert np.array_equal(h[good], ref)
+    with pytest.raises(ValueError):
+        wlsqm.PointGrid(np.full((10, 2), np.inf))
+    huge = np.array([[-1e200, -1e200, -1e200], [1e200, 1e200, 1e200], [0.0, 0.0, 0.0]])
+    with pytest.raises(ValueError):
+        wlsqm.PointGrid(huge)
+
+
+def test_work_is_ordered_against_torch_side_streams():
+    """inputs produced on a NON-default torch stream right before the call, outputs consumed right after it on that
+    stream: one-shot fits, the search grid and a solver that changes streams between prepare and solve"""
+    torch = pytest.importorskip("torch")
+    n, k = 200_000, 12
+    x, hoods, f = parity.make_case(n, 2, k, unit_box=True)
+    nk, od, kn, wm = _meta(n, k, 2, 1, 2)
+    xk, fk = parity.gathered(x, f, hoods)
+    fi0 = np.zeros((n, 6)); fi0[:, 0] = f
+    ref = fi0.copy()
+    wlsqm.fit_2D_many_parallel(xk, fk, nk, x, ref, None, 0, od, kn, wm)
+    xk_h, fk_h, x_h, fi_h = (torch.from_numpy(a).pin_memory() for a in (xk, fk, x, fi0))
+    side, side2 = torch.cuda.Stream(), torch.cuda.Stream()
+    for rep in range(3):
+        with torch.cuda.stream(side):
+            # a long copy chain queued on the side stream; the library call must wait for it
+            junk = torch.empty(64 << 20, dtype=torch.float64, device="cuda")
+            for _ in range(4):
+                junk.mul_(1.0000001)
+            xk_d, fk_d, x_d = (t.to("cuda", non_blocking=True) for t in (xk_h, fk_h, x_h))
+            fi_d = fi_h.to("cuda", non_blocking=True)
+            wlsqm.fit_2D_many_parallel(xk_d, fk_d, nk, x_d, fi_d, None, 0, od, kn, wm)
+            out = fi_d.cpu().numpy()
+        assert np.array_equal(out, ref)
+        with torch.cuda.stream(side):
+            junk.mul_(1.0000001)
+            x_d2 = x_h.to("cuda", non_blocking=True)
+            hd = wlsqm.knn_hoods(x_d2, k)
+        assert np.array_equal(hd.cpu().numpy(), hoods)
+        # prepare on one stream, solve on another
+        s = wlsqm.ExpertSolver(2, nk, od, kn, wm)
+        with torch.cuda.stream(side):
+            junk.mul_(1.0000001)
+            xk_d, x_d = xk_h.to("cuda", non_blocking=True), x_h.to("cuda", non_blocking=True)
+            s.prepare(x_d, xk_d)
+        with torch.cuda.stream(side2):
+            side2.wait_stream(side)          # (the tensors were produced on `side`)
+            fk_d, fi_d = fk_h.to("cuda", non_blocking=True), fi_h.to("cuda", non_blocking=True)
+            s.solve(fk_d, fi_d)
+            out = fi_d.cpu().numpy()
+        assert np.array_equal(out, ref)
+        del junk
+
+
+def test_host_xk_with_a_longer_last_axis_and_list_outputs():
+    """the reference's double[:,:,::contiguous] xk accepts an (n, k, 3) array for a 2D fit and reads the first two
+    columns; a list passed where results are written is refused (the reference's memoryviews raise, too)"""
+    n, k = 300, 12
+    x, hoods, f = parity.make_case(n, 2, k, unit_box=True)
+    nk, od, kn, wm = _meta(n, k, 2, 1, 2)
+    xk, fk = parity.gathered(x, f, hoods)
+    xk3 = np.concatenate([xk, np.full((n, k, 1), 7.0)], axis=2)
+    fi_a = np.zeros((n, 6)); fi_a[:, 0] = f
+    fi_b = fi_a.copy(); fi_c = fi_a.copy()
+    wlsqm.fit_2D_many_parallel(xk, fk, nk, x, fi_a, None, 0, od, kn, wm)
+    wlsqm.fit_2D_many_parallel(xk3, fk, nk, x, fi_b, None, 0, od, kn, wm)
+    assert np.array_equal(fi_a, fi_b)
+    s = wlsqm.ExpertSolver(2, nk, od, kn, wm)
+    s.prepare(x, xk3)
+    s.solve(fk, fi_c)
+    assert np.array_equal(fi_a, fi_c)
+    with pytest.raises((TypeError, ValueError)):
+        s.solve(fk, fi_c.tolist())

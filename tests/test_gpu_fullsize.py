@@ -295,3 +295,140 @@ def test_cfg3_shard_size_iterative_sens():
     for dd in range(1, order + 1):
         ee = e[:, torch.as_tensor(np.nonzero(d == dd)[0], device="cuda")]
         assert float(ee.max()) <= REPRO_MAX, (dd, float(ee.max()))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# configs 3 and 4 at their FULL sizes on real kNN neighbourhoods, with an oracle subsample
+# ---------------------------------------------------------------------------------------------------------------
+def _subsample_vs_oracle(dim, idx, meta_all, x_d, hoods_d, f_d, fi_in_d, fi_out_d, algorithm, max_iter, label,
+                         sens_d=None, iters=None):
+    """the oracle on the cases `idx` (host), against the rows of the full-size GPU result: noise floor of
+    tests/parity.py per order group; returns the report"""
+    it = torch.from_numpy(idx).cuda()
+    hd = hoods_d[it].long()
+    x2 = x_d if x_d.dim() == 2 else x_d[:, None]
+    xk_s = x2[hd].cpu().numpy()
+    if dim == 1:
+        xk_s = np.ascontiguousarray(xk_s[:, :, 0])
+    fk_s = f_d[hd].cpu().numpy()
+    xi_s = x_d[it].cpu().numpy()
+    nk, od, kn, wm = (a[idx] for a in meta_all)
+    fi0 = fi_in_d[it].cpu().numpy()
+    ref, sens_o, _, so = parity.oracle_solve(dim, nk, od, kn, wm, xi_s, xk_s, fk_s, fi0, algorithm, sens_d is not None, max_iter)
+    a, b = parity.hetero_self_noise(dim, nk, od, kn, wm, xi_s, xk_s, fk_s, fi0, algorithm, max_iter)
+    got = fi_out_d[it].cpu().numpy()
+    order = int(od[0])
+    rep = []
+    for knv in np.unique(kn):          # one group per knowns pattern (interior / boundary)
+        m = kn == knv
+        rep.append(parity.check_against_floor(got[m], ref[m], (b + (ref - a))[m], dim, order,
+                                              "%s knowns=%d (%d cases)" % (label, int(knv), int(m.sum()))))
+    if sens_d is not None:
+        parity.check_sens(sens_d[it].cpu().numpy(), sens_o, label)
+    if iters is not None:
+        assert np.array_equal(iters[idx], so.iters), (label, "per-case iteration counts differ from the oracle's")
+    return "\n".join(rep)
+
+
+@pytest.mark.parametrize("dim,k", [(2, 24), (1, 8)])
+def test_cfg4_full_size_knn_hoods_boundary_construction(dim, k):
+    """BASELINE.json configs[3] as SURVEY.md 8d builds it: 2M points, order 3, WEIGHT_UNIFORM; interior points know F;
+    boundary points (2D: the 4 sqrt(n) points nearest the box edges; 1D: the two end points and every 1000th point) know
+    the derivative dF/dy (dF/dx in 1D) from the analytic field instead, and take their neighbours from the interior
+    points only (the Neumann-boundary stencil of wlsqm/fitter/defs.pyx:199-207).  Neighbourhoods are real k-nearest-
+    neighbour lists (device-side search, spot-checked against cKDTree)."""
+    from scipy.spatial import cKDTree
+    n, order = 2_000_000, 3
+    no = wlsqm.number_of_dofs(dim, order)
+    p = parity.cfg4_problem(dim, n, k)
+    x, x2, bnd, interior, boundary, hoods_d, iB = (p[key] for key in ("x", "x2", "bnd", "interior", "boundary", "hoods_d", "iB"))
+    nk, od, kn, wm = p["meta"]
+    x_d, f_d, fi_in_d = p["x_d"], p["f_d"], p["fi_in_d"]
+    # hood indexing: bit exact against cKDTree on a sample of both groups
+    tree = cKDTree(x2[interior])
+    si = interior[:: max(1, len(interior) // 500)]
+    ref_i = interior[tree.query(x2[si], k + 1)[1][:, 1:]]
+    assert np.array_equal(hoods_d[torch.from_numpy(si).cuda()].cpu().numpy(), ref_i)
+    sb = boundary[:: max(1, len(boundary) // 300)]
+    ref_b = interior[tree.query(x2[sb], k)[1]]
+    assert np.array_equal(hoods_d[torch.from_numpy(sb).cuda()].cpu().numpy(), ref_b)
+    fi_d = fi_in_d.clone()
+    s = wlsqm.ExpertSolver(dim, nk, od, kn, wm)
+    s.prepare_hoods(x_d, hoods_d)
+    assert s.solve_hoods(f_d, fi_d) == 0
+    # knowns untouched bit for bit at every point; every unknown slot overwritten
+    bd = torch.from_numpy(bnd).cuda()
+    assert torch.equal(fi_d[~bd, 0], fi_in_d[~bd, 0]) and torch.equal(fi_d[bd, iB], fi_in_d[bd, iB])
+    unk = torch.ones((n, no), dtype=torch.bool, device="cuda")
+    unk[~bd, 0] = False
+    unk[bd, iB] = False
+    assert not bool((fi_d[unk] == 123.0).any())
+    # sanity: the fitted value at the boundary points against the analytic field (one-sided order-3 stencils of radius
+    # ~5 h0: truncation error ~ (pi r)^4 / 24)
+    assert float((fi_d[bd, 0] - f_d[bd]).abs().max()) < 1e-3
+    # the oracle on ~1000 interior and ~500 boundary cases, noise floor per group
+    idx = np.sort(np.concatenate([interior[:: len(interior) // 1000], boundary[:: max(1, len(boundary) // 500)]]))
+    print(_subsample_vs_oracle(dim, idx, (nk, od, kn, wm), x_d, hoods_d, f_d, fi_in_d, fi_d, 1, 0,
+                               "cfg4 %dD 2M kNN hoods" % dim))
+
+
+def test_cfg3_full_size_4M_knn_hoods_iterative_sens():
+    """BASELINE.json configs[2] at its FULL size on one GPU: 4M points 3D, order 4, k = 60 nearest neighbours, F known,
+    ALGO_ITERATIVE max_iter = 3, do_sens (about 150 GB of the 180 GB: operators 66 GB + sens 67 GB + geometry).
+    Checked: knowns bit for bit, NaN pattern of sens at every point, sens^T-identity on a sample, shard invariance
+    (one rank's 500k-point range of the 8-GPU split solved alone == the same rows), and the oracle on ~1000 cases
+    (noise floor, sens, per-case iteration counts).  Skipped when the device has less than 160 GB free."""
+    free, total = torch.cuda.mem_get_info()
+    torch.cuda.empty_cache()
+    wlsqm.pool_trim()
+    free, total = torch.cuda.mem_get_info()
+    if free < 160e9:
+        pytest.skip("needs 160 GB of free device memory, have %.0f GB" % (free / 1e9))
+    n, dim, order, k, no = 4_000_000, 3, 4, 60, 35
+    x = wl.cloud(n, dim)
+    x_d = torch.from_numpy(x).cuda()
+    hoods_d = wlsqm.knn_hoods(x_d, k)
+    from scipy.spatial import cKDTree
+    sample = np.arange(0, n, 7993)
+    ref_h = cKDTree(x).query(x[sample], k + 1, workers=-1)[1][:, 1:]
+    assert np.array_equal(hoods_d[torch.from_numpy(sample).cuda()].cpu().numpy(), ref_h)
+    nk, od, kn, wm = _meta(n, k, order, wlsqm.b3_F, wlsqm.WEIGHT_CENTER)
+    f = wl.field(x)
+    f_d = torch.from_numpy(f).cuda()
+    fi_in_d = torch.zeros((n, no), dtype=torch.float64, device="cuda")
+    fi_in_d[:, 0] = f_d
+    fi_d = fi_in_d.clone()
+    s = wlsqm.ExpertSolver(dim, nk, od, kn, wm, algorithm=wlsqm.ALGO_ITERATIVE, do_sens=True, max_iter=3)
+    s.prepare_hoods(x_d, hoods_d)
+    sens = torch.empty((n, k, no), dtype=torch.float64, device="cuda")
+    iters = s.solve_hoods(f_d, fi_d, sens)
+    assert 1 <= iters <= 3
+    assert torch.equal(fi_d[:, 0], f_d)
+    # NaN exactly in the known slot, at every point (chunked: the mask of the whole array would be 8 GB)
+    for c0 in range(0, n, 500_000):
+        blk = torch.isnan(sens[c0:c0 + 500_000])
+        assert bool(blk[:, :, 0].all()) and not bool(blk[:, :, 1:].any())
+        del blk
+    its = s.iterations()
+    # the oracle on every 3989th case
+    idx = np.arange(0, n, 3989)
+    print(_subsample_vs_oracle(dim, idx, (nk, od, kn, wm), x_d, hoods_d, f_d, fi_in_d, fi_d, 2, 3, "cfg3 4M kNN hoods",
+                               sens_d=sens, iters=its))
+    # shard invariance: rank 5 of 8 owns [2.5M, 3M); solved alone it gives the same rows, bit for bit
+    keep_rows = fi_d[2_500_000:3_000_000].clone()
+    keep_sens = sens[2_500_000:2_500_100].clone()
+    del sens, s
+    torch.cuda.empty_cache()
+    wlsqm.pool_trim()
+    lo, hi = 2_500_000, 3_000_000
+    s2 = wlsqm.ExpertSolver(dim, nk[lo:hi], od[lo:hi], kn[lo:hi], wm[lo:hi], algorithm=wlsqm.ALGO_ITERATIVE, do_sens=True,
+                            max_iter=3)
+    s2.prepare_hoods(x_d, hoods_d[lo:hi], xi=x_d[lo:hi])
+    fi2 = fi_in_d[lo:hi].clone()
+    sens2 = torch.empty((hi - lo, k, no), dtype=torch.float64, device="cuda")
+    s2.solve_hoods(f_d, fi2, sens2)
+    assert torch.equal(fi2, keep_rows)
+    assert torch.equal(torch.nan_to_num(sens2[:100]), torch.nan_to_num(keep_sens))
+    del s2, sens2
+    torch.cuda.empty_cache()
+    wlsqm.pool_trim()
