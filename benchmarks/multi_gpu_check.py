@@ -54,14 +54,42 @@ def main():
     ms = torch.tensor([e0.elapsed_time(e1) / steps], device=dev)
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     same_rows = bool(torch.equal(fi_loc, fi_full[sh.lo:sh.hi]))
-    whole = sh.gather(fi_loc)                                  # optional: the whole field on every rank
+    whole = sh.gather(fi_loc)                                  # collective gather: the whole field on every rank
     same_all = bool(torch.equal(whole, fi_full))
-    ok = torch.tensor([int(same_rows and same_all)], device=dev)
+
+    def timed(fn):
+        fn()
+        torch.cuda.synchronize()
+        dist.barrier()
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) / steps], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+    f_full = f
+    out_buf = torch.empty((n, no), dtype=torch.float64, device=dev)
+    ms_local = timed(lambda: sh.solve_hoods(f_full, fi_loc, local=True))
+    ms_nccl = timed(lambda: (sh.solve_hoods(f_full, fi_loc, local=True), sh.gather(fi_loc, out=out_buf)))
+    # fused gather: the solve kernel stores its rows into every GPU's copy of the global array over NVLink
+    fi_glob = sh.enable_fused_gather()
+    sh.solve_hoods(f_full, fi_loc, local=True)
+    sh.sync_gather()
+    torch.cuda.synchronize()
+    same_fused = bool(torch.equal(fi_glob, fi_full))
+    ms_fused = timed(lambda: (sh.solve_hoods(f_full, fi_loc, local=True), sh.sync_gather()))
+    sh.disable_fused_gather()
+    ok = torch.tensor([int(same_rows and same_all and same_fused)], device=dev)
     dist.all_reduce(ok, op=dist.ReduceOp.MIN)
     if rank == 0:
-        print(json.dumps({"check": "sharded solve_hoods == unsharded, bit for bit, on every rank", "ok": bool(ok.item()),
+        print(json.dumps({"check": "sharded solve_hoods == unsharded, bit for bit, on every rank (local rows, NCCL all-gather, "
+                                   "fused peer-store gather)", "ok": bool(ok.item()),
                           "world": world, "points": n, "ms_per_step_incl_allgather_of_f": float(ms.item()),
-                          "points_per_s": n / (float(ms.item()) * 1e-3)}), flush=True)
+                          "ms_per_step_local_rows_only": ms_local, "ms_per_step_with_nccl_all_gather_of_fi": ms_nccl,
+                          "ms_per_step_with_fused_gather_of_fi": ms_fused,
+                          "points_per_s_fused": n / (ms_fused * 1e-3)}), flush=True)
     dist.barrier()
     dist.destroy_process_group()
     sys.exit(0 if ok.item() else 1)

@@ -73,6 +73,7 @@ WLSQM_API int wlsqm_meta_summary(int64_t ncases, const int32_t* nk, const int32_
 
 /* page-locked host buffers for the staged (host-pointer) path */
 WLSQM_API void* wlsqm_pinned_alloc(int64_t bytes);
+WLSQM_API void* wlsqm_pinned_alloc_wc(int64_t bytes);          /* write-combined: for buffers the host only writes */
 WLSQM_API void wlsqm_pinned_free(void* p);
 
 /* Device memory of the library comes from one stream-ordered CUDA memory pool per device: what a destroyed solver or
@@ -201,6 +202,22 @@ WLSQM_API int wlsqm_solver_index_models(wlsqm_solver_t* s);
 WLSQM_API int wlsqm_solver_nearest_models(wlsqm_solver_t* s, const double* x, int64_t x_s0, int64_t nx, int64_t* I_out);
 WLSQM_API int wlsqm_solver_interpolate_continuous(wlsqm_solver_t* s, const double* x, int64_t x_s0, int64_t nx, double r,
                                         int diff, double* out);
+
+/* ---- fused result gather over NVLink peer memory (multi-GPU, one process per GPU) --------------------------------
+ * The reference is one process: all cases of a solver write into one fi array (the prange of expert.pyx:536-557).
+ * With the cases sharded over GPUs the same array exists once per GPU; instead of an all-gather after the solve, the
+ * solve kernel stores every row it computes into ALL copies through peer memory.
+ *   wlsqm_peer_alloc: this rank's copy (plain cudaMalloc, zero-filled) and its 64-byte CUDA IPC handle, to be sent to
+ *                     the other ranks by any means (torch.distributed.all_gather_object in the Python mirror);
+ *   wlsqm_peer_open / _close: map / unmap a peer's copy in this process;  wlsqm_peer_free: release the own copy;
+ *   wlsqm_solver_set_gather: row c of this solver is row row0 + c (row stride row_stride >= max no, in doubles) of each
+ *                     of the ntargets (<= 8) arrays; ntargets = 0 switches the gather off.
+ * Rows written by peers are visible after a synchronisation between the ranks (a stream-ordered barrier per step). */
+WLSQM_API int wlsqm_peer_alloc(int device, int64_t bytes, void** ptr, void* ipc_handle_64);
+WLSQM_API int wlsqm_peer_open(int device, const void* ipc_handle_64, void** ptr);
+WLSQM_API int wlsqm_peer_close(void* ptr);
+WLSQM_API int wlsqm_peer_free(void* ptr);
+WLSQM_API int wlsqm_solver_set_gather(wlsqm_solver_t* s, int ntargets, void* const* bases, int64_t row0, int64_t row_stride);
 
 /* ---- batched general drivers: wlsqm/utils/lapackdrivers.pyx:1551-1723 ------------------------------ */
 /* A (n,n,nlhs) Fortran-contiguous, b (n,nlhs) Fortran, ipiv (n,nlhs) int32 Fortran, 1-based; in place. */

@@ -352,16 +352,40 @@ def msymmetrize(A):
             A[j, i, :] = t
 
 
-def load_reference():
-    """Import the compiled unmodified reference from oracle/_ref (None if it is not built)."""
-    ref = HERE / "_ref"
-    if not (ref / "wlsqm" / "__init__.py").exists():
+def _cpu_has(*flags):
+    try:
+        txt = Path("/proc/cpuinfo").read_text()
+        line = next(l for l in txt.splitlines() if l.startswith("flags"))
+        have = set(line.split(":", 1)[1].split())
+        return all(f in have for f in flags)
+    except Exception:
+        return False
+
+
+def reference_variants():
+    """{name: directory} of the reference builds present AND runnable on this host (oracle/build_ref.py)"""
+    out = {}
+    if (HERE / "_ref" / "wlsqm" / "__init__.py").exists():
+        out["generic"] = HERE / "_ref"
+    if (HERE / "_ref" / "_tuned" / "wlsqm" / "__init__.py").exists() and _cpu_has("avx2", "fma", "bmi2"):
+        out["tuned"] = HERE / "_ref" / "_tuned"
+    return out
+
+
+def load_reference(variant: str = "generic"):
+    """Import the compiled unmodified reference from oracle/_ref (None if it is not built).  One variant per process:
+    `variant` = "generic" (-O2, the checker) or "tuned" (-O2 -march=x86-64-v3, CPU-baseline timing only)."""
+    ref = reference_variants().get(variant)
+    if ref is None:
         return None
     if str(ref) not in sys.path:
         sys.path.insert(0, str(ref))
     os.environ.setdefault("OMP_WAIT_POLICY", "passive")
     os.environ.setdefault("OPENBLAS_NUM_THREADS", "1")
     try:
-        return importlib.import_module("wlsqm")
+        mod = importlib.import_module("wlsqm")
     except Exception:  # pragma: no cover - e.g. ABI mismatch on a foreign box
         return None
+    if Path(mod.__file__).resolve().parent.parent != Path(ref).resolve():
+        return None      # another variant is already imported in this process
+    return mod

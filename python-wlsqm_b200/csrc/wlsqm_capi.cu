@@ -222,6 +222,10 @@ struct wlsqm_solver {
     DevBuf hoods_dev, hood_x, hood_f, hood_fk;   // prepare_hoods / solve_hoods: neighbour lists and gathered data
     long long hood_points = 0;
     int* hood_err = nullptr;                     // device flag: a used hood index fell outside [0, npoints)
+    // fused result gather: global solution arrays of the GPUs of the job (peer memory), see wlsqm_solver_set_gather
+    int ngather = 0;
+    double* gather[WLSQM_MAX_PEERS] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    long long gather_row0 = 0, gather_s0 = 0;
     wlsqm_grid* models_grid = nullptr;           // search grid over the model origins (index_models)
     wlsqm_solver* lender = nullptr;              // guest mode: op / dmeta / dorder / xi_dev / As / xk_keep belong to this solver
     long long bytes_state = 0;
@@ -514,6 +518,17 @@ void* wlsqm_pinned_alloc(int64_t bytes) {
     }
     return p;
 }
+// write-combined page-locked memory: faster for the device to read over PCIe on some hosts, slow for the CPU to read back
+// -- for buffers the host only WRITES (the per-step input fk)
+void* wlsqm_pinned_alloc_wc(int64_t bytes) {
+    void* p = nullptr;
+    if (bytes <= 0) return nullptr;
+    if (cudaHostAlloc(&p, (size_t)bytes, cudaHostAllocWriteCombined) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
 void wlsqm_pinned_free(void* p) {
     if (p) cudaFreeHost(p);
 }
@@ -788,6 +803,59 @@ int wlsqm_solver_set_stream(wlsqm_solver_t* s, void* cuda_stream) {
     return WLSQM_OK;
 }
 
+// ---- fused result gather over peer memory (multi-GPU) -----------------------------------------------
+// One process per GPU.  Every rank allocates its copy of the GLOBAL solution array with wlsqm_peer_alloc and publishes
+// the 64-byte IPC handle; the others open it (wlsqm_peer_open).  wlsqm_solver_set_gather hands the solver the base
+// pointers of all copies: from then on solve() stores every row it computes into each of them (its own included),
+// i.e. the all-gather of fi happens inside the solve kernel, tile by tile, over NVLink.  The ranks still need one
+// synchronisation per step before they read rows written by their peers (any stream-ordered barrier).
+int wlsqm_peer_alloc(int device, int64_t bytes, void** ptr, void* ipc_handle_64) {
+    if (!ptr || !ipc_handle_64 || bytes <= 0) return fail(WLSQM_E_VALUE, "wlsqm_peer_alloc: bad argument");
+    *ptr = nullptr;
+    if (wlsqm_device_count() < 1) return fail(WLSQM_E_CUDA, "no CUDA device available (there is no CPU fallback)");
+    CU(cudaSetDevice(device));
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, (size_t)bytes);      // (IPC needs a plain allocation, not a block of the stream-ordered pool)
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(WLSQM_E_MEMORY, "cudaMalloc(%lld bytes) failed: %s", (long long)bytes, cudaGetErrorString(e)); }
+    cudaIpcMemHandle_t h;
+    e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) { cudaGetLastError(); cudaFree(p); return fail(WLSQM_E_CUDA, "cudaIpcGetMemHandle: %s", cudaGetErrorString(e)); }
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    memcpy(ipc_handle_64, &h, 64);
+    CU(cudaMemset(p, 0, (size_t)bytes));
+    *ptr = p;
+    return WLSQM_OK;
+}
+int wlsqm_peer_open(int device, const void* ipc_handle_64, void** ptr) {
+    if (!ptr || !ipc_handle_64) return fail(WLSQM_E_VALUE, "wlsqm_peer_open: bad argument");
+    *ptr = nullptr;
+    CU(cudaSetDevice(device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, ipc_handle_64, 64);
+    cudaError_t e = cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) { cudaGetLastError(); *ptr = nullptr; return fail(WLSQM_E_CUDA, "cudaIpcOpenMemHandle: %s", cudaGetErrorString(e)); }
+    return WLSQM_OK;
+}
+int wlsqm_peer_close(void* ptr) {
+    if (ptr && cudaIpcCloseMemHandle(ptr) != cudaSuccess) cudaGetLastError();
+    return WLSQM_OK;
+}
+int wlsqm_peer_free(void* ptr) {
+    if (ptr && cudaFree(ptr) != cudaSuccess) cudaGetLastError();
+    return WLSQM_OK;
+}
+int wlsqm_solver_set_gather(wlsqm_solver_t* s, int ntargets, void* const* bases, int64_t row0, int64_t row_stride) {
+    if (!s) return fail(WLSQM_E_VALUE, "NULL solver");
+    if (ntargets < 0 || ntargets > WLSQM_MAX_PEERS) return fail(WLSQM_E_VALUE, "between 0 and %d gather targets", WLSQM_MAX_PEERS);
+    if (ntargets > 0 && (!bases || row_stride < s->maxno || row0 < 0)) return fail(WLSQM_E_VALUE, "wlsqm_solver_set_gather: bad layout");
+    for (int p = 0; p < ntargets; ++p)
+        if (!bases[p]) return fail(WLSQM_E_VALUE, "wlsqm_solver_set_gather: NULL target");
+    s->ngather = ntargets;
+    for (int p = 0; p < WLSQM_MAX_PEERS; ++p) s->gather[p] = p < ntargets ? (double*)bases[p] : nullptr;
+    s->gather_row0 = row0; s->gather_s0 = row_stride;
+    return WLSQM_OK;
+}
+
 int wlsqm_set_caller_stream(void* cuda_stream) {
     set_caller_stream((cudaStream_t)cuda_stream);
     return WLSQM_OK;
@@ -914,6 +982,9 @@ int wlsqm_solver_solve(wlsqm_solver_t* s, const double* fk, int64_t fk_s0, int64
         P.iters_max = s->iters_dev;
         P.iters_case = s->iters_dev + 1;
     }
+    P.ngather = s->ngather;
+    for (int p = 0; p < s->ngather; ++p) P.gather[p] = s->gather[p];
+    P.gather_row0 = s->gather_row0; P.gather_s0 = s->gather_s0;
 
     // ---- device-side views of the arguments (host arrays get dense device mirrors) -------------------
     const bool staged = !fk_dev || !fi_dev || !sens_dev;

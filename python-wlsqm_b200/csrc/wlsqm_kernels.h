@@ -7,6 +7,7 @@ namespace wlsqm {
 
 constexpr int PREP_MAX_THREADS = 512;        // shared-memory variant (wlsqm_prepare_smem.cu)
 constexpr int PREP_REG_THREADS = 512;        // register/DMMA variant (wlsqm_prepare.cu): launch bound; the host picks the CTA size
+constexpr int WLSQM_MAX_PEERS = 8;           // GPUs of one NVSwitch domain that can receive the fused gather
 constexpr int PREP_CB = 36;                  // row stride (doubles) inside a 32-column block of the monomial table
 constexpr int SOLVE_MAX_THREADS = 1024;       // ALGO_BASIC variants (<= 64 registers per thread)
 constexpr int SOLVE_MAX_THREADS_ITER = 512;   // ALGO_ITERATIVE variants carry the Taylor evaluator
@@ -70,6 +71,12 @@ struct SolveParams {
     int bar_off_bytes;                               // start of the mbarrier array
     int f_tma, xk_tma;                               // fk / xk rows qualify for bulk copies (alignment, unit stride)
     int pack_lw;                                     // packed variant: log2 of the lanes per case
+    // fused result gather (multi-GPU): every solved row is also stored into the global solution array of
+    // each of `ngather` GPUs (this one included) through peer memory over NVLink -- the all-gather of fi without a
+    // collective: row c of this solver is row gather_row0 + c there
+    int ngather;
+    double* gather[WLSQM_MAX_PEERS];
+    long long gather_row0, gather_s0;
 };
 
 struct InterpParams {

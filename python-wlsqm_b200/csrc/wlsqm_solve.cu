@@ -375,6 +375,16 @@ solve_kernel(SolveParams P) {
             P.fi_case[c * P.fi_case_ld + lane + 32] = v1;
             if (P.fi_out && unk1) P.fi_out[c * P.fi_out_s0 + lane + 32] = v1;
         }
+        if (P.ngather) {
+            // fused all-gather: the whole row (knowns included) into every GPU's copy of the global array (peer stores
+            // over NVLink; 8 * no bytes per peer against the 8 * nq * nr bytes of the block just streamed)
+            const long long g = (P.gather_row0 + c) * P.gather_s0;
+#pragma unroll 1
+            for (int p = 0; p < P.ngather; ++p) {
+                if (in0) P.gather[p][g + lane] = v0;
+                if (in1) P.gather[p][g + lane + 32] = v1;
+            }
+        }
         __syncwarp();   // every lane is done with this stage before lane 0 re-arms it
         if (++stage == S) { stage = 0; phase ^= 1u; }
         mt = mt_next; g0 = gn0; g1 = gn1;
@@ -515,6 +525,11 @@ __global__ void __launch_bounds__(SOLVE_MAX_THREADS) solve_pack_kernel(SolvePara
         if (valid) {
             P.fi_case[c * P.fi_case_ld + o] = v;
             if (P.fi_out && !isk) P.fi_out[c * P.fi_out_s0 + o] = v;
+            if (P.ngather) {
+                const long long g = (P.gather_row0 + c) * P.gather_s0 + o;
+#pragma unroll 1
+                for (int p = 0; p < P.ngather; ++p) P.gather[p][g] = v;
+            }
         }
         // ---- sensitivities: the operator itself, re-indexed by DOF slot (impl.pyx:838-846) ----------------
         if (SENS && nr > 0) {

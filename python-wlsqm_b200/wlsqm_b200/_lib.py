@@ -35,6 +35,7 @@ SIGNATURES = {
     "wlsqm_number_of_dofs": (_int, [_int, _int]),
     "wlsqm_meta_summary": (_int, [_i64, _vp, _vp, _vp, _vp, _i32p, _i32p, _i32p, _i32p]),
     "wlsqm_pinned_alloc": (_vp, [_i64]),
+    "wlsqm_pinned_alloc_wc": (_vp, [_i64]),
     "wlsqm_pinned_free": (None, [_vp]),
     "wlsqm_pool_stats": (_int, [_int, _i64p, _i64p]),
     "wlsqm_pool_trim": (_int, [_int]),
@@ -65,6 +66,11 @@ SIGNATURES = {
     "wlsqm_solver_index_models": (_int, [_vp]),
     "wlsqm_solver_nearest_models": (_int, [_vp, _vp, _i64, _i64, _vp]),
     "wlsqm_solver_interpolate_continuous": (_int, [_vp, _vp, _i64, _i64, C.c_double, _int, _vp]),
+    "wlsqm_peer_alloc": (_int, [_int, _i64, C.POINTER(_vp), _vp]),
+    "wlsqm_peer_open": (_int, [_int, _vp, C.POINTER(_vp)]),
+    "wlsqm_peer_close": (_int, [_vp]),
+    "wlsqm_peer_free": (_int, [_vp]),
+    "wlsqm_solver_set_gather": (_int, [_vp, _int, C.POINTER(_vp), _i64, _i64]),
     "wlsqm_mgetrf": (_int, [_int, _i64, _vp, _vp, _int]),
     "wlsqm_mgetrs": (_int, [_int, _i64, _vp, _vp, _vp, _int]),
     "wlsqm_mgesv": (_int, [_int, _i64, _vp, _vp, _vp, _int]),
@@ -219,11 +225,12 @@ def meta_array(a, dtype, name) -> np.ndarray:
     return np.ascontiguousarray(a)
 
 
-def pinned_empty(shape, dtype=np.float64) -> np.ndarray:
-    """Page-locked host array (fast, asynchronous H2D/D2H for the staged host-pointer path)."""
+def pinned_empty(shape, dtype=np.float64, write_combined=False) -> np.ndarray:
+    """Page-locked host array (fast, asynchronous H2D/D2H for the staged host-pointer path).  ``write_combined``: for
+    arrays the host only writes (inputs); reading them back on the CPU is very slow."""
     dtype = np.dtype(dtype)
     n = int(np.prod(shape)) * dtype.itemsize
-    p = lib().wlsqm_pinned_alloc(max(n, 1))
+    p = (lib().wlsqm_pinned_alloc_wc if write_combined else lib().wlsqm_pinned_alloc)(max(n, 1))
     if not p:
         raise MemoryError(f"cudaHostAlloc({n} bytes) failed")
     buf = (C.c_char * max(n, 1)).from_address(p)

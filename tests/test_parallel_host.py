@@ -39,15 +39,29 @@ def _worker(rank, world, port, n, q):
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        lo, hi = parallel.shard_range(n, rank, world)
         full = torch.arange(n * 3, dtype=torch.float64).reshape(n, 3)
-        got = parallel.all_gather_rows(full[lo:hi].clone(), n, lo)
+        # near-equal shards (uneven by one row when world does not divide n): sizes come from (n, world) alone
+        ranges = parallel.shard_ranges(n, world)
+        lo, hi = ranges[rank]
+        got = parallel.all_gather_rows(full[lo:hi].clone(), ranges)
         ok = bool(torch.equal(got, full))
+        # even shards: one all_gather_into_tensor straight into a preallocated output
+        ne = n - n % world
+        re = parallel.shard_ranges(ne, world)
+        out = torch.full((ne, 3), -1.0, dtype=torch.float64)
+        got_e = parallel.all_gather_rows(full[re[rank][0]:re[rank][1]], re, out=out)
+        ok = ok and got_e is out and bool(torch.equal(out, full[:ne]))
         # uneven shards from the work balancer
         cost = np.linspace(1.0, 5.0, n)
-        lo2, hi2 = parallel.balanced_shards(cost, world)[rank]
-        got2 = parallel.all_gather_rows(full[lo2:hi2].clone(), n, lo2)
+        r2 = parallel.balanced_shards(cost, world)
+        got2 = parallel.all_gather_rows(full[r2[rank][0]:r2[rank][1]].clone(), r2)
         ok = ok and bool(torch.equal(got2, full))
+        # a rank whose rows do not match its range is refused
+        try:
+            parallel.all_gather_rows(full[:1], ranges)
+            ok = ok and (ranges[rank][1] - ranges[rank][0] == 1)
+        except ValueError:
+            pass
         q.put((rank, ok))
     finally:
         dist.destroy_process_group()
