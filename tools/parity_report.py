@@ -69,7 +69,13 @@ def subsample_compare(label, dim, order, idx, meta, x_d, hoods_d, f_d, fi_in_d, 
     cond = conds_of(dim, m, xi_s, xk_s)
     extra = ""
     if iters is not None:
-        extra = "iterations: gpu == oracle for %d of %d cases (max %d)" % (int((iters[idx] == so.iters).sum()), len(idx), int(so.iters.max()))
+        gi, oi = iters[idx], so.iters
+        pairs = {}
+        for g_, o_ in zip(gi.tolist(), oi.tolist()):
+            pairs[(g_, o_)] = pairs.get((g_, o_), 0) + 1
+        extra = ("refinement iterations: gpu == oracle for %d of %d cases, max gpu %d / oracle %d; (gpu, oracle) -> cases: %s "
+                 "[the exit `norm == prev_norm` (impl.pyx:1057-1060) compares bit patterns, so it can fire one round apart]"
+                 % (int((gi == oi).sum()), len(idx), int(gi.max()), int(oi.max()), sorted(pairs.items())))
     if sens_d is not None:
         sg = sens_d[it].cpu().numpy()
         same_nan = np.array_equal(np.isnan(sg), np.isnan(sens_o))
@@ -127,8 +133,8 @@ def main():
     got = fi0.copy()
     wlsqm.fit_2D_many_parallel(xk, fk, m[0], x, got, None, 0, m[1], m[2], m[3], ntasks=8)
     ref, _, _, _ = parity.oracle_solve(2, *m, x, xk, fk, fi0)
-    a, b = parity.permuted_self_noise(2, *m, x, xk, fk, fi0)
-    report("cfg1: fit_2D_many_parallel, 10k points, order 2, k=12, b2_F, WEIGHT_CENTER [all cases]", 2, 2, got, ref, b + (ref - a),
+    pa, pb = parity.permuted_self_noise(2, *m, x, xk, fk, fi0)
+    report("cfg1: fit_2D_many_parallel, 10k points, order 2, k=12, b2_F, WEIGHT_CENTER [all cases]", 2, 2, got, ref, pb + (ref - pa),
            conds_of(2, m, x, xk))
     expert_cfg("cfg2 headline: 2D order 4, k=30, knowns=0, WEIGHT_UNIFORM, ALGO_BASIC", 1_000_000, 2, 4, 30, 0, 1, 1, False, 499)
     expert_cfg("cfg2 variant: knowns=b2_F", 1_000_000, 2, 4, 30, 1, 1, 1, False, 499)
