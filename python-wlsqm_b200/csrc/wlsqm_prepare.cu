@@ -67,11 +67,12 @@ int prep_reg_fit_doubles(int dim, int maxorder, int nb, int nkn_max) {
     const int d = nop * (nop + 2) + nb * 32 + 4 * nrp + nop / 2 + nkn_max * nop;
     return (d + 1) & ~1;
 }
-// per warp: the monomial table CT [nb][NOP][PREP_CB] (transient: Gram phase, then right-hand-side gather and
-// operator staging) followed by prep_reg_fits_per_warp() fit regions
+// per warp: ONE block of the monomial table CT [NOP][PREP_CB] (transient: the Gram phase walks the neighbours 32 at a
+// time; then right-hand-side gather and operator staging) followed by prep_reg_fits_per_warp() fit regions.  The
+// staging of 32 operator rows needs 32 * nr <= NOP * PREP_CB doubles.
 int prep_reg_warp_doubles(int dim, int maxorder, int nb, int nkn_max) {
     const int nop = (prep_no(dim, maxorder) + 7) & ~7;
-    const int d = nb * nop * PREP_CB + prep_reg_fits_per_warp(dim, maxorder) * prep_reg_fit_doubles(dim, maxorder, nb, nkn_max);
+    const int d = nop * PREP_CB + prep_reg_fits_per_warp(dim, maxorder) * prep_reg_fit_doubles(dim, maxorder, nb, nkn_max);
     return (d + 15) & ~15;
 }
 
@@ -128,8 +129,8 @@ __global__ void __launch_bounds__(PK<DIM, ORD>::MAXT, PK<DIM, ORD>::MINB) prepar
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int nwarps = blockDim.x >> 5;
-    double* CT = smem + (size_t)warp * P.warp_doubles;   // [nb][NOP][CB] monomials (transposed); P5: gather + staging
-    double* fits = CT + P.nb * BLK;
+    double* CT = smem + (size_t)warp * P.warp_doubles;   // [NOP][CB] monomials of 32 neighbours (transposed); P5: gather + staging
+    double* fits = CT + BLK;
     // carve-up of one fit's region (offsets in doubles)
     constexpr int oG = 0;                      // [NOP][LDA]  Gram matrix, later the LU factors (pivot order)
     constexpr int oW = oG + NOP * LDA;         // [nb*32]     weights of the right-hand-side columns
@@ -230,20 +231,29 @@ __global__ void __launch_bounds__(PK<DIM, ORD>::MAXT, PK<DIM, ORD>::MINB) prepar
             double* W = fb + oW;
             int* R2O = reinterpret_cast<int*>(fb + oR2O);
 
-            // ---- P1. monomials and squared distances (lane = neighbour) ----------------------------
+            // ---- P1a. squared distances and weights (lane = neighbour; infra.pyx:679-702) ---------------
+            // columns >= nk carry weight 0 through the Gram phase
             double max_d2 = 0.0;
 #pragma unroll 1
             for (int b = 0; b < nblk; ++b) {
                 const int k = b * 32 + lane;
-                const double d2 = monomial_column(c, k, nk, no, CT + b * BLK + lane);
+                double d2 = 0.0;
+                if (k < nk) {
+                    const double* xp = P.xk + c * P.xk_s0 + (long long)k * P.xk_s1;
+                    const double* xo = P.xi + c * P.xi_s0;
+#pragma unroll
+                    for (int d = 0; d < DIM; ++d) {
+                        const double dd = xp[d] - xo[d];
+                        d2 += dd * dd;
+                    }
+                }
                 max_d2 = max_nn(max_d2, d2);
                 W[k] = d2;
             }
-            // ---- weights (infra.pyx:679-702); columns >= nk carry weight 0 through the Gram phase ----
             if (mt.wm == WLSQM_WEIGHT_CENTER) {
                 max_d2 = warp_max(max_d2);
-    #pragma unroll 1
-            for (int b = 0; b < nblk; ++b) {
+#pragma unroll 1
+                for (int b = 0; b < nblk; ++b) {
                     const int k = b * 32 + lane;
                     double w = 0.0;
                     if (k < nk) {
@@ -253,8 +263,8 @@ __global__ void __launch_bounds__(PK<DIM, ORD>::MAXT, PK<DIM, ORD>::MINB) prepar
                     W[k] = w;
                 }
             } else {
-    #pragma unroll 1
-            for (int b = 0; b < nblk; ++b) {
+#pragma unroll 1
+                for (int b = 0; b < nblk; ++b) {
                     const int k = b * 32 + lane;
                     W[k] = k < nk ? 1.0 : 0.0;
                 }
@@ -264,31 +274,39 @@ __global__ void __launch_bounds__(PK<DIM, ORD>::MAXT, PK<DIM, ORD>::MINB) prepar
                 if (!((knowns >> o) & 1LL)) R2O[o - __popcll(below)] = o;        // unknown: reduced index
                 else R2O[nr + __popcll(below)] = o;                              // known slots, ascending, after the unknowns
             }
-            __syncwarp();
 
-            // ---- P2. G = C^T W C on the FP64 tensor cores ----------------------------------------
+            // ---- P1b + P2, one block of 32 neighbours at a time: monomials c[k][s] into the (single) CT block, then
+            //      G += C^T W C on the FP64 tensor cores; the accumulators stay in registers across the blocks ----------
             {
                 double acc[T * (T + 1) / 2][2];
 #pragma unroll
                 for (int t = 0; t < T * (T + 1) / 2; ++t) acc[t][0] = acc[t][1] = 0.0;
                 const int kk = lane & 3, jj = lane >> 2;
-                for (int k0 = 0; k0 < nkp; k0 += 4) {
-                    const int k = k0 + kk;
-                    const double* ctk = CT + (k >> 5) * BLK + (k & 31) + jj * CB;
-                    const double w = W[k];
-                    double cf[T], wf[T];
+                const int nkblk = (nkp + 31) >> 5;
+#pragma unroll 1
+                for (int b = 0; b < nkblk; ++b) {
+                    __syncwarp();                                   // the previous block's fragments have been read
+                    monomial_column(c, b * 32 + lane, nk, no, CT + lane);
+                    __syncwarp();
+                    const int kend = min(32, nkp - b * 32);
+                    for (int k0 = 0; k0 < kend; k0 += 4) {
+                        const int k = k0 + kk;
+                        const double* ctk = CT + k + jj * CB;
+                        const double w = W[b * 32 + k];
+                        double cf[T], wf[T];
 #pragma unroll
-                    for (int t = 0; t < T; ++t) {
-                        cf[t] = ctk[8 * t * CB];
-                        wf[t] = w * cf[t];
+                        for (int t = 0; t < T; ++t) {
+                            cf[t] = ctk[8 * t * CB];
+                            wf[t] = w * cf[t];
+                        }
+#pragma unroll
+                        for (int tj = 0; tj < T; ++tj)
+#pragma unroll
+                            for (int tm = 0; tm <= tj; ++tm) dmma884(acc[tj * (tj + 1) / 2 + tm], cf[tj], wf[tm]);
                     }
-#pragma unroll
-                    for (int tj = 0; tj < T; ++tj)
-#pragma unroll
-                        for (int tm = 0; tm <= tj; ++tm) dmma884(acc[tj * (tj + 1) / 2 + tm], cf[tj], wf[tm]);
                 }
                 // lower triangle, mirrored (make_A computes (w c_m) c_j for the full square; the mirror makes
-                // the matrix exactly symmetric, which the single-pass Ruiz sweep below relies on)
+                // the matrix exactly symmetric, which the equilibration below relies on)
 #pragma unroll
                 for (int tj = 0; tj < T; ++tj)
 #pragma unroll
@@ -332,12 +350,13 @@ __global__ void __launch_bounds__(PK<DIM, ORD>::MAXT, PK<DIM, ORD>::MINB) prepar
         if (nrmax < 1) { phase_barrier(); phase_barrier(); continue; }
         double a[RPL][NRP];
         double rj[RPL];
-        int roff[RPL];
+        int roff[RPL], ojs[RPL];
 #pragma unroll
         for (int t = 0; t < RPL; ++t) {
             const int j = jl + 32 * t;
             const bool valid = j < nr;
             const int oj = valid ? gR2O[j] : 0;
+            ojs[t] = oj;
             roff[t] = oj * CB;
             rj[t] = 1.0;
             const double* g = gG + oj * LDA;
@@ -372,55 +391,25 @@ __global__ void __launch_bounds__(PK<DIM, ORD>::MAXT, PK<DIM, ORD>::MINB) prepar
                 }
             }
         }
-        // A is exactly symmetric, so the reference's row and column passes coincide (DR == DC); the running
-        // reciprocal products row_j = 1/DRp_j are kept instead of dividing every entry.  The scale vector is
-        // double buffered (RS / DINV, which is free until the LU) so that a sweep needs one warp barrier.
-        // A fit that has converged stops updating while its warp-mates finish.
-        for (int i = jl; i < NRP; i += LPF) gRS[i] = gDINV[i] = 1.0;
-        __syncwarp();
+        // Equilibration (rescale_ruiz2001_c, lapackdrivers.pyx:553-623): the reference iterates r_j <- r_j / sqrt(scaled
+        // inf-norm of row j) until every row norm is within 1e-15 of 1 (8-11 sweeps over the matrix).  A is symmetric (row
+        // and column passes coincide) and positive definite, and for such a matrix that iteration has exactly ONE fixed
+        // point: |s_jm| < sqrt(s_jj s_mm) (Cauchy-Schwarz) means a row maximum of 1 can only sit on the diagonal, so
+        // s_jj = 1 for all j, i.e. r_j = a_jj^(-1/2).  The fixed point is evaluated directly (the reference's converged
+        // scaled matrices have diag = 1 +- 2e-15 on every seeded and golden case).  The sweeps themselves live on in the
+        // shared-memory variant of this kernel (wlsqm_prepare_smem.cu, WLSQM_PREP_KERNEL=smem), against which
+        // tests/test_gpu_variants.py compares this one.  Singular matrices (nk < nr) have no unique fixed point -- and no
+        // meaningful fit in the reference either.
         {
-            bool done = nr < 1;
-            double* rs_cur = gRS;
-            double* rs_nxt = gDINV;
-            for (int it = 0; it < 100; ++it) {
-                double mx[RPL][4];
+            for (int i = jl; i < NRP; i += LPF) gRS[i] = 1.0;       // (padding columns: finite scale for the zero entries)
 #pragma unroll
-                for (int t = 0; t < RPL; ++t) mx[t][0] = mx[t][1] = mx[t][2] = mx[t][3] = 0.0;
-#pragma unroll
-                for (int m = 0; m < NRP; m += 4) {
-                    const double2 r2 = ld2(rs_cur + m), r3 = ld2(rs_cur + m + 2);
-#pragma unroll
-                    for (int t = 0; t < RPL; ++t) {
-                        mx[t][0] = max_nn(mx[t][0], fabs(a[t][m]) * r2.x);
-                        mx[t][1] = max_nn(mx[t][1], fabs(a[t][m + 1]) * r2.y);
-                        mx[t][2] = max_nn(mx[t][2], fabs(a[t][m + 2]) * r3.x);
-                        mx[t][3] = max_nn(mx[t][3], fabs(a[t][m + 3]) * r3.y);
-                    }
+            for (int t = 0; t < RPL; ++t) {
+                const int j = jl + 32 * t;                          // (the same lane wrote gRS[j] just above)
+                if (j < nr) {
+                    rj[t] = rsqrt(gG[ojs[t] * LDA + ojs[t]]);
+                    gRS[j] = rj[t];
                 }
-                bool conv = true;
-#pragma unroll
-                for (int t = 0; t < RPL; ++t) {
-                    const int j = jl + 32 * t;
-                    if (j < nr) {
-                        if (!done) {
-                            // = DR_j^2, the scaled inf-norm of row j
-                            const double m2 = max_nn(max_nn(mx[t][0], mx[t][1]), max_nn(mx[t][2], mx[t][3])) * rj[t];
-                            conv = conv && (fabs(1.0 - m2) < 1e-15);
-                            rj[t] *= rsqrt(m2);
-                        }
-                        rs_nxt[j] = rj[t];
-                    }
-                }
-                const unsigned cb = __ballot_sync(FULL, conv);
-                done = done || (((cb >> (grp * LPF)) & GMASK) == GMASK);
-                __syncwarp();
-                double* tmp = rs_cur; rs_cur = rs_nxt; rs_nxt = tmp;
-                if (__all_sync(FULL, done)) break;
             }
-            // the final scale vector lives in RS (P5 reads it there)
-#pragma unroll
-            for (int t = 0; t < RPL; ++t)
-                if (jl + 32 * t < nr) gRS[jl + 32 * t] = rj[t];
             __syncwarp();
         }
         // ---- A <- diag(row) A diag(col)  (lapackdrivers.pyx:293-299) -----------------------------
