@@ -236,6 +236,15 @@ WLSQM_API int wlsqm_msytrs(int n, int64_t nlhs, const double* UDU, const int32_t
 WLSQM_API int wlsqm_msysv(int n, int64_t nlhs, double* A, int32_t* ipiv, double* b, int device);
 WLSQM_API int wlsqm_msymmetrize(int n, int64_t nlhs, double* A, int device);
 
+/* ---- batched matrix equilibration: wlsqm/utils/lapackdrivers.pyx:285-847 --------------------------------------------
+ * do_rescale (:319-385) for every matrix of a batch: A (nrows, ncols, nlhs) Fortran-contiguous is scaled in place
+ * (apply_scaling_c, :293-299), row_scale (nrows, nlhs) / col_scale (ncols, nlhs) Fortran receive the factors
+ * (scaled_b = b * row_scale; x = scaled_x * col_scale).  algo = ScalingAlgo (:305-317): 1 columns (Euclidean), 2 rows,
+ * 3 two-pass, 4 Ruiz (2001), 5 SCALGM, 6 DGEEQU.  ok (int32[nlhs], may be NULL): 0 where DGEEQU met a zero row or
+ * column -- that matrix is left unscaled (the reference raises LinAlgError for it) -- else 1. */
+WLSQM_API int wlsqm_mrescale(int nrows, int ncols, int64_t nlhs, double* A, int algo, double* row_scale, double* col_scale,
+                   int32_t* ok, int device);
+
 #ifdef __cplusplus
 }
 #endif

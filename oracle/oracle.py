@@ -389,3 +389,113 @@ def load_reference(variant: str = "generic"):
     if Path(mod.__file__).resolve().parent.parent != Path(ref).resolve():
         return None      # another variant is already imported in this process
     return mod
+
+
+# ---- matrix scaling: restatement of wlsqm/utils/lapackdrivers.pyx:285-847 (test infrastructure) -----------------------
+def do_rescale(A, algo):
+    """do_rescale (lapackdrivers.pyx:319-385): scales the (nrows, ncols) matrix A in place, returns (row_scale, col_scale).
+    algo: 1 rescale_columns_c (:412-424), 2 rescale_rows_c (:441-453), 3 rescale_twopass_c (:474-495), 4 rescale_ruiz2001_c
+    (:553-623), 5 rescale_scalgm_c (:626-847), 6 rescale_dgeequ_c (:517-523 -> LAPACK DGEEQU).  Plain Python loops in the
+    reference's order of operations (small matrices only).  Raises numpy.linalg.LinAlgError where the reference does."""
+    import math
+    nrows, ncols = A.shape
+    rs, cs = [1.0] * nrows, [1.0] * ncols
+    a = [[float(A[j, m]) for m in range(ncols)] for j in range(nrows)]
+    eps = 1e-15                                                                  # lapackdrivers.pyx:87
+
+    def cols_eucl():
+        for m in range(ncols):
+            c, acc = cs[m], 0.0
+            for j in range(nrows):
+                tmp = a[j][m] * (c * rs[j])
+                acc += tmp * tmp
+            cs[m] /= math.sqrt(acc)
+
+    def rows_eucl():
+        for j in range(nrows):
+            r, acc = rs[j], 0.0
+            for m in range(ncols):
+                tmp = a[j][m] * (r * cs[m])
+                acc += tmp * tmp
+            rs[j] /= math.sqrt(acc)
+
+    if algo == 1:
+        cols_eucl()
+    elif algo == 2:
+        rows_eucl()
+    elif algo == 3:
+        cols_eucl()
+        rows_eucl()
+    elif algo == 6:
+        # DGEEQU (LAPACK 3.x dgeequ.f): smlnum = dlamch('S'), bignum = 1 / smlnum
+        sml = sys.float_info.min
+        big = 1.0 / sml
+        r = [max(abs(a[j][m]) for m in range(ncols)) for j in range(nrows)]
+        if min(r) == 0.0:
+            raise np.linalg.LinAlgError("Matrix scaling failed (e.g. singular row or column).")
+        rs = [1.0 / min(max(v, sml), big) for v in r]
+        c = [max(abs(a[j][m]) * rs[j] for j in range(nrows)) for m in range(ncols)]
+        if min(c) == 0.0:
+            raise np.linalg.LinAlgError("Matrix scaling failed (e.g. singular row or column).")
+        cs = [1.0 / min(max(v, sml), big) for v in c]
+    elif algo == 4:
+        drp, dcp = [1.0] * nrows, [1.0] * ncols
+        for _k in range(100):
+            dr = [math.sqrt(max([0.0] + [abs(a[j][m] / (drp[j] * dcp[m])) for m in range(ncols)])) for j in range(nrows)]
+            dc = [math.sqrt(max([0.0] + [abs(a[j][m] / (dcp[m] * drp[j])) for j in range(nrows)])) for m in range(ncols)]
+            for j in range(nrows):
+                drp[j] *= dr[j]
+                rs[j] /= dr[j]
+            for m in range(ncols):
+                dcp[m] *= dc[m]
+                cs[m] /= dc[m]
+            if max(abs(1.0 - v * v) for v in dr) < eps and max(abs(1.0 - v * v) for v in dc) < eps:
+                break
+    elif algo == 5:
+        def up(vals):          # smallest non-zero magnitude (:664-683)
+            acc = 0.0
+            for tmp in vals:
+                if acc == 0.0 or (tmp > 0.0 and tmp < acc):
+                    acc = tmp
+            return 1.0 / acc if acc != 0.0 else math.inf
+
+        def down(vals):        # largest magnitude (:712-731)
+            acc = 0.0
+            for tmp in vals:
+                if tmp > acc:
+                    acc = tmp
+            return 1.0 / acc if acc != 0.0 else math.inf
+
+        def rows(f, mod_cs):
+            if mod_cs is None:
+                return [f([abs(a[j][m] * (rs[j] * cs[m])) for m in range(ncols)]) for j in range(nrows)]
+            return [f([abs(a[j][m] * (rs[j] * cs[m] * mod_cs[m])) for m in range(ncols)]) for j in range(nrows)]
+
+        def cols(f, mod_rs):
+            if mod_rs is None:
+                return [f([abs(a[j][m] * (cs[m] * rs[j])) for j in range(nrows)]) for m in range(ncols)]
+            return [f([abs(a[j][m] * (cs[m] * rs[j] * mod_rs[j])) for j in range(nrows)]) for m in range(ncols)]
+        mode = 1
+        for _k in range(100):
+            for f in ((up, down) if mode == 1 else (down,)):
+                dr1 = rows(f, None)
+                dc1 = cols(f, dr1)
+                dc2 = cols(f, None)
+                dr2 = rows(f, dc2)
+                for j in range(nrows):
+                    rs[j] *= math.sqrt(dr1[j] * dr2[j])
+                for m in range(ncols):
+                    cs[m] *= math.sqrt(dc1[m] * dc2[m])
+            er = max(abs(1.0 - max([0.0] + [abs(a[j][m] * (rs[j] * cs[m])) for m in range(ncols)])) for j in range(nrows))
+            ec = max(abs(1.0 - max([0.0] + [abs(a[j][m] * (cs[m] * rs[j])) for j in range(nrows)])) for m in range(ncols))
+            if er < eps and ec < eps:
+                if mode == 1:
+                    mode = 2
+                else:
+                    break
+    else:
+        raise ValueError("Unknown algorithm identifier, got %d" % (algo))
+    for m in range(ncols):                                                        # apply_scaling_c (:293-299)
+        for j in range(nrows):
+            A[j, m] = a[j][m] * (rs[j] * cs[m])
+    return np.array(rs), np.array(cs)

@@ -1634,6 +1634,44 @@ int wlsqm_msysv(int n, int64_t nlhs, double* A, int32_t* ipiv, double* b, int de
     if (!A || !b) return fail(WLSQM_E_VALUE, "NULL argument");
     return lapack_common(n, nlhs, A, ipiv, b, device, 1, 1, 1);
 }
+// do_rescale (lapackdrivers.pyx:319-385) over a batch: scale every matrix in place, return the scale vectors
+int wlsqm_mrescale(int nrows, int ncols, int64_t nlhs, double* A, int algo, double* row_scale, double* col_scale, int32_t* ok,
+                   int device) {
+    if (nrows < 0 || ncols < 0 || nlhs < 0) return fail(WLSQM_E_VALUE, "nrows, ncols and nlhs must be >= 0");
+    if (algo < 1 || algo > 6) return fail(WLSQM_E_VALUE, "Unknown algorithm identifier, got %d", algo);
+    if (nrows == 0 || ncols == 0 || nlhs == 0) return WLSQM_OK;
+    if (!A || !row_scale || !col_scale) return fail(WLSQM_E_VALUE, "NULL argument");
+    if (wlsqm_device_count() < 1) return fail(WLSQM_E_CUDA, "no CUDA device available (there is no CPU fallback)");
+    CU(cudaSetDevice(device));
+    const size_t na = (size_t)nrows * ncols * nlhs * 8, nr = (size_t)nrows * nlhs * 8, nc = (size_t)ncols * nlhs * 8, nk = (size_t)nlhs * 4;
+    const bool a_dev = is_device_ptr(A), r_dev = is_device_ptr(row_scale), c_dev = is_device_ptr(col_scale);
+    const bool k_dev = ok ? is_device_ptr(ok) != 0 : true;
+    DevBuf ba, br, bc, bk;
+    int rc = WLSQM_OK;
+    if (!a_dev) rc = ba.reserve(na);
+    if (!rc && !r_dev) rc = br.reserve(nr);
+    if (!rc && !c_dev) rc = bc.reserve(nc);
+    if (!rc && !k_dev) rc = bk.reserve(nk);
+    auto done = [&](int r) { ba.release(); br.release(); bc.release(); bk.release(); return r; };
+    if (rc) return done(rc);
+    cudaStream_t st = caller_stream();
+    double* dA = a_dev ? A : (double*)ba.p;
+    double* dR = r_dev ? row_scale : (double*)br.p;
+    double* dC = c_dev ? col_scale : (double*)bc.p;
+    int* dK = ok ? (k_dev ? ok : (int*)bk.p) : nullptr;
+    cudaError_t e = cudaSuccess;
+    if (!a_dev) e = cudaMemcpyAsync(dA, A, na, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = launch_rescale(nrows, ncols, nlhs, dA, algo, dR, dC, dK, st);
+    if (e == cudaSuccess && !a_dev) e = cudaMemcpyAsync(A, dA, na, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess && !r_dev) e = cudaMemcpyAsync(row_scale, dR, nr, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess && !c_dev) e = cudaMemcpyAsync(col_scale, dC, nc, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess && ok && !k_dev) e = cudaMemcpyAsync(ok, dK, nk, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e == cudaErrorInvalidValue) return done(fail(WLSQM_E_VALUE, "a %d x %d matrix is too large for the shared-memory scaler", nrows, ncols));
+    if (e != cudaSuccess) return done(fail(WLSQM_E_CUDA, "batched rescale: %s", cudaGetErrorString(e)));
+    return done(WLSQM_OK);
+}
+
 int wlsqm_msymmetrize(int n, int64_t nlhs, double* A, int device) {
     if (n < 0 || nlhs < 0) return fail(WLSQM_E_VALUE, "n and nlhs must be >= 0");
     if (n == 0 || nlhs == 0) return WLSQM_OK;

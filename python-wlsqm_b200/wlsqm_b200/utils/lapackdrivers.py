@@ -3,8 +3,10 @@ symmetric counterparts ``msymmetric[p]``, ``msymmetricfactor[p]``, ``msymmetricf
 
 Host-side mirror of the batched families of ``wlsqm/utils/lapackdrivers.pyx`` (general: ``:1551-1723``, on the
 fitter's path; symmetric: ``:1107-1354`` and ``:204-278``).  The single-system convenience
-wrappers of that module (``general``, ``symmetric``, ``tridiag``, the ``rescale_*`` family, ...) solve one small
-system per call and have nothing to batch -- keep importing the reference for those.
+wrappers of that module (``general``, ``symmetric``, ``tridiag``, ...) solve one small system per call and have nothing
+to batch -- keep importing the reference for those.  The matrix-scaling family (``do_rescale`` and the six
+``rescale_*`` algorithms, ``:285-847``) is served as one batched kernel: ``mdo_rescale[p]`` scales nlhs matrices per
+launch, and ``do_rescale`` / ``rescale_*`` are the reference's single-matrix entry points on top of it.
 Layout is the reference's: ``A`` (n, n, nlhs) Fortran-contiguous, ``b`` (n, nlhs) Fortran,
 ``ipiv`` (n, nlhs) int32 Fortran, 1-based pivots; everything is overwritten in place; LAPACK's ``info``
 is not reported (the reference drops it too: a singular system silently yields inf/NaN).
@@ -18,7 +20,8 @@ import numpy as np
 
 from .. import _lib
 
-__all__ = ["ScalingAlgo", "mgeneral", "mgeneralp", "mgeneralfactor", "mgeneralfactorp", "mgeneralfactored", "mgeneralfactoredp",
+__all__ = ["ScalingAlgo", "do_rescale", "mdo_rescale", "mdo_rescalep", "rescale_columns", "rescale_rows", "rescale_twopass",
+           "rescale_ruiz2001", "rescale_scalgm", "rescale_dgeequ", "mgeneral", "mgeneralp", "mgeneralfactor", "mgeneralfactorp", "mgeneralfactored", "mgeneralfactoredp",
            "msymmetric", "msymmetricp", "msymmetricfactor", "msymmetricfactorp", "msymmetricfactored",
            "msymmetricfactoredp", "msymmetrize", "msymmetrizep"]
 
@@ -26,7 +29,7 @@ __all__ = ["ScalingAlgo", "mgeneral", "mgeneralp", "mgeneralfactor", "mgeneralfa
 class ScalingAlgo(IntEnum):
     """The reference's enum of matrix-scaling algorithms (``lapackdrivers.pyx:305-317``; plain ints, so comparisons with
     int literals work).  The fitter's ``prepare`` stage uses ``ALGO_RUIZ2001`` (``impl.pyx:620-689``) -- here phase P3 of
-    ``prepare_reg_kernel``; the single-matrix ``do_rescale`` / ``rescale_*`` wrappers themselves are not served."""
+    ``prepare_reg_kernel``; ``do_rescale`` / ``mdo_rescale`` below take any of them."""
     ALGO_COLS_EUCL = 1
     ALGO_ROWS_EUCL = 2
     ALGO_TWOPASS = 3
@@ -195,3 +198,85 @@ def msymmetricfactoredp(A, ipiv, b, ntasks=1, device=None):
 def msymmetrizep(A, ntasks=1, device=None):
     """``lapackdrivers.pyx:233-278``"""
     return msymmetrize(A, device)
+
+
+# ---- matrix scaling (equilibration): lapackdrivers.pyx:285-847 -------------------------------------------------------
+def mdo_rescale(A, algo, device=None):
+    """``do_rescale`` (``lapackdrivers.pyx:319-385``) for nlhs independent matrices in one launch (batched extension in the
+    reference's ``m*`` naming): A (nrows, ncols, nlhs) Fortran-contiguous is scaled in place; returns
+    ``(row_scale, col_scale)`` of shapes (nrows, nlhs) / (ncols, nlhs), Fortran order -- numpy arrays, or CUDA tensors if A
+    is one.  ``scaled_b = b * row_scale``, ``x = scaled_x * col_scale``.  ``algo``: a :class:`ScalingAlgo` value.
+    ``LinAlgError`` if ALGO_DGEEQU meets a zero row or column in any matrix (those matrices are left unscaled)."""
+    algo = int(algo)
+    if algo not in tuple(int(a) for a in ScalingAlgo):
+        raise ValueError("Unknown algorithm identifier, got %d" % (algo))
+    pa, sa, da = _f3(A, "A", np.float64, 3)
+    nrows, ncols, nlhs = sa
+    dev = _dev(device, da)
+    if da is not None:
+        import torch
+        rs = torch.empty((nlhs, nrows), dtype=torch.float64, device=A.device).t()
+        cs = torch.empty((nlhs, ncols), dtype=torch.float64, device=A.device).t()
+        ok = torch.ones((nlhs,), dtype=torch.int32, device=A.device)
+        pr, pc, pk = int(rs.data_ptr()), int(cs.data_ptr()), int(ok.data_ptr())
+    else:
+        rs = np.empty((nrows, nlhs), dtype=np.float64, order="F")
+        cs = np.empty((ncols, nlhs), dtype=np.float64, order="F")
+        ok = np.ones((nlhs,), dtype=np.int32)
+        pr, pc, pk = rs.ctypes.data, cs.ctypes.data, ok.ctypes.data
+    _lib.check(_lib.lib().wlsqm_mrescale(nrows, ncols, nlhs, pa, algo, pr, pc, pk, int(dev)))
+    bad = (ok == 0)
+    if bool(bad.any()):
+        idx = np.nonzero(bad.cpu().numpy() if da is not None else bad)[0]
+        raise np.linalg.LinAlgError("Matrix scaling failed (e.g. singular row or column) for %d of %d matrices, first: %d"
+                                    % (len(idx), nlhs, int(idx[0])))
+    return rs, cs
+
+
+def mdo_rescalep(A, algo, ntasks=1, device=None):
+    """``mdo_rescale`` with the ``*p`` signature (``ntasks`` has no meaning on the GPU)"""
+    return mdo_rescale(A, algo, device)
+
+
+def do_rescale(A, algo, device=None):
+    """Generic dispatcher for matrix scaling (preconditioning) routines (``lapackdrivers.pyx:319-385``): scales the
+    Fortran-contiguous (nrows, ncols) matrix A in place and returns ``(row_scale, col_scale)``."""
+    algo = int(algo)
+    if algo not in tuple(int(a) for a in ScalingAlgo):
+        raise ValueError("Unknown algorithm identifier, got %d" % (algo))
+    pa, sa, da = _f3(A, "A", np.float64, 2)
+    if da is not None:
+        rs, cs = mdo_rescale(A.unsqueeze(2), algo, device)
+    else:
+        rs, cs = mdo_rescale(A.reshape(sa[0], sa[1], 1, order="F"), algo, device)     # a view: A itself is scaled
+    return rs[:, 0], cs[:, 0]
+
+
+def rescale_columns(A, device=None):
+    """column scaling only, Euclidean norm (``lapackdrivers.pyx:394-424``)"""
+    return do_rescale(A, ScalingAlgo.ALGO_COLS_EUCL, device)
+
+
+def rescale_rows(A, device=None):
+    """row scaling only, Euclidean norm (``lapackdrivers.pyx:427-453``)"""
+    return do_rescale(A, ScalingAlgo.ALGO_ROWS_EUCL, device)
+
+
+def rescale_twopass(A, device=None):
+    """columns first, then rows (``lapackdrivers.pyx:456-495``)"""
+    return do_rescale(A, ScalingAlgo.ALGO_TWOPASS, device)
+
+
+def rescale_dgeequ(A, device=None):
+    """LAPACK's DGEEQU (``lapackdrivers.pyx:498-523``)"""
+    return do_rescale(A, ScalingAlgo.ALGO_DGEEQU, device)
+
+
+def rescale_ruiz2001(A, device=None):
+    """simultaneous row and column scaling of Ruiz (2001), symmetry-preserving (``lapackdrivers.pyx:526-623``)"""
+    return do_rescale(A, ScalingAlgo.ALGO_RUIZ2001, device)
+
+
+def rescale_scalgm(A, device=None):
+    """SCALGM of Chiang and Chandler (2008) (``lapackdrivers.pyx:626-847``)"""
+    return do_rescale(A, ScalingAlgo.ALGO_SCALGM, device)

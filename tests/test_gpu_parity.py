@@ -427,3 +427,48 @@ def test_msymmetric_drivers_vs_reference_golden_and_lapack():
         ld.msymmetric(A_t, b_t)
         torch.cuda.synchronize()
         assert np.array_equal(b_t.cpu().numpy(), x)
+
+
+def test_batched_scalers_vs_reference_golden():
+    """mdo_rescale / do_rescale / rescale_* (SURVEY 8f item 4): one launch over a batch of matrices against the unmodified
+    reference's do_rescale applied matrix by matrix (tests/golden/golden_scale.npz) -- scale vectors and scaled matrices
+    bit for bit, for all six algorithms, square / rectangular / Gram-like batches; host arrays and CUDA tensors; the
+    DGEEQU failure (zero row) raises LinAlgError like the reference and leaves that matrix alone."""
+    from wlsqm_b200.utils import lapackdrivers as ld
+    torch = pytest.importorskip("torch")
+    g = np.load(parity.GOLDEN_DIR / "golden_scale.npz")
+    for nm in (str(s) for s in g["names"]):
+        A = g[f"{nm}/A"]
+        for algo in ld.ScalingAlgo:
+            M = np.asfortranarray(A.copy())
+            rs, cs = ld.mdo_rescale(M, algo)
+            a = int(algo)
+            assert np.array_equal(rs, g[f"{nm}/rs{a}"]), (nm, a)
+            assert np.array_equal(cs, g[f"{nm}/cs{a}"]), (nm, a)
+            assert np.array_equal(M, g[f"{nm}/S{a}"]), (nm, a)
+            # CUDA tensors, zero copy (Fortran order = permuted view of a C-contiguous tensor)
+            M_t = torch.from_numpy(np.ascontiguousarray(A.transpose(2, 1, 0))).cuda().permute(2, 1, 0)
+            rs_t, cs_t = ld.mdo_rescalep(M_t, a, ntasks=4)
+            torch.cuda.synchronize()
+            assert np.array_equal(rs_t.cpu().numpy(), rs) and np.array_equal(cs_t.cpu().numpy(), cs)
+            assert np.array_equal(M_t.cpu().numpy(), M)
+        # the reference's single-matrix entry points
+        for fn, a in ((ld.rescale_columns, 1), (ld.rescale_rows, 2), (ld.rescale_twopass, 3), (ld.rescale_ruiz2001, 4),
+                      (ld.rescale_scalgm, 5), (ld.rescale_dgeequ, 6)):
+            M1 = np.asfortranarray(A[:, :, 1].copy())
+            r1, c1 = fn(M1)
+            assert np.array_equal(r1, g[f"{nm}/rs{a}"][:, 1]) and np.array_equal(c1, g[f"{nm}/cs{a}"][:, 1])
+            assert np.array_equal(M1, g[f"{nm}/S{a}"][:, :, 1])
+    # Ruiz keeps a symmetric matrix symmetric (the reference's tests/test_lapackdrivers.py:90-98)
+    S = np.asfortranarray(g["gram15/A"][:, :, 3].copy())
+    ld.do_rescale(S, ld.ScalingAlgo.ALGO_RUIZ2001)
+    assert np.allclose(S, S.T, rtol=0, atol=1e-15)
+    # DGEEQU on a matrix with a zero row: LinAlgError (tests/test_lapackdrivers.py:109-115); the other matrices are scaled
+    B = np.asfortranarray(g["sq3/A"][:, :, :4].copy())
+    B[1, :, 2] = 0.0
+    B0 = B.copy()
+    with pytest.raises(np.linalg.LinAlgError):
+        ld.mdo_rescale(B, ld.ScalingAlgo.ALGO_DGEEQU)
+    assert np.array_equal(B[:, :, 2], B0[:, :, 2]) and np.array_equal(B[:, :, 0], g["sq3/S6"][:, :, 0])
+    with pytest.raises(ValueError, match="Unknown algorithm"):
+        ld.do_rescale(np.asfortranarray(np.eye(3)), 9)
