@@ -24,6 +24,8 @@ from .. import _lib
 
 __all__ = ["number_of_dofs", "ExpertSolver"]
 
+BINDING = "ctypes"
+
 
 def number_of_dofs(dimension, order):
     """Number of DOFs for given dimension (1,2,3) and order (0..4); -1 / -2 for a bad dimension / order
@@ -36,15 +38,10 @@ def number_of_dofs(dimension, order):
     return defs.NUMBER_OF_DOFS[dimension][order]
 
 
-class NoneIntegerError(TypeError, ValueError):
-    """``None`` where a C int is expected.  The reference's source raises ``ValueError("... cannot be None")``
-    (``expert.pyx:140-149``), but its typed signature (``int algorithm=...``, ``expert.pyx:92-93``) makes Cython refuse the
-    call first with ``TypeError("an integer is required")``; code written against either catches this."""
-
-
 def _as_c_int(v, name):
+    """typed `int` arguments of the reference (expert.pyx:92-93): Cython refuses None with TypeError"""
     if v is None:
-        raise NoneIntegerError(f"{name} cannot be None (an integer is required)")
+        raise TypeError(f"{name}: an integer is required")
     return int(v)
 
 
@@ -458,3 +455,13 @@ class _DeviceModelIndex:
             return None, It
         _lib.check(_lib.lib().wlsqm_solver_nearest_models(s._handle, xa.ptr, x_s0, nx, I.ctypes.data))
         return None, I
+
+
+# ---- the shipped binding is the Cython shim (wlsqm_b200/_shim.pyx); this module's ctypes twin above is the fallback ------
+import os as _os
+
+if _os.environ.get("WLSQM_BINDING", "cython") != "ctypes":
+    try:
+        from .._shim import ExpertSolver, number_of_dofs, _DeviceModelIndex, BINDING     # noqa: F401,F811
+    except ImportError:      # the shim has not been built (python-wlsqm_b200/build_shim.py): ctypes serves the same API
+        pass

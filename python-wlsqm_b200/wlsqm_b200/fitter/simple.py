@@ -39,8 +39,7 @@ def _fit_many(dim, xk, fk, nk, xi, fi, sens, do_sens, order, knowns, weighting_m
     if order_a.shape[0] != ncases or knowns_a.shape[0] != ncases or wm_a.shape[0] != ncases:
         raise ValueError("nk, order, knowns and weighting_method must have the same length")
     if max_iter is None or do_sens is None:      # typed `int` arguments of the reference: Cython raises TypeError
-        from .expert import NoneIntegerError
-        raise NoneIntegerError("do_sens and max_iter cannot be None (an integer is required)")
+        raise TypeError("do_sens / max_iter: an integer is required")
     if ncases < 1:         # CaseManager_new (infra.pyx:308-360) refuses an empty batch
         raise ValueError("Must specify max_cases > 0 when creating a CaseManager.")
     do_sens = int(do_sens)
@@ -173,3 +172,18 @@ def _make(dim):
 for _d in (1, 2, 3):
     globals().update(_make(_d))
 del _d
+
+
+# ---- the shipped binding is the Cython shim (wlsqm_b200/_shim.pyx); the ctypes functions above are the fallback ----------
+import os as _os
+
+BINDING = "ctypes"
+if _os.environ.get("WLSQM_BINDING", "cython") != "ctypes":
+    try:
+        from .. import _shim as _s
+        for _n in __all__:
+            globals()[_n] = getattr(_s, _n)
+        BINDING = _s.BINDING
+        del _n, _s
+    except ImportError:      # the shim has not been built (python-wlsqm_b200/build_shim.py)
+        pass

@@ -63,7 +63,7 @@ def test_argument_validation_needs_no_device():
         w.ExpertSolver(2, nk, od[:1], kn, wm)
     with pytest.raises(ValueError, match="Dimension"):
         w.ExpertSolver(5, nk, od, kn, wm)
-    with pytest.raises(ValueError, match="algorithm"):
+    with pytest.raises(TypeError, match="integer"):      # typed `int algorithm` (expert.pyx:92-93): what the compiled reference raises
         w.ExpertSolver(2, nk, od, kn, wm, algorithm=None)
     with pytest.raises(ValueError, match="Unknown algorithm"):
         w.ExpertSolver(2, nk, od, kn, wm, algorithm=3)
@@ -205,8 +205,38 @@ def test_constructor_errors_match_the_live_reference():
         with pytest.raises(Exception) as e_new:
             w.ExpertSolver(*args, **kw)
         assert issubclass(e_new.type, e_ref.type), (what, e_ref.type, e_new.type, str(e_ref.value), str(e_new.value))
-    # None for a typed int: the reference's source says ValueError, its compiled signature raises TypeError -- both are caught
-    with pytest.raises(ValueError, match="cannot be None"):
+    # None for a typed int: the compiled signature of the reference refuses it with TypeError before its own
+    # `cannot be None` checks can run (expert.pyx:92-93 vs :140-149) -- the Cython shim here does exactly the same
+    with pytest.raises(TypeError, match="an integer is required"):
         w.ExpertSolver(2, nk, od, kn, wm, max_iter=None)
     with pytest.raises(TypeError, match="an integer is required"):
         w.fit_2D_many(np.zeros((2, 6, 2)), np.zeros((2, 6)), nk, np.zeros((2, 2)), np.zeros((2, 3)), None, None, od, kn, wm)
+
+
+def test_cython_shim_is_the_binding_and_ctypes_is_the_fallback():
+    """the shipped binding is the Cython C-ABI shim (wlsqm_b200/_shim.pyx, built by __graft_entry__.build()); with
+    WLSQM_BINDING=ctypes the ctypes twins serve the same names and the same validation errors"""
+    import subprocess
+    import sys
+    import wlsqm_b200 as w
+    from wlsqm_b200.fitter import expert, simple
+    assert expert.BINDING == "cython" and simple.BINDING == "cython", "build the shim: python python-wlsqm_b200/build_shim.py"
+    assert w.ExpertSolver.__module__ == "wlsqm_b200._shim" and w.fit_3D_iterative_many_parallel.__module__ == "wlsqm_b200._shim"
+    assert w.fit_2D_many_parallel.__name__ == "fit_2D_many_parallel"
+    with pytest.raises(ValueError, match="Buffer dtype mismatch"):          # Cython's own memoryview coercion error
+        w.fit_2D_many_parallel(np.zeros((3, 4, 2), np.float32), np.zeros((3, 4)), np.full(3, 4, np.int32), np.zeros((3, 2)),
+                               np.zeros((3, 6)), None, 0, np.full(3, 2, np.int32), np.zeros(3, np.int64), np.ones(3, np.int32))
+    with pytest.raises(ValueError, match="wrong number of dimensions"):
+        w.fit_2D_many_parallel(np.zeros((3, 4)), np.zeros((3, 4)), np.full(3, 4, np.int32), np.zeros((3, 2)),
+                               np.zeros((3, 6)), None, 0, np.full(3, 2, np.int32), np.zeros(3, np.int64), np.ones(3, np.int32))
+    with pytest.raises(TypeError):
+        w.fit_2D_many_parallel(np.zeros((3, 4, 2)), np.zeros((3, 4)), np.full(3, 4, np.int32), np.zeros((3, 2)),
+                               np.zeros((3, 6)), None, None, np.full(3, 2, np.int32), np.zeros(3, np.int64), np.ones(3, np.int32))
+    code = ("import sys; sys.path.insert(0, %r); import numpy as np, wlsqm_b200 as w\n"
+            "from wlsqm_b200.fitter import expert, simple\n"
+            "assert expert.BINDING == 'ctypes' and simple.BINDING == 'ctypes' and w.ExpertSolver.__module__.endswith('expert')\n"
+            "try:\n    w.ExpertSolver(2, np.zeros(2, np.int32), np.zeros(2, np.int32), np.zeros(2, np.int64), np.ones(2, np.int32), algorithm=None)\n"
+            "except TypeError: print('ok')\n" % str(ROOT / "python-wlsqm_b200"))
+    import os
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=dict(os.environ, WLSQM_BINDING="ctypes"))
+    assert r.stdout.strip() == "ok", r.stderr[-600:]
