@@ -3,7 +3,11 @@
 fraction per stage.  Not the driver's bench line (that is bench.py / configs[1]); this is the measurement
 behind DESIGN.md section 7 for the other kernels' variants.
 
-    python benchmarks/run_configs.py [--scale 1.0] [--only cfg3]
+    python benchmarks/run_configs.py [--scale 1.0] [--only cfg3] [--no-cpu]
+
+Beside every GPU figure stands the reference's own CPU figure for the same stage (lines with "impl": "reference-cpu"):
+the unmodified reference (oracle/_ref, OpenMP) on this box's host cores, on a bounded subsample of the same workload,
+chunked where one reference solver cannot hold the cases, best of ntasks in {8, all cores}.
 
 Inputs are generated on the device: xk = xi + h*U(-1,1)^dim (same shapes and conditioning class as kNN hoods,
 without a 4M-point kd-tree build on the host); data = the analytic field of workloads.py at xk.
@@ -62,6 +66,76 @@ def emit(config, stage, n, ms, bytes_per_unit, extra=None):
     print(json.dumps(line), flush=True)
 
 
+# ---- the reference on the host cores (the CPU figure beside every GPU figure) -------------------------------------------
+_REF = [None, False]
+
+
+def reference():
+    if not _REF[1]:
+        _REF[1] = True
+        try:
+            sys.path.insert(0, str(ROOT / "oracle"))
+            import os
+            os.environ.setdefault("OMP_WAIT_POLICY", "passive")
+            os.environ.setdefault("OPENBLAS_NUM_THREADS", "1")
+            import oracle as orc
+            _REF[0] = orc.load_reference()
+        except Exception as exc:
+            print("reference unavailable: %r" % (exc,), file=sys.stderr)
+    return _REF[0]
+
+
+def cpu_emit(config, stage, n, sec, extra=None):
+    line = {"impl": "reference-cpu", "config": config, "stage": stage, "n": n, "ms": round(1e3 * sec, 3), "per_s": n / sec}
+    if extra:
+        line.update(extra)
+    print(json.dumps(line), flush=True)
+
+
+def cpu_expert(config, n, dim, order, k, knowns, wm, algo, do_sens, max_iter=3, mixed=None, note=""):
+    """prepare + solve of the reference on n cases (one ExpertSolver: n must fit its int-sized arena)"""
+    import os
+    import time
+    ref = reference()
+    if ref is None:
+        return
+    g = torch.Generator().manual_seed(0)
+    h = 1e-2
+    xi = (h * n ** (1.0 / dim) * torch.rand((n, dim), dtype=torch.float64, generator=g))
+    xk = xi[:, None, :] + 1.5 * h * (2 * torch.rand((n, k, dim), dtype=torch.float64, generator=g) - 1)
+    fk = field(xk).numpy().copy()
+    no = NO[dim][order]
+    fi = np.zeros((n, no))
+    fi[:, 0] = field(xi).numpy()
+    xi_h, xk_h = xi.numpy(), xk.numpy()
+    if dim == 1:
+        xi_h, xk_h = np.ascontiguousarray(xi_h[:, 0]), np.ascontiguousarray(xk_h[:, :, 0])
+    nk, od, kn, w = np.full(n, k, np.int32), np.full(n, order, np.int32), np.full(n, knowns, np.int64), np.full(n, wm, np.int32)
+    if mixed is not None:
+        kn[::mixed[0]] = mixed[1]
+    sens = np.zeros((n, k, no)) if do_sens else None
+    cores = os.cpu_count() or 1
+    best = None
+    for nt in sorted({min(8, cores), cores}):
+        s = ref.ExpertSolver(dim, nk, od, kn, w, algorithm=algo, do_sens=do_sens, max_iter=max_iter, ntasks=nt)
+        t0 = time.perf_counter()
+        s.prepare(xi_h, xk_h)
+        tp = time.perf_counter() - t0
+        s.solve(fk, fi, sens)
+        ts = []
+        for _ in range(2):
+            t0 = time.perf_counter()
+            s.solve(fk, fi, sens)
+            ts.append(time.perf_counter() - t0)
+        del s
+        if best is None or min(ts) < best[1]:
+            best = (tp, min(ts), nt)
+    tp, tsv, nt = best
+    ex = {"ntasks": nt, "host_cores": cores, "sample": "%d cases in one reference ExpertSolver%s" % (n, note)}
+    cpu_emit(config, "prepare", n, tp, ex)
+    cpu_emit(config, "solve", n, tsv, ex)
+
+
 def make(n, dim, k, seed=0):
     g = torch.Generator(device="cuda").manual_seed(seed)
     h = 1e-2
@@ -111,7 +185,9 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--scale", type=float, default=1.0)
     ap.add_argument("--only", default="")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the reference's CPU figures")
     a = ap.parse_args()
+    cpu = not a.no_cpu
     sc = a.scale
     want = lambda c: (not a.only) or a.only in c
 
@@ -130,20 +206,46 @@ def main():
         fk_d = torch.from_numpy(fk_h).cuda()
         f = lambda: wlsqm.fit_2D_many_parallel(xk, fk_d, meta[0], xi, fi_d, None, 0, meta[1], meta[2], meta[3], ntasks=8)
         emit("cfg1 fit_2D_many_parallel 10k o2 k12 (CUDA tensors, one-shot)", "fit", n, timeit(f), None)
+        if cpu and reference() is not None:
+            import os
+            import time
+            ref = reference()
+            best = None
+            for nt in sorted({1, 8, os.cpu_count() or 1}):
+                for _ in range(3):
+                    t0 = time.perf_counter()
+                    ref.fit_2D_many_parallel(xk_h, fk_h, meta[0], xi_h, fi_h, None, 0, meta[1], meta[2], meta[3], ntasks=nt)
+                    d = time.perf_counter() - t0
+                    if best is None or d < best[0]:
+                        best = (d, nt)
+            cpu_emit("cfg1 fit_2D_many_parallel 10k o2 k12", "fit", n, best[0], {"ntasks": best[1], "sample": "the whole configuration"})
     if want("cfg2v"):
         run_expert("cfg2 variant 2D o4 k30 b2_F UNIFORM BASIC", int(1_000_000 * sc), 2, 4, 30, 1, 1, 1, False)
         run_expert("cfg2 2D o4 k30 knowns=0 CENTER ITERATIVE(3)", int(1_000_000 * sc), 2, 4, 30, 0, 2, 2, False)
+        if cpu:
+            cpu_expert("cfg2 variant 2D o4 k30 b2_F UNIFORM BASIC", 100_000, 2, 4, 30, 1, 1, 1, False, note=" (of 1M; <= 300k per solver)")
+            cpu_expert("cfg2 2D o4 k30 knowns=0 CENTER ITERATIVE(3)", 100_000, 2, 4, 30, 0, 2, 2, False, note=" (of 1M)")
     if want("cfg3"):
         n3 = int(2_000_000 * sc)     # --scale 2.0 = the full 4M-point configuration (140 GB: fits one B200)
         run_expert("cfg3 3D o4 k60 b3_F ITERATIVE(3) do_sens (%.3gM of 4M points on one GPU)" % (n3 / 1e6), n3, 3, 4, 60,
                    1, 2, 2, True)
         torch.cuda.empty_cache()
         run_expert("cfg3-basic 3D o4 k60 b3_F BASIC no sens", int(2_000_000 * sc), 3, 4, 60, 1, 2, 1, False)
+        if cpu:
+            # one reference solver holds at most ~76k cases of this configuration (27 928 B per case in an int-sized arena)
+            cpu_expert("cfg3 3D o4 k60 b3_F ITERATIVE(3) do_sens", 65_000, 3, 4, 60, 1, 2, 2, True,
+                       note=" = one chunk of the 62 the 4M points need; scale linearly")
+            cpu_expert("cfg3-basic 3D o4 k60 b3_F BASIC no sens", 65_000, 3, 4, 60, 1, 2, 1, False, note=" = one chunk")
     if want("cfg4"):
         run_expert("cfg4 2D o3 k24 UNIFORM, b2_F interior + b2_Y every 1000th", int(2_000_000 * sc), 2, 3, 24, 1, 1, 1, False,
                    mixed=(1000, wlsqm.b2_Y))
         run_expert("cfg4 1D o3 k8 UNIFORM, b1_F interior + b1_X every 1000th", int(2_000_000 * sc), 1, 3, 8, 1, 1, 1, False,
                    mixed=(1000, wlsqm.b1_X))
+        if cpu:
+            cpu_expert("cfg4 2D o3 k24 UNIFORM, b2_F interior + b2_Y every 1000th", 200_000, 2, 3, 24, 1, 1, 1, False,
+                       mixed=(1000, wlsqm.b2_Y), note=" (of 2M; <= 600k per solver)")
+            cpu_expert("cfg4 1D o3 k8 UNIFORM, b1_F interior + b1_X every 1000th", 200_000, 1, 3, 8, 1, 1, 1, False,
+                       mixed=(1000, wlsqm.b1_X), note=" (of 2M)")
     if want("cfg5"):
         n = int(1_000_000 * sc)
         s, xi, fi = run_expert("cfg5 cloud (cfg2)", n, 2, 4, 30, 0, 1, 1, False)
@@ -163,6 +265,37 @@ def main():
                 s.interpolate(xq, diff=d, I=I)
         ms15 = timeit(all15, reps=3, warm=1)
         emit("cfg5 interpolate d=0..14 (15 reference-style calls)", "interpolate", nq, ms15, 15 * (16 + 8 + 8 + 136 / 16))
+        if cpu and reference() is not None:
+            import os
+            import time
+            ref = reference()
+            nc = 100_000
+            gq = torch.Generator().manual_seed(5)
+            xi_c, xk_c = (t.cpu() for t in make(nc, 2, 30))
+            xi_h, xk_h = xi_c.numpy(), xk_c.numpy()
+            fk_h = field(xk_c).numpy().copy()
+            fi_h = np.zeros((nc, 15))
+            nt = os.cpu_count() or 1
+            sr = ref.ExpertSolver(2, np.full(nc, 30, np.int32), np.full(nc, 4, np.int32), np.zeros(nc, np.int64), np.full(nc, 1, np.int32),
+                                  algorithm=1, do_sens=False, ntasks=nt)
+            sr.prepare(xi_h, xk_h)
+            sr.solve(fk_h, fi_h)
+            Ih = np.repeat(np.arange(nc), 16)
+            xq_h = xi_h[Ih] + 0.3e-2 * (2 * torch.rand((16 * nc, 2), dtype=torch.float64, generator=gq).numpy() - 1)
+            t0 = time.perf_counter()
+            sr.prep_interpolate()
+            t_tree = time.perf_counter() - t0
+            t0 = time.perf_counter()
+            _, I0 = sr.interpolate(xq_h, mode='nearest', diff=0)          # first call: cKDTree.query inside
+            t_first = time.perf_counter() - t0
+            t0 = time.perf_counter()
+            for d in range(15):
+                sr.interpolate(xq_h, mode='nearest', diff=d, I=I0)
+            t15 = time.perf_counter() - t0
+            ex = {"ntasks": nt, "sample": "%d-point cloud, 16 queries per model (of 1M / 16M)" % nc}
+            cpu_emit("cfg5 prep_interpolate (cKDTree build over the model origins)", "interpolate", nc, t_tree, ex)
+            cpu_emit("cfg5 interpolate diff=0, first call (cKDTree.query for the model index inside)", "interpolate", 16 * nc, t_first, ex)
+            cpu_emit("cfg5 interpolate d=0..14 (15 reference-style calls, I reused)", "interpolate", 16 * nc, t15, ex)
 
 
 if __name__ == "__main__":

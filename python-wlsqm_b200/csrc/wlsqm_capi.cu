@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <new>
 #include <string>
 #include <vector>
@@ -290,10 +291,24 @@ bool config_prepare_reg(const wlsqm_solver* s, PrepRegParams& P, LaunchCfg& L, b
     const int fpw = prep_reg_fits_per_warp(s->dim, kord);
     const size_t per_warp = (size_t)P.warp_doubles * 8;
     if (per_warp > SMEM_PER_CTA) return false;
-    // CTA size: the one that keeps most warps resident (shared memory and registers both limit it)
+    // CTA size: the one that keeps most warps resident (shared memory and registers both limit it).  The answer depends
+    // only on (kernel instantiation, bytes per warp): remembered, so that a small one-shot fit does not pay sixteen
+    // occupancy queries (tens of microseconds) on every call.
     int best_w = 0, best_ctas = 0;
     const int force_w = env_int("WLSQM_PREP_WARPS", 0);
-    for (int w = 1; w <= PREP_REG_THREADS / 32; ++w) {
+    struct OccKey { int dim, ord, direct, force; size_t per_warp; int w, ctas; };
+    static std::mutex occ_mu;
+    static std::vector<OccKey> occ_cache;
+    {
+        std::lock_guard<std::mutex> lock(occ_mu);
+        for (const OccKey& k : occ_cache)
+            if (k.dim == s->dim && k.ord == kord && k.direct == (int)direct && k.force == force_w && k.per_warp == per_warp) {
+                best_w = k.w; best_ctas = k.ctas;
+                break;
+            }
+    }
+    const bool cached = best_w > 0;
+    for (int w = 1; !cached && w <= PREP_REG_THREADS / 32; ++w) {
         if (force_w > 0 && w != force_w) continue;
         if (w * per_warp > SMEM_PER_CTA) break;
         int c = 0;
@@ -307,6 +322,10 @@ bool config_prepare_reg(const wlsqm_solver* s, PrepRegParams& P, LaunchCfg& L, b
         if (w * c >= best_w * best_ctas) { best_w = w; best_ctas = c; }
     }
     if (best_w < 1 || best_ctas < 1) return false;
+    if (!cached) {
+        std::lock_guard<std::mutex> lock(occ_mu);
+        occ_cache.push_back(OccKey{s->dim, kord, (int)direct, force_w, per_warp, best_w, best_ctas});
+    }
     const int warps = best_w;
     int ctas = best_ctas;
     L.threads = warps * 32;
@@ -1015,17 +1034,17 @@ int wlsqm_solver_solve(wlsqm_solver_t* s, const double* fk, int64_t fk_s0, int64
         P.fi_in = (const double*)s->st_fi.p; P.fi_in_s0 = s->maxno;
     }
     const long long plane = (long long)s->maxnk * s->maxno;
-    if (s->do_sens) {
-        if (sens_dev) {
-            P.sens = sens; P.sens_s0 = sens_s0; P.sens_s1 = sens_s1;
-        } else {
-            rc = s->st_sens.reserve((size_t)n * plane * 8);
-            if (rc) return rc;
-            P.sens = (double*)s->st_sens.p; P.sens_s0 = plane; P.sens_s1 = s->maxno;
-        }
-    }
-    const bool sens_direct = s->do_sens && !sens_dev && s->uniform && s->uni.nk == s->maxnk &&
-                             sens_s1 == s->maxno && sens_s0 == plane;
+    // host sens: the kernel writes each chunk of cases into one of two rotating device buffers (2 x chunk x nk x no
+    // doubles -- not a mirror of the whole array, which is 67 GB for BASELINE.json configs[2]); a chunk goes back to the
+    // host while the next one is being computed
+    const bool sens_host = s->do_sens && !sens_dev;
+    if (s->do_sens && sens_dev) { P.sens = sens; P.sens_s0 = sens_s0; P.sens_s1 = sens_s1; }
+    // page-locked, dense, uniform: straight asynchronous copies; anything else (ordinary numpy memory, pitched rows,
+    // per-case nk / no) goes through the page-locked ring and is scattered by the host threads
+    const bool sens_direct = sens_host && s->uniform && s->uni.nk == s->maxnk && sens_s1 == s->maxno && sens_s0 == plane &&
+                             !is_pageable_host(sens);
+    const bool sens_drain = sens_host && !sens_direct;
+    constexpr int SENS_BUFS = 2;
 
     // ---- chunked pipeline: H2D of chunk i+1, kernel of chunk i and D2H of chunk i-1 overlap ------------
     // (device-resident arguments: one chunk, everything on the solver's stream, no synchronisation)
@@ -1033,10 +1052,17 @@ int wlsqm_solver_solve(wlsqm_solver_t* s, const double* fk, int64_t fk_s0, int64
     cudaStream_t s_in = st, s_out = st;
     if (staged) {
         chunk = std::max<long long>(1024, env_int("WLSQM_SOLVE_CHUNK", 65536));
+        if (sens_host) {
+            // a chunk of sens must fit a share of the ring slot granularity and keep the buffers modest
+            const long long cap = std::max<long long>(256, (long long)((1ull << 30) / ((size_t)std::max<long long>(plane, 1) * 8)));
+            chunk = std::min(chunk, cap);
+            rc = s->st_sens.reserve((size_t)SENS_BUFS * (size_t)std::min(chunk, n) * plane * 8);
+            if (rc) return rc;
+        }
         if (!s->s_in) CU(cudaStreamCreateWithFlags(&s->s_in, cudaStreamNonBlocking));
         if (!s->s_out) CU(cudaStreamCreateWithFlags(&s->s_out, cudaStreamNonBlocking));
         s_in = s->s_in; s_out = s->s_out;
-        const size_t nev = 2 * (size_t)((n + chunk - 1) / chunk) + 1;
+        const size_t nev = 2 * (size_t)((n + chunk - 1) / chunk) + 1 + SENS_BUFS;
         while (s->events.size() < nev) {
             cudaEvent_t e;
             CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -1056,8 +1082,9 @@ int wlsqm_solver_solve(wlsqm_solver_t* s, const double* fk, int64_t fk_s0, int64
         bool on = false;
         ~RingGuard() { if (on) bounce_unlock(); }
     } ring_guard;
+    const bool fi_scatter = !fi_dev && !s->uniform_no;       // per-case row lengths: unpacked by the host threads
     BouncePair* rings = nullptr;
-    if (fk_bounce || fi_bounce) {
+    if (fk_bounce || fi_bounce || sens_drain || fi_scatter) {
         bounce_lock();
         ring_guard.on = true;
         rings = &bounce_rings(s->device);
@@ -1070,10 +1097,42 @@ int wlsqm_solver_solve(wlsqm_solver_t* s, const double* fk, int64_t fk_s0, int64
         CU(d2h_bounced_finish(rings->out, p.slot, fi + p.c0 * fi_s0, fi_s0, p.rows, s->uni.no));
         return WLSQM_OK;
     };
+    // one chunk of sens from its device buffer to the caller's host array (first nk_j rows x no_j columns of every case)
+    struct SensChunk { long long c0 = 0, rows = 0; const double* buf = nullptr; bool live = false; } sens_prev;
+    auto drain_sens = [&](const SensChunk& ch) -> int {
+        while (!pend.empty()) { int r2 = finish_oldest(); if (r2) return r2; }      // (the ring is shared with the fi pieces)
+        const cudaError_t e2 = d2h_pieces(rings->out, ch.buf, ch.rows, plane, s_out, [&](const double* piece, long long r0, long long nr) {
+            par_for((size_t)nr, [&](size_t lo, size_t hi) {
+                for (size_t r = lo; r < hi; ++r) {
+                    const long long i = ch.c0 + r0 + (long long)r;
+                    const CaseMeta& m = s->hmeta.size() > (size_t)i ? s->hmeta[(size_t)i] : s->uni;
+                    if (m.nr < 1) continue;     // silent no-op case: sens untouched (impl.pyx:742)
+                    const double* src = piece + r * plane;
+                    double* dst = sens + i * sens_s0;
+                    if (m.no == s->maxno && sens_s1 == s->maxno) memcpy(dst, src, (size_t)m.nk * m.no * 8);
+                    else
+                        for (int k = 0; k < m.nk; ++k) memcpy(dst + (long long)k * sens_s1, src + (size_t)k * s->maxno, (size_t)m.no * 8);
+                }
+            });
+        });
+        if (e2 != cudaSuccess) return fail(WLSQM_E_CUDA, "device -> host staging of sens: %s", cudaGetErrorString(e2));
+        return WLSQM_OK;
+    };
     LaunchCfg L;
     size_t ev = 0;
-    for (long long c0 = 0; c0 < n; c0 += chunk) {
+    long long chunk_index = 0;
+    const size_t sens_ev0 = s->events.size() >= (size_t)SENS_BUFS ? s->events.size() - 1 - SENS_BUFS : 0;   // (staged: reserved above)
+    for (long long c0 = 0; c0 < n; c0 += chunk, ++chunk_index) {
         const long long c1 = std::min(n, c0 + chunk), rows = c1 - c0;
+        const int sb = (int)(chunk_index % SENS_BUFS);
+        double* sens_buf = nullptr;
+        if (sens_host) {
+            sens_buf = (double*)s->st_sens.p + (size_t)sb * (size_t)std::min(chunk, n) * plane;
+            // the kernel indexes sens by the global case number: bias the base so that case c0 lands at the buffer's start
+            P.sens = reinterpret_cast<double*>(reinterpret_cast<uintptr_t>(sens_buf) - (uintptr_t)c0 * (uintptr_t)plane * 8u);
+            P.sens_s0 = plane; P.sens_s1 = s->maxno;
+            if (sens_direct && chunk_index >= SENS_BUFS) CU(cudaStreamWaitEvent(st, s->events[sens_ev0 + sb], 0));   // its last copy out is done
+        }
         if (fk_bounce) {
             CU(h2d_bounced(rings->in, (double*)s->st_fk.p + c0 * s->maxnk, fk + c0 * fk_s0, rows, s->maxnk, fk_s0, s_in));
         } else if (!fk_dev) {
@@ -1100,6 +1159,12 @@ int wlsqm_solver_solve(wlsqm_solver_t* s, const double* fk, int64_t fk_s0, int64
             if (rc) return rc;
             CU(launch_solve(s->dim, P, L.blocks, L.threads, L.smem, st));
         }
+        if (sens_drain) {
+            // the previous chunk goes to the host while this one is being computed (its copies were queued on s_out
+            // before s_out is told to wait for this chunk's kernel)
+            if (sens_prev.live) { rc = drain_sens(sens_prev); if (rc) return rc; }
+            sens_prev.c0 = c0; sens_prev.rows = rows; sens_prev.buf = sens_buf; sens_prev.live = true;
+        }
         if (staged) {
             CU(cudaEventRecord(s->events[ev], st));
             CU(cudaStreamWaitEvent(s_out, s->events[ev], 0));
@@ -1114,32 +1179,27 @@ int wlsqm_solver_solve(wlsqm_solver_t* s, const double* fk, int64_t fk_s0, int64
             rc = from_dense(fi + c0 * fi_s0, fi_s0, s->fi_case + c0 * s->maxno, s->maxno, rows, s->uni.no, s_out);
             if (rc) return rc;
         }
-        if (sens_direct)
-            CU(cudaMemcpyAsync(sens + c0 * plane, (const double*)s->st_sens.p + c0 * plane, (size_t)rows * plane * 8,
-                               cudaMemcpyDeviceToHost, s_out));
+        if (sens_direct) {
+            CU(cudaMemcpyAsync(sens + c0 * plane, sens_buf, (size_t)rows * plane * 8, cudaMemcpyDeviceToHost, s_out));
+            CU(cudaEventRecord(s->events[sens_ev0 + sb], s_out));
+        }
     }
+    if (sens_drain && sens_prev.live) { rc = drain_sens(sens_prev); if (rc) return rc; }
     while (!pend.empty()) { rc = finish_oldest(); if (rc) return rc; }
     if (deferred) CU(launch_scatter_fi(s->dmeta, s->uni, n, s->fi_case, s->maxno, fi, fi_s0, st));
 
-    // ---- results that need a host-side scatter (heterogeneous no / nk, pitched sens) ---------------------
-    if (!fi_dev && !s->uniform_no) {
-        std::vector<double> tmp((size_t)n * s->maxno);
-        CU(cudaMemcpyAsync(tmp.data(), s->fi_case, tmp.size() * 8, cudaMemcpyDeviceToHost, s_out));
-        CU(cudaStreamSynchronize(s_out));
-        for (long long i = 0; i < n; ++i)
-            memcpy(fi + i * fi_s0, tmp.data() + (size_t)i * s->maxno, (size_t)s->hmeta[(size_t)i].no * 8);
-    }
-    if (s->do_sens && !sens_dev && !sens_direct) {
-        std::vector<double> tmp((size_t)n * plane);
-        CU(cudaMemcpyAsync(tmp.data(), s->st_sens.p, tmp.size() * 8, cudaMemcpyDeviceToHost, s_out));
-        CU(cudaStreamSynchronize(s_out));
-        for (long long i = 0; i < n; ++i) {
-            const CaseMeta& m = s->hmeta.size() > (size_t)i ? s->hmeta[(size_t)i] : s->uni;
-            if (m.nr < 1) continue;     // silent no-op case: sens untouched
-            for (int k = 0; k < m.nk; ++k)
-                memcpy(sens + i * sens_s0 + (long long)k * sens_s1, tmp.data() + (size_t)i * plane + (size_t)k * s->maxno,
-                       (size_t)m.no * 8);
-        }
+    // ---- fi with per-case row lengths: pieces through the page-locked ring, scattered by the host threads ----------
+    if (fi_scatter) {
+        const int ld = s->maxno;
+        const cudaError_t e2 = d2h_pieces(rings->out, s->fi_case, n, ld, s_out, [&](const double* piece, long long r0, long long nr) {
+            par_for((size_t)nr, [&](size_t lo, size_t hi) {
+                for (size_t r = lo; r < hi; ++r) {
+                    const long long i = r0 + (long long)r;
+                    memcpy(fi + i * fi_s0, piece + r * ld, (size_t)s->hmeta[(size_t)i].no * 8);
+                }
+            });
+        });
+        if (e2 != cudaSuccess) return fail(WLSQM_E_CUDA, "device -> host staging of fi: %s", cudaGetErrorString(e2));
     }
     int32_t it = 0;
     if (iter) CU(cudaMemcpyAsync(&it, s->iters_dev, 4, cudaMemcpyDeviceToHost, st));

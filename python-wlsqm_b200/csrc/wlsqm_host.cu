@@ -211,6 +211,46 @@ cudaError_t d2h_bounced_finish(BounceRing& ring, int slot, double* dst, long lon
     return cudaSuccess;
 }
 
+cudaError_t d2h_pieces(BounceRing& ring, const double* src, long long rows, long long width, cudaStream_t stream,
+                       const std::function<void(const double*, long long, long long)>& unpack) {
+    if (rows <= 0 || width <= 0) return cudaSuccess;
+    cudaError_t e = ring.init();
+    if (e != cudaSuccess) return e;
+    const size_t row_bytes = (size_t)width * 8;
+    if (row_bytes > BOUNCE_SLOT_BYTES) return cudaErrorInvalidValue;
+    const long long per = std::max<long long>(1, (long long)(BOUNCE_SLOT_BYTES / row_bytes));
+    struct Piece { long long r0, nr; int s; };
+    Piece prev{0, 0, -1};
+    auto finish = [&](const Piece& p) -> cudaError_t {
+        cudaError_t e2 = cudaEventSynchronize(ring.ev[p.s]);
+        if (e2 != cudaSuccess) return e2;
+        ring.busy[p.s] = false;
+        unpack((const double*)ring.slot[p.s], p.r0, p.nr);
+        return cudaSuccess;
+    };
+    for (long long r0 = 0; r0 < rows; r0 += per) {
+        const long long nr = std::min(per, rows - r0);
+        const int s = ring.next;
+        ring.next = (ring.next + 1) % BOUNCE_SLOTS;
+        if (ring.busy[s]) {
+            e = cudaEventSynchronize(ring.ev[s]);
+            if (e != cudaSuccess) return e;
+            ring.busy[s] = false;
+        }
+        e = cudaMemcpyAsync(ring.slot[s], src + r0 * width, (size_t)nr * row_bytes, cudaMemcpyDeviceToHost, stream);
+        if (e == cudaSuccess) e = cudaEventRecord(ring.ev[s], stream);
+        if (e != cudaSuccess) return e;
+        ring.busy[s] = true;
+        if (prev.s >= 0) {
+            e = finish(prev);
+            if (e != cudaSuccess) return e;
+        }
+        prev = Piece{r0, nr, s};
+    }
+    if (prev.s >= 0) e = finish(prev);
+    return e;
+}
+
 cudaError_t d2h_bounced(BounceRing& ring, double* dst, long long pitch, const double* src, long long src_pitch, long long rows,
                         long long width, cudaStream_t stream) {
     if (rows <= 0 || width <= 0) return cudaSuccess;

@@ -53,6 +53,13 @@ int d2h_bounced_begin(BounceRing& ring, const double* src, long long src_pitch, 
                       cudaStream_t stream);
 cudaError_t d2h_bounced_finish(BounceRing& ring, int slot, double* dst, long long pitch, long long rows, long long width);
 
+// Device -> host in pieces of at most one ring slot, unpacked by the caller: for every piece, rows [r0, r0 + nr) of the
+// dense device array `src` (rows of `width` doubles) arrive in a page-locked slot and `unpack(slot, r0, nr)` runs on the
+// calling thread (it may use par_for) while the device copy of the next piece is already in flight.  For results whose
+// host layout is not a plain strided array (per-case row lengths).  Copies already queued on `stream` are honoured.
+cudaError_t d2h_pieces(BounceRing& ring, const double* src, long long rows, long long width, cudaStream_t stream,
+                       const std::function<void(const double*, long long, long long)>& unpack);
+
 // Device -> host (pageable), rows of `width` doubles from dense device rows of `src_pitch` doubles into host rows of
 // `pitch` doubles.  Copies already queued on `stream` are honoured; returns when the host array holds the data.
 cudaError_t d2h_bounced(BounceRing& ring, double* dst, long long pitch, const double* src, long long src_pitch, long long rows,

@@ -306,3 +306,48 @@ def test_host_xk_with_a_longer_last_axis_and_list_outputs():
     assert np.array_equal(fi_c, fi_d)
     with pytest.raises((TypeError, ValueError)):
         s.solve(fk, fi_c.tolist())
+
+
+@pytest.mark.parametrize("hetero", [False, True])
+def test_host_sens_and_fi_go_back_in_chunks(hetero, monkeypatch):
+    """host sens / fi of a many-chunk batch: the kernel writes sens into two rotating chunk buffers (no device mirror of the
+    whole array) and the chunks go back through the page-locked ring (ordinary numpy memory, per-case nk / no) or by
+    direct asynchronous copies (page-locked, dense, uniform); same bits as the device-tensor path"""
+    torch = pytest.importorskip("torch")
+    monkeypatch.setenv("WLSQM_SOLVE_CHUNK", "4096")
+    n, k, dim = 30_000, 14, 2
+    x, hoods, f = parity.make_case(n, dim, k)
+    xk, fk = parity.gathered(x, f, hoods)
+    rng = np.random.default_rng(9)
+    if hetero:
+        od = rng.integers(1, 4, n).astype(np.int32)
+        nk = rng.integers(11, k + 1, n).astype(np.int32)
+        kn = rng.integers(0, 2, n).astype(np.int64)
+        kn[::17] = (1 << 3) - 1          # all DOFs of an order-1 model known where od == 1: a silent no-op case
+    else:
+        od, nk, kn = np.full(n, 3, np.int32), np.full(n, k, np.int32), np.full(n, 1, np.int64)
+    wm = np.full(n, 2, np.int32)
+    no = 10
+    fi0 = rng.standard_normal((n, no)); fi0[:, 0] = f
+    s = wlsqm.ExpertSolver(dim, nk, od, kn, wm, do_sens=True)
+    s.prepare(x, xk)
+    fi_d = torch.from_numpy(fi0).cuda()
+    sens_d = torch.full((n, k, no), -7.0, dtype=torch.float64, device="cuda")
+    s.solve(torch.from_numpy(fk).cuda(), fi_d, sens_d)
+    torch.cuda.synchronize()
+    ref_fi, ref_sens = fi_d.cpu().numpy(), sens_d.cpu().numpy()
+    # ordinary numpy memory
+    fi_h, sens_h = fi0.copy(), np.full((n, k, no), -7.0)
+    s.solve(fk, fi_h, sens_h)
+    assert np.array_equal(fi_h, ref_fi)
+    assert np.array_equal(np.isnan(sens_h), np.isnan(ref_sens)) and np.array_equal(np.nan_to_num(sens_h), np.nan_to_num(ref_sens))
+    # pitched host sens (rows longer than the model) and page-locked memory
+    sens_p = np.full((n, k + 2, no + 3), -7.0)
+    fi_h2 = fi0.copy()
+    s.solve(fk, fi_h2, sens_p[:, :k, :no])
+    assert np.array_equal(np.nan_to_num(sens_p[:, :k, :no]), np.nan_to_num(ref_sens)) and (sens_p[:, k:, :] == -7.0).all() and (sens_p[:, :, no:] == -7.0).all()
+    sens_l = wlsqm.pinned_empty((n, k, no)); sens_l[...] = -7.0
+    fi_l = wlsqm.pinned_empty((n, no)); fi_l[...] = fi0
+    s.solve(fk, fi_l, sens_l)
+    assert np.array_equal(fi_l, ref_fi) and np.array_equal(np.nan_to_num(sens_l), np.nan_to_num(ref_sens))
+    wlsqm.pinned_free(sens_l); wlsqm.pinned_free(fi_l)

@@ -4,7 +4,7 @@ TAG=${1:-r02c}
 mkdir -p gpurun_out
 ( time timeout 1800 python -m pytest tests -m gpu -q ) > gpurun_out/pytest_gpu_$TAG.log 2>&1; tail -8 gpurun_out/pytest_gpu_$TAG.log
 grep -n "^E  " gpurun_out/pytest_gpu_$TAG.log | head -40 | cut -c1-300
-timeout 900 python benchmarks/run_configs.py 2>&1 | tee gpurun_out/configs_$TAG.jsonl | python -c "
+timeout 900 python benchmarks/run_configs.py --no-cpu 2>&1 | tee gpurun_out/configs_$TAG.jsonl | python -c "
 import sys,json
 for l in sys.stdin:
     try: d=json.loads(l)
