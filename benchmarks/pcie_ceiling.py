@@ -24,48 +24,54 @@ sys.path[:0] = [str(ROOT), str(ROOT / "python-wlsqm_b200")]
 H2D_BYTES, D2H_BYTES = 240_000_000, 120_000_000
 
 
-def worker(rank, world, variant, steps, barrier, q):
+VARIANTS = ("pinned", "pinned+affinity", "wc+affinity")
+
+
+def worker(rank, world, steps, barrier, q):
     import torch
     import wlsqm_b200 as wlsqm
     sys.path.insert(0, str(ROOT))
     import bench
-    if variant != "pinned":
-        bench.bind_to_gpu_cpus(rank)
     torch.cuda.set_device(rank)
     dev = torch.device("cuda", rank)
-    src = wlsqm.pinned_empty((H2D_BYTES // 8,), write_combined=(variant == "wc+affinity"))
-    src[...] = 1.0
-    dst = wlsqm.pinned_empty((D2H_BYTES // 8,))
-    dst[...] = 0.0
-    src_t, dst_t = torch.from_numpy(src), torch.from_numpy(dst)
     d_in = torch.empty(H2D_BYTES // 8, dtype=torch.float64, device=dev)
     d_out = torch.ones(D2H_BYTES // 8, dtype=torch.float64, device=dev)
     s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
-
-    def step():
-        with torch.cuda.stream(s1):
-            d_in.copy_(src_t, non_blocking=True)
-        with torch.cuda.stream(s2):
-            dst_t.copy_(d_out, non_blocking=True)
-    for _ in range(3):
-        step()
-    torch.cuda.synchronize()
-    res = {}
-    for what in ("both", "h2d", "d2h"):
-        barrier.wait()
-        t0 = time.perf_counter()
-        for _ in range(steps):
-            if what in ("both", "h2d"):
-                with torch.cuda.stream(s1):
-                    d_in.copy_(src_t, non_blocking=True)
-            if what in ("both", "d2h"):
-                with torch.cuda.stream(s2):
-                    dst_t.copy_(d_out, non_blocking=True)
-            torch.cuda.synchronize()          # a step is complete when both copies are (like solve() on host arrays)
-        dt = time.perf_counter() - t0
-        barrier.wait()
-        res[what] = 1e3 * dt / steps
-    q.put((rank, res))
+    out = {}
+    for variant in VARIANTS:
+        if variant != "pinned":
+            bench.bind_to_gpu_cpus(rank)          # (stays bound for the remaining variants)
+        src = wlsqm.pinned_empty((H2D_BYTES // 8,), write_combined=(variant == "wc+affinity"))
+        src[...] = 1.0
+        dst = wlsqm.pinned_empty((D2H_BYTES // 8,))
+        dst[...] = 0.0
+        src_t, dst_t = torch.from_numpy(src), torch.from_numpy(dst)
+        for _ in range(3):
+            with torch.cuda.stream(s1):
+                d_in.copy_(src_t, non_blocking=True)
+            with torch.cuda.stream(s2):
+                dst_t.copy_(d_out, non_blocking=True)
+        torch.cuda.synchronize()
+        res = {}
+        for what in ("both", "h2d", "d2h"):
+            barrier.wait()
+            t0 = time.perf_counter()
+            for _ in range(steps):
+                if what in ("both", "h2d"):
+                    with torch.cuda.stream(s1):
+                        d_in.copy_(src_t, non_blocking=True)
+                if what in ("both", "d2h"):
+                    with torch.cuda.stream(s2):
+                        dst_t.copy_(d_out, non_blocking=True)
+                torch.cuda.synchronize()          # a step is complete when both copies are (like solve() on host arrays)
+            dt = time.perf_counter() - t0
+            barrier.wait()
+            res[what] = 1e3 * dt / steps
+        out[variant] = res
+        del src_t, dst_t
+        wlsqm.pinned_free(src)
+        wlsqm.pinned_free(dst)
+    q.put((rank, out))
 
 
 def topo():
@@ -92,15 +98,15 @@ def main():
     for n in (1, 2, 4, 8):
         if n > ngpu:
             break
-        for variant in ("pinned", "pinned+affinity", "wc+affinity"):
-            barrier, q = ctx.Barrier(n), ctx.Queue()
-            procs = [ctx.Process(target=worker, args=(r, n, variant, a.steps, barrier, q)) for r in range(n)]
-            for p in procs:
-                p.start()
-            res = [q.get(timeout=600) for _ in procs]
-            for p in procs:
-                p.join(timeout=120)
-            ms = {w: max(r[1][w] for r in res) for w in ("both", "h2d", "d2h")}
+        barrier, q = ctx.Barrier(n), ctx.Queue()
+        procs = [ctx.Process(target=worker, args=(r, n, a.steps, barrier, q)) for r in range(n)]
+        for p in procs:
+            p.start()
+        res = [q.get(timeout=900) for _ in procs]
+        for p in procs:
+            p.join(timeout=120)
+        for variant in VARIANTS:
+            ms = {w: max(r[1][variant][w] for r in res) for w in ("both", "h2d", "d2h")}
             entry = {"ms_per_step": ms["both"], "h2d_only_ms": ms["h2d"], "d2h_only_ms": ms["d2h"],
                      "h2d_GBps_aggregate_concurrent": n * H2D_BYTES / (ms["both"] * 1e-3) / 1e9,
                      "d2h_GBps_aggregate_concurrent": n * D2H_BYTES / (ms["both"] * 1e-3) / 1e9,
