@@ -120,7 +120,7 @@ __device__ __forceinline__ unsigned group_min(unsigned v, int grp) {
 template <int DIM, int ORD, bool DIRECT>
 __global__ void __launch_bounds__(PK<DIM, ORD>::MAXT, PK<DIM, ORD>::MINB) prepare_reg_kernel(PrepRegParams P) {
     using K = PK<DIM, ORD>;
-    static_assert(!DIRECT || (K::RPL == 1 && K::NOP > K::NO), "the one-shot path needs one row per lane and a free padding slot");
+    static_assert(!DIRECT || K::NOP > K::NO, "the one-shot path needs a free padding slot in the monomial table");
     constexpr int NOP = K::NOP, NRP = K::NRP, RPL = K::RPL, T = K::T, LDA = K::LDA, CB = PREP_CB, BLK = K::BLK;
     constexpr int LPF = K::LPF, FPW = K::FPW;
     constexpr unsigned FULL = 0xffffffffu;
@@ -379,15 +379,20 @@ __global__ void __launch_bounds__(PK<DIM, ORD>::MAXT, PK<DIM, ORD>::MINB) prepar
             }
         }
         // one-shot fit: this row's right-hand side, knowns eliminated (impl.pyx:792-818): b_j = G[oj][NO] - sum_m fi[om] A[oj][om]
-        double bj = 0.0;
+        double bj[RPL];
+#pragma unroll
+        for (int t = 0; t < RPL; ++t) bj[t] = 0.0;
         if constexpr (DIRECT) {
-            if (jl < nr) {
-                const double* g = gG + gR2O[jl] * LDA;
-                bj = g[K::NO];
-                const int nkn_g = __popcll(knowns);
-                for (int mk = 0; mk < nkn_g; ++mk) {
-                    const int om = gR2O[nr + mk];
-                    bj = fma(-P.fi[cg * P.fi_s0 + om], g[om], bj);
+#pragma unroll
+            for (int t = 0; t < RPL; ++t) {
+                if (jl + 32 * t < nr) {
+                    const double* g = gG + ojs[t] * LDA;
+                    bj[t] = g[K::NO];
+                    const int nkn_g = __popcll(knowns);
+                    for (int mk = 0; mk < nkn_g; ++mk) {
+                        const int om = gR2O[nr + mk];
+                        bj[t] = fma(-P.fi[cg * P.fi_s0 + om], g[om], bj[t]);
+                    }
                 }
             }
         }
@@ -422,7 +427,10 @@ __global__ void __launch_bounds__(PK<DIM, ORD>::MAXT, PK<DIM, ORD>::MINB) prepar
                 a[t][m + 1] *= rj[t] * r2.y;
             }
         }
-        if constexpr (DIRECT) bj *= rj[0];
+        if constexpr (DIRECT) {
+#pragma unroll
+            for (int t = 0; t < RPL; ++t) bj[t] *= rj[t];
+        }
         if (P.As && nr > 0) {   // debug=True: keep the scaled matrix for conds() (impl.pyx:662-682)
             double* as = P.As + cg * (long long)P.as_stride;
 #pragma unroll
@@ -492,7 +500,7 @@ __global__ void __launch_bounds__(PK<DIM, ORD>::MAXT, PK<DIM, ORD>::MINB) prepar
                         double* row = gG + p * LDA;
 #pragma unroll
                         for (int m = 0; m < NRP; m += 2) st2(row + m, a[t][m], a[t][m + 1]);
-                        if constexpr (DIRECT) row[NOP] = bj;
+                        if constexpr (DIRECT) row[NOP] = bj[t];
                         gREC[p] = make_double2(rj[t], __hiloint2double(0, roff[t]));
                         pos[t] = p;
                         act[t] = false;
@@ -509,7 +517,7 @@ __global__ void __launch_bounds__(PK<DIM, ORD>::MAXT, PK<DIM, ORD>::MINB) prepar
                     l[t] = a[t][p] * rp;
                     if (act[t]) a[t][p] = l[t];
                     if constexpr (DIRECT) {
-                        if (act[t]) bj = fma(-l[t], gG[p * LDA + NOP], bj);
+                        if (act[t]) bj[t] = fma(-l[t], gG[p * LDA + NOP], bj[t]);
                     }
                 }
 #pragma unroll
@@ -528,7 +536,26 @@ __global__ void __launch_bounds__(PK<DIM, ORD>::MAXT, PK<DIM, ORD>::MINB) prepar
         __syncwarp();
 
         phase_barrier();
-        if constexpr (DIRECT) {
+        if constexpr (DIRECT && RPL == 2) {
+            // ---- U x = y for more rows than lanes (3D order 4): the right-hand side sits in column NOP of the published
+            //      LU (pivot order); from the bottom row up, the whole warp forms the dot product of a row with the part
+            //      of the solution already known ----
+            for (int i = nr - 1; i >= 0; --i) {
+                double part = 0.0;
+                for (int m = i + 1 + lane; m < nr; m += 32) part = fma(gG[i * LDA + m], gG[m * LDA + NOP], part);
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(FULL, part, o);
+                if (lane == 0) gG[i * LDA + NOP] = (gG[i * LDA + NOP] - part) / gG[i * LDA + i];     // dgetrs divides by the pivot
+                __syncwarp();
+            }
+#pragma unroll
+            for (int t = 0; t < RPL; ++t) {
+                const int j = jl + 32 * t;
+                if (j < nr) P.fi[cg * P.fi_s0 + gR2O[j]] = gG[j * LDA + NOP] * gRS[j];
+            }
+            __syncwarp();
+            continue;
+        } else if constexpr (DIRECT) {
             // ---- U x = y across the lanes: lane jl takes row jl of the pivot order (re-read from the published LU) ----
             double u[NRP];
             double y = 0.0;
@@ -662,10 +689,7 @@ static cudaError_t launch_k(const PrepRegParams& P, int blocks, int threads, siz
 template <int DIM, int ORD>
 static cudaError_t launch_t(const PrepRegParams& P, int blocks, int threads, size_t smem, cudaStream_t st,
                             int* occupancy) {
-    if (P.fk) {
-        if constexpr (PK<DIM, ORD>::RPL == 1) return launch_k<DIM, ORD, true>(P, blocks, threads, smem, st, occupancy);
-        else return cudaErrorInvalidValue;      // (3D order 4: two rows per lane -- the caller takes the operator path)
-    }
+    if (P.fk) return launch_k<DIM, ORD, true>(P, blocks, threads, smem, st, occupancy);
     return launch_k<DIM, ORD, false>(P, blocks, threads, smem, st, occupancy);
 }
 
@@ -695,8 +719,8 @@ cudaError_t prepare_reg_occupancy(int dim, int maxorder, int threads, size_t sme
 }
 
 bool prepare_reg_direct_ok(int dim, int maxorder) {
-    const int nrp = (prep_no(dim, maxorder) + 3) & ~3;
-    return nrp <= 32;
+    const int no = prep_no(dim, maxorder);
+    return ((no + 7) & ~7) > no;      // a free padding slot carries the data through the Gram phase (true for every model)
 }
 
 cudaError_t launch_prepare_reg(int dim, int maxorder, const PrepRegParams& P, int blocks, int threads, size_t smem,

@@ -343,3 +343,43 @@ def test_ab_switches_give_the_same_answers(tmp_path):
     assert np.array_equal(smem["ipiv"], base["ipiv"])
     assert np.allclose(smem["LU"], base["LU"], rtol=1e-10, atol=1e-12)
     assert np.allclose(smem["x"], base["x"], rtol=1e-9, atol=1e-11)
+
+
+ONESHOT_CASES = [
+    # dim, order, k, knowns, wm, n
+    pytest.param(3, 4, 60, 1, 2, 601, id="3D-o4-k60-bF-center (two matrix rows per lane)"),
+    pytest.param(3, 4, 70, 0, 1, 333, id="3D-o4-k70-nr35-uniform"),
+    pytest.param(3, 3, 40, 1, 1, 1001, id="3D-o3-k40"),
+    pytest.param(2, 4, 30, 0, 1, 2001, id="2D-o4-k30"),
+    pytest.param(1, 4, 9, 1, 2, 2003, id="1D-o4-k9"),
+]
+
+
+@pytest.mark.parametrize("dim,order,k,knowns,wm,n", ONESHOT_CASES)
+def test_one_shot_kernel_vs_oracle(dim, order, k, knowns, wm, n):
+    """fit_*_many_parallel without sens on a uniform batch: ONE fused kernel (assemble, equilibrate, factor, solve; no
+    operator is formed) -- generic_fit_basic_many_parallel, simple.pyx:953-1058 -- for every model size including 3D
+    order 4 (35 DOFs: two matrix rows per lane, back-substitution through shared memory).  Against the oracle with the
+    noise-floor criterion, and against the prepare + solve path."""
+    x, hoods, f = parity.make_case(n, dim, k)
+    xk, fk = parity.gathered(x, f, hoods)
+    no = wlsqm.number_of_dofs(dim, order)
+    nk, od, kn, w = np.full(n, k, np.int32), np.full(n, order, np.int32), np.full(n, knowns, np.int64), np.full(n, wm, np.int32)
+    fi0 = np.zeros((n, no)); fi0[:, 0] = f
+    got = fi0.copy()
+    fit = getattr(wlsqm, "fit_%dD_many_parallel" % dim)
+    assert fit(xk, fk, nk, x, got, None, 0, od, kn, w, ntasks=4) == 0
+    ref, _, _, _ = parity.oracle_solve(dim, nk, od, kn, w, x, xk, fk, fi0)
+    a, b = parity.permuted_self_noise(dim, nk, od, kn, w, x, xk, fk, fi0)
+    print(parity.check_against_floor(got, ref, b + (ref - a), dim, order, "one-shot kernel vs oracle"))
+    for o in range(no):
+        if knowns >> o & 1:
+            assert np.array_equal(got[:, o], fi0[:, o])
+    exp, _, _ = _solve_gpu(dim, nk, od, kn, w, x, xk, fk, fi0)
+    print(parity.check_against_floor(got, exp, b + (exp - a), dim, order, "one-shot kernel vs prepare + solve"))
+    # the same through CUDA tensors, bit for bit
+    torch = pytest.importorskip("torch")
+    got_d = torch.from_numpy(fi0).cuda()
+    fit(torch.from_numpy(xk).cuda(), torch.from_numpy(fk).cuda(), nk, torch.from_numpy(x).cuda(), got_d, None, 0, od, kn, w)
+    torch.cuda.synchronize()
+    assert np.array_equal(got_d.cpu().numpy(), got)
