@@ -534,6 +534,15 @@ __global__ void __launch_bounds__(PK<DIM, ORD>::MAXT, PK<DIM, ORD>::MINB) prepar
             }
         }
         __syncwarp();
+        if constexpr (!DIRECT) {
+            // rows nr .. NRP-1 of the pivot-order LU storage and their reciprocal pivots: zeros (they held Gram entries),
+            // so that the operator phase can run its substitutions over the padded size without a branch per row
+            if (nr > 0) {
+                for (int t = jl; t < (NRP - nr) * NRP; t += LPF) gG[(nr + t / NRP) * LDA + (t % NRP)] = 0.0;
+                for (int t = nr + jl; t < NRP; t += LPF) gDINV[t] = 0.0;
+            }
+            __syncwarp();
+        }
 
         phase_barrier();
         if constexpr (DIRECT && RPL == 2) {
@@ -626,6 +635,8 @@ __global__ void __launch_bounds__(PK<DIM, ORD>::MAXT, PK<DIM, ORD>::MINB) prepar
                         y[i] = rec.x * (wq * ctq[__double2loint(rec.y)]);
                     }
                 }
+                if constexpr (NRP > 16) {
+                // (3D orders 3 and 4: 20 / 36 solution components per lane leave no registers for overlapped rows -- row by row)
                 // unit-lower forward substitution
 #pragma unroll
                 for (int i = 1; i < NRP; ++i) {
@@ -650,6 +661,42 @@ __global__ void __launch_bounds__(PK<DIM, ORD>::MAXT, PK<DIM, ORD>::MINB) prepar
                         }
                         y[i] *= DI[i];
                     }
+                }
+                } else {
+                // Both substitutions in column (axpy) order, two columns per step, WITHOUT a branch per row: rows and
+                // columns beyond the fit's size hold zeros (cleared after the LU), so the whole block is one stretch of
+                // straight-line code in which the updates of different rows are independent and overlap -- with a
+                // branch per row (one dependent FMA chain per basic block) the substitutions were latency-bound.
+                // unit-lower forward substitution: y_i -= l_ip y_p, p ascending (dtrsm's order)
+#pragma unroll
+                for (int p = 0; p + 1 < NRP; p += 2) {
+                    {
+                        const double2 l2 = ld2(G + (p + 1) * LDA + p);
+                        y[p + 1] = fma(-l2.x, y[p], y[p + 1]);
+                    }
+#pragma unroll
+                    for (int i = p + 2; i < NRP; ++i) {
+                        const double2 l2 = ld2(G + i * LDA + p);
+                        y[i] = fma(-l2.x, y[p], y[i]);
+                        y[i] = fma(-l2.y, y[p + 1], y[i]);
+                    }
+                }
+                // upper backward substitution: x_m = y_m / u_mm, then y_i -= u_im x_m for i < m, m descending (dtrsm's order)
+#pragma unroll
+                for (int m = NRP - 2; m >= 0; m -= 2) {
+                    y[m + 1] *= DI[m + 1];
+                    {
+                        const double2 u2 = ld2(G + m * LDA + m);      // (u_mm, u_m,m+1)
+                        y[m] = fma(-u2.y, y[m + 1], y[m]);
+                        y[m] *= DI[m];
+                    }
+#pragma unroll
+                    for (int i = 0; i < m; ++i) {
+                        const double2 u2 = ld2(G + i * LDA + m);
+                        y[i] = fma(-u2.y, y[m + 1], y[i]);
+                        y[i] = fma(-u2.x, y[m], y[i]);
+                    }
+                }
                 }
                 // Op[q][j] = x_j * col_j: 32 consecutive operator rows staged in CT, one bulk store per block
                 const int rows = min(32, nqf - b * 32);
