@@ -47,6 +47,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--nlhs", type=int, default=1_000_000)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--scalers", action="store_true", help="also time the batched matrix scalers (mdo_rescale)")
     a = ap.parse_args()
     ref = None
     if not a.no_cpu:
@@ -95,6 +96,34 @@ def main():
                         best = (dt, nt)
                 line["cpu_reference"] = {"s_per_problem": best[0] / m, "cores": best[1], "sample": m}
                 line["speedup_vs_cpu_reference"] = (best[0] / m) / (t / nlhs)
+            print(json.dumps(line), flush=True)
+    if a.scalers:
+        # batched equilibration (mdo_rescale) of Gram-like 15 x 15 matrices, every algorithm of ScalingAlgo; CPU: the
+        # reference's do_rescale matrix by matrix (it has no batched scaler)
+        n, nlhs = 15, a.nlhs // 4
+        c = torch.randn((nlhs, 40, n), dtype=torch.float64, device="cuda", generator=g) * (10.0 ** torch.linspace(-3, 1, n, dtype=torch.float64, device="cuda"))
+        gram = c.transpose(1, 2) @ c
+        work = torch.empty_like(gram)
+        for algo in ld.ScalingAlgo:
+            def step():
+                work.copy_(gram)
+                ld.mdo_rescale(work.permute(2, 1, 0), algo)
+
+            def copies():
+                work.copy_(gram)
+            t = gpu_time(step) - gpu_time(copies)
+            bytes_per = 16 * n * n + 16 * n
+            line = {"driver": "mdo_rescale " + algo.name, "n": n, "nlhs": nlhs, "s_per_problem": t / nlhs, "problems_per_s": nlhs / t,
+                    "GBps": bytes_per * nlhs / t / 1e9, "hbm_frac": bytes_per * nlhs / t / 1e9 / PEAK}
+            if ref is not None:
+                m = 20_000
+                Ah = gram[:m].cpu().numpy()
+                t0 = time.perf_counter()
+                for l in range(m):
+                    ref.do_rescale(np.asfortranarray(Ah[l]), int(algo))
+                dt = time.perf_counter() - t0
+                line["cpu_reference"] = {"s_per_problem": dt / m, "cores": 1, "sample": m, "note": "do_rescale per matrix (no batched scaler in the reference)"}
+                line["speedup_vs_cpu_reference"] = (dt / m) / (t / nlhs)
             print(json.dumps(line), flush=True)
 
 

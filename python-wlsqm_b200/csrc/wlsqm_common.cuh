@@ -193,6 +193,48 @@ __device__ __forceinline__ double eval_taylor_nested(int no, const double* fi, d
     const Steps hx = steps_of(dx), hy = steps_of(DIM >= 2 ? dy : 0.0), hz = steps_of(DIM >= 3 ? dz : 0.0);
     return eval_diff_from<DIM, 0>([&](int S) { return fi[S]; }, no, hx, hy, hz);
 }
+// ... for a model of the dimension's full size (order 4): no test per coefficient
+template <int DIM>
+__device__ __forceinline__ double eval_taylor_nested_full(const double* fi, double dx, double dy, double dz) {
+    const Steps hx = steps_of(dx), hy = steps_of(DIM >= 2 ? dy : 0.0), hz = steps_of(DIM >= 3 ? dz : 0.0);
+    return eval_diff_from<DIM, 0>([&](int S) { return fi[S]; }, max_no<DIM>(), hx, hy, hz);
+}
+
+// The same model value at TWO offsets at once (the refinement loop of the solve kernel evaluates the model at a case's
+// neighbours, lane = neighbour: with more than 32 neighbours a lane owns two): every coefficient is loaded once for both
+// points and the two nested Horner chains are independent, so their latencies overlap.  Same operations per point as
+// eval_taylor_nested.
+template <int DIM, bool FULL>
+__device__ __forceinline__ void eval_taylor_nested2(int no, const double* fi, double dx0, double dy0, double dz0, double dx1,
+                                                    double dy1, double dz1, double& r0, double& r1) {
+    const Steps hx0 = steps_of(dx0), hy0 = steps_of(DIM >= 2 ? dy0 : 0.0), hz0 = steps_of(DIM >= 3 ? dz0 : 0.0);
+    const Steps hx1 = steps_of(dx1), hy1 = steps_of(DIM >= 2 ? dy1 : 0.0), hz1 = steps_of(DIM >= 3 ? dz1 : 0.0);
+    constexpr int CMAX = DIM >= 3 ? 4 : 0;
+    double vz0 = 0.0, vz1 = 0.0;
+    static_rfor<CMAX, 0>([&](auto Cc) {
+        constexpr int c = decltype(Cc)::value;
+        constexpr int BMAX = DIM >= 2 ? 4 - c : 0;
+        double vy0 = 0.0, vy1 = 0.0;
+        static_rfor<BMAX, 0>([&](auto Bc) {
+            constexpr int b = decltype(Bc)::value;
+            constexpr int AMAX = 4 - b - c;
+            double vx0 = 0.0, vx1 = 0.0;
+            static_rfor<AMAX, 0>([&](auto Ac) {
+                constexpr int a = decltype(Ac)::value;
+                constexpr int S = slot_of<DIM>(a, b, c);
+                const double u = (FULL || S < no) ? fi[S] : 0.0;
+                if constexpr (a == AMAX) { vx0 = u; vx1 = u; }
+                else { vx0 = fma(vx0, hx0.s[a], u); vx1 = fma(vx1, hx1.s[a], u); }
+            });
+            if constexpr (b == BMAX) { vy0 = vx0; vy1 = vx1; }
+            else { vy0 = fma(vy0, hy0.s[b], vx0); vy1 = fma(vy1, hy1.s[b], vx1); }
+        });
+        if constexpr (c == CMAX) { vz0 = vy0; vz1 = vy1; }
+        else { vz0 = fma(vz0, hz0.s[c], vy0); vz1 = fma(vz1, hz1.s[c], vy1); }
+    });
+    r0 = vz0;
+    r1 = vz1;
+}
 
 __device__ __forceinline__ double warp_max(double v) {
 #pragma unroll

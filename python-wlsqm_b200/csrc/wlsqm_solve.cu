@@ -332,16 +332,47 @@ solve_kernel(SolveParams P) {
             if (DIM >= 3) xi2 = P.xi[c * P.xi_s0 + 2];
             double prev = -1.0;
             bool broke = false;
+            const bool full_model = no == max_no<DIM>();     // (warp-uniform) order 4: no test per coefficient
             for (it = 0; it < P.max_iter; ++it) {
                 double nrm = 0.0;
-                for (int k = lane; k < nk; k += 32) {
-                    const double dx = xks[k * DIM] - xi0;
-                    const double dy = DIM >= 2 ? xks[k * DIM + (DIM >= 2 ? 1 : 0)] - xi1 : 0.0;
-                    const double dz = DIM >= 3 ? xks[k * DIM + (DIM >= 3 ? 2 : 0)] - xi2 : 0.0;
-                    const double r = fext[k] - eval_taylor_nested<DIM>(no, fis, dx, dy, dz);
-                    rs[k] = r;
-                    const double ar = fabs(r);
-                    nrm = ar > nrm ? ar : nrm;          // `if tmp > norm` (impl.pyx:1037-1041)
+                if (DIM == 3 && nk > 32) {
+                    // more neighbours than lanes: a lane evaluates the model at its two neighbours k and k + 32 together
+                    // (coefficients loaded once, two independent Horner chains).  3D only: the 1D / 2D instantiations run
+                    // 24 warps per SM at 80 registers and have none to spare for the second chain.
+                    for (int k = lane; k < nk; k += 64) {
+                        const int k1 = k + 32;
+                        const bool has1 = k1 < nk;
+                        const int kb = has1 ? k1 : k;
+                        const double dx0 = xks[k * DIM] - xi0, dx1 = xks[kb * DIM] - xi0;
+                        const double dy0 = DIM >= 2 ? xks[k * DIM + (DIM >= 2 ? 1 : 0)] - xi1 : 0.0;
+                        const double dy1 = DIM >= 2 ? xks[kb * DIM + (DIM >= 2 ? 1 : 0)] - xi1 : 0.0;
+                        const double dz0 = DIM >= 3 ? xks[k * DIM + (DIM >= 3 ? 2 : 0)] - xi2 : 0.0;
+                        const double dz1 = DIM >= 3 ? xks[kb * DIM + (DIM >= 3 ? 2 : 0)] - xi2 : 0.0;
+                        double m0, m1;
+                        if (full_model) eval_taylor_nested2<DIM, true>(no, fis, dx0, dy0, dz0, dx1, dy1, dz1, m0, m1);
+                        else eval_taylor_nested2<DIM, false>(no, fis, dx0, dy0, dz0, dx1, dy1, dz1, m0, m1);
+                        const double r0 = fext[k] - m0;
+                        rs[k] = r0;
+                        const double a0 = fabs(r0);
+                        nrm = a0 > nrm ? a0 : nrm;          // `if tmp > norm` (impl.pyx:1037-1041)
+                        if (has1) {
+                            const double r1 = fext[k1] - m1;
+                            rs[k1] = r1;
+                            const double a1 = fabs(r1);
+                            nrm = a1 > nrm ? a1 : nrm;
+                        }
+                    }
+                } else {
+                    for (int k = lane; k < nk; k += 32) {
+                        const double dx = xks[k * DIM] - xi0;
+                        const double dy = DIM >= 2 ? xks[k * DIM + (DIM >= 2 ? 1 : 0)] - xi1 : 0.0;
+                        const double dz = DIM >= 3 ? xks[k * DIM + (DIM >= 3 ? 2 : 0)] - xi2 : 0.0;
+                        const double r = fext[k] - (full_model ? eval_taylor_nested_full<DIM>(fis, dx, dy, dz)
+                                                               : eval_taylor_nested<DIM>(no, fis, dx, dy, dz));
+                        rs[k] = r;
+                        const double ar = fabs(r);
+                        nrm = ar > nrm ? ar : nrm;          // `if tmp > norm` (impl.pyx:1037-1041)
+                    }
                 }
                 nrm = warp_max_nonneg(nrm);
                 if (nrm == prev) { broke = true; break; }

@@ -47,7 +47,8 @@ G = ROOT / "gpurun_out"
 for name, stem in (("solve_kernel", "solve"), ("prepare_reg_kernel", "prepare"), ("interpolate_kernel", "interp"),
                    ("solve_kernel_3d_iter_sens", "solve3d"), ("solve_pack_kernel", "solvepack"),
                    ("solve_kernel_2d_iterative", "solveiter"), ("interpolate_kernel_one_slot", "interp1"),
-                   ("fit_direct_kernel", "fitdirect"), ("lu_reg_kernel", "lureg")):
+                   ("fit_direct_kernel", "fitdirect"), ("lu_reg_kernel", "lureg"), ("prepare_reg_kernel_3d", "prepare3d"),
+                   ("rescale_kernel", "rescale")):
     rep = G / f"{stem}_{tag}.ncu-rep"
     if not rep.exists():
         print("missing", rep); continue
@@ -60,7 +61,7 @@ for name, stem in (("solve_kernel", "solve"), ("prepare_reg_kernel", "prepare"),
         (OUT / "solve_kernel_traffic.json").write_text(json.dumps({
             "kernel": "wlsqm::solve_kernel<1,false,false,true>", "points": 1000000, "dram_bytes_read": rd, "dram_bytes_write": wr,
             "dram_bytes_per_launch": rd + wr, "algorithmic_bytes_per_launch": 4080000000,
-            "source": f"ncu --set full --clock-control none, gpurun_out/solve_{tag}.ncu-rep (round 1), launch 1 of 2"}, indent=1) + "\n")
+            "source": f"ncu --set full --clock-control none, gpurun_out/solve_{tag}.ncu-rep ({rnd}), launch 1 of 2"}, indent=1) + "\n")
     print("ok", name)
 src = G / f"launches_{tag}.csv"
 if src.exists():
