@@ -176,17 +176,32 @@ __global__ void __launch_bounds__(PK<DIM, ORD>::MAXT, PK<DIM, ORD>::MINB) prepar
         if (DIM >= 2) d2 += dy * dy;
         if (DIM >= 3) d2 += dz * dz;
         const Pow5 px = scaled_powers(dx), py = scaled_powers(dy), pz = scaled_powers(dz);
-        static_for<0, NOP>([&](auto I) {
-            constexpr int s = decltype(I)::value;
-            double v = 0.0;
-            if constexpr (s < K::NO) {
-                if (in && s < no) v = monomial<DIM, s>(px, py, pz);
-            }
-            if constexpr (DIRECT && s == K::NO) {
-                if (in) v = P.fk[c * P.fk_s0 + (long long)k * P.fk_s1];
-            }
-            ctb[s * CB] = v;
-        });
+        if (no == K::NO) {
+            // the model of this instantiation's own order (every uniform batch, every per-order launch): no test per
+            // slot.  Columns outside the neighbourhood hold the monomials of a zero offset -- finite values that their
+            // zero weight removes from every sum.
+            static_for<0, NOP>([&](auto I) {
+                constexpr int s = decltype(I)::value;
+                double v = 0.0;
+                if constexpr (s < K::NO) v = monomial<DIM, s>(px, py, pz);
+                if constexpr (DIRECT && s == K::NO) {
+                    if (in) v = P.fk[c * P.fk_s0 + (long long)k * P.fk_s1];
+                }
+                ctb[s * CB] = v;
+            });
+        } else {
+            static_for<0, NOP>([&](auto I) {
+                constexpr int s = decltype(I)::value;
+                double v = 0.0;
+                if constexpr (s < K::NO) {
+                    if (in && s < no) v = monomial<DIM, s>(px, py, pz);
+                }
+                if constexpr (DIRECT && s == K::NO) {
+                    if (in) v = P.fk[c * P.fk_s0 + (long long)k * P.fk_s1];
+                }
+                ctb[s * CB] = v;
+            });
+        }
         return d2;
     };
 
@@ -454,6 +469,11 @@ __global__ void __launch_bounds__(PK<DIM, ORD>::MAXT, PK<DIM, ORD>::MINB) prepar
 #pragma unroll
         for (int p = 0; p < NRP; ++p) {
             if (p < nrmax) {
+                // every row's reciprocal of its entry in this column, BEFORE the pivot is known: the division overlaps the
+                // pivot search instead of following the publication of the pivot row (the LU is a chain of such steps)
+                double rcp[RPL];
+#pragma unroll
+                for (int t = 0; t < RPL; ++t) rcp[t] = 1.0 / a[t][p];
                 // pivot = largest |a[.][p]| among the active rows, first in current row order on ties (idamax)
                 bool piv[RPL];
                 bool has_piv;
@@ -502,6 +522,7 @@ __global__ void __launch_bounds__(PK<DIM, ORD>::MAXT, PK<DIM, ORD>::MINB) prepar
                         for (int m = 0; m < NRP; m += 2) st2(row + m, a[t][m], a[t][m + 1]);
                         if constexpr (DIRECT) row[NOP] = bj[t];
                         gREC[p] = make_double2(rj[t], __hiloint2double(0, roff[t]));
+                        gDINV[p] = rcp[t];
                         pos[t] = p;
                         act[t] = false;
                     } else if (has_piv && pos[t] == p) {
@@ -509,11 +530,10 @@ __global__ void __launch_bounds__(PK<DIM, ORD>::MAXT, PK<DIM, ORD>::MINB) prepar
                     }
                 }
                 __syncwarp();
-                const double rp = 1.0 / gG[p * LDA + p];
+                const double rp = gDINV[p];      // = 1 / (the pivot), published with its row
                 double l[RPL];
 #pragma unroll
                 for (int t = 0; t < RPL; ++t) {
-                    if (piv[t]) gDINV[p] = rp;
                     l[t] = a[t][p] * rp;
                     if (act[t]) a[t][p] = l[t];
                     if constexpr (DIRECT) {
