@@ -236,6 +236,10 @@ WLSQM_API int wlsqm_msytrs(int n, int64_t nlhs, const double* UDU, const int32_t
 WLSQM_API int wlsqm_msysv(int n, int64_t nlhs, double* A, int32_t* ipiv, double* b, int device);
 WLSQM_API int wlsqm_msymmetrize(int n, int64_t nlhs, double* A, int device);
 
+/* tridiag (wlsqm/utils/lapackdrivers.pyx:854-877 -> DGTSV, one right-hand side): dl (n-1 used), d (n), du (n-1 used) are
+ * overwritten by the factorisation, b by the solution; all four on the host or all four on the device. */
+WLSQM_API int wlsqm_gtsv(int n, double* dl, double* d, double* du, double* b, int device);
+
 /* ---- batched matrix equilibration: wlsqm/utils/lapackdrivers.pyx:285-847 --------------------------------------------
  * do_rescale (:319-385) for every matrix of a batch: A (nrows, ncols, nlhs) Fortran-contiguous is scaled in place
  * (apply_scaling_c, :293-299), row_scale (nrows, nlhs) / col_scale (ncols, nlhs) Fortran receive the factors

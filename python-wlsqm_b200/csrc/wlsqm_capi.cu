@@ -1694,6 +1694,43 @@ int wlsqm_msysv(int n, int64_t nlhs, double* A, int32_t* ipiv, double* b, int de
     if (!A || !b) return fail(WLSQM_E_VALUE, "NULL argument");
     return lapack_common(n, nlhs, A, ipiv, b, device, 1, 1, 1);
 }
+// tridiag (lapackdrivers.pyx:854-877): DGTSV with one right-hand side; a = DL (n-1 used), b = D (n), c = DU (n-1 used), x = RHS
+int wlsqm_gtsv(int n, double* dl, double* d, double* du, double* b, int device) {
+    if (n < 0) return fail(WLSQM_E_VALUE, "n must be >= 0");
+    if (n == 0) return WLSQM_OK;
+    if (!dl || !d || !du || !b) return fail(WLSQM_E_VALUE, "NULL argument");
+    if (wlsqm_device_count() < 1) return fail(WLSQM_E_CUDA, "no CUDA device available (there is no CPU fallback)");
+    CU(cudaSetDevice(device));
+    const bool dev = is_device_ptr(dl) && is_device_ptr(d) && is_device_ptr(du) && is_device_ptr(b);
+    const bool host = !is_device_ptr(dl) && !is_device_ptr(d) && !is_device_ptr(du) && !is_device_ptr(b);
+    if (!dev && !host) return fail(WLSQM_E_VALUE, "tridiag: the four arrays must live on the same side (host or device)");
+    cudaStream_t st = caller_stream();
+    const size_t nb = (size_t)n * 8;
+    DevBuf buf;
+    double *p0 = dl, *p1 = d, *p2 = du, *p3 = b;
+    if (host) {
+        int rc = buf.reserve(4 * nb);
+        if (rc) return rc;
+        p0 = (double*)buf.p; p1 = p0 + n; p2 = p1 + n; p3 = p2 + n;
+        cudaError_t e = cudaMemcpyAsync(p0, dl, nb, cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(p1, d, nb, cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(p2, du, nb, cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(p3, b, nb, cudaMemcpyHostToDevice, st);
+        if (e != cudaSuccess) { buf.release(); return fail(WLSQM_E_CUDA, "tridiag upload: %s", cudaGetErrorString(e)); }
+    }
+    cudaError_t e = launch_gtsv(n, p0, p1, p2, p3, st);
+    if (e == cudaSuccess && host) {
+        e = cudaMemcpyAsync(dl, p0, nb, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d, p1, nb, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(du, p2, nb, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(b, p3, nb, cudaMemcpyDeviceToHost, st);
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    buf.release();
+    if (e != cudaSuccess) return fail(WLSQM_E_CUDA, "tridiag: %s", cudaGetErrorString(e));
+    return WLSQM_OK;
+}
+
 // do_rescale (lapackdrivers.pyx:319-385) over a batch: scale every matrix in place, return the scale vectors
 int wlsqm_mrescale(int nrows, int ncols, int64_t nlhs, double* A, int algo, double* row_scale, double* col_scale, int32_t* ok,
                    int device) {

@@ -117,6 +117,7 @@ cudaError_t launch_getrs(int n, long long nlhs, const double* LU, const int* ipi
 cudaError_t launch_gesv(int n, long long nlhs, double* A, int* ipiv, double* b, cudaStream_t st);
 cudaError_t launch_sy(int n, long long nlhs, double* A, int* ipiv, double* b, int do_factor, cudaStream_t st);
 cudaError_t launch_symmetrize(int n, long long nlhs, double* A, cudaStream_t st);
+cudaError_t launch_gtsv(int n, double* dl, double* d, double* du, double* b, cudaStream_t st);
 cudaError_t launch_rescale(int nrows, int ncols, long long nlhs, double* A, int algo, double* row_scale, double* col_scale,
                            int* ok, cudaStream_t st);
 cudaError_t launch_cond(int n_max, long long ncases, const CaseMeta* meta, const CaseMeta& uni, const double* As,

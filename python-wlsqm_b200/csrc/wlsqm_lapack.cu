@@ -596,6 +596,46 @@ cudaError_t launch_symmetrize(int n, long long nlhs, double* A, cudaStream_t st)
     return cudaGetLastError();
 }
 
+// ---- tridiag (lapackdrivers.pyx:854-877 -> LAPACK DGTSV, one right-hand side) --------------------------------------
+// The reference's minimal example driver: Gaussian elimination with partial pivoting on a tridiagonal system; dl / d / du
+// are overwritten by the factorisation like DGTSV does, b by the solution.  One thread: the recurrence is sequential.
+__global__ void gtsv_kernel(int n, double* __restrict__ dl, double* __restrict__ d, double* __restrict__ du,
+                            double* __restrict__ b) {
+    if (threadIdx.x || blockIdx.x) return;
+    for (int i = 0; i < n - 1; ++i) {
+        if (fabs(d[i]) >= fabs(dl[i])) {
+            if (d[i] == 0.0) return;                      // singular: DGTSV stops with info = i + 1 (the reference ignores info)
+            const double fact = dl[i] / d[i];
+            d[i + 1] -= fact * du[i];
+            b[i + 1] -= fact * b[i];
+            dl[i] = 0.0;
+        } else {                                          // interchange rows i and i + 1
+            const double fact = d[i] / dl[i];
+            d[i] = dl[i];
+            double temp = d[i + 1];
+            d[i + 1] = du[i] - fact * temp;
+            if (i < n - 2) {
+                dl[i] = du[i + 1];
+                du[i + 1] = -fact * dl[i];
+            }
+            du[i] = temp;
+            temp = b[i];
+            b[i] = b[i + 1];
+            b[i + 1] = temp - fact * b[i + 1];
+        }
+    }
+    if (d[n - 1] == 0.0) return;
+    b[n - 1] /= d[n - 1];
+    if (n > 1) b[n - 2] = (b[n - 2] - du[n - 2] * b[n - 1]) / d[n - 2];
+    for (int i = n - 3; i >= 0; --i) b[i] = (b[i] - du[i] * b[i + 1] - dl[i] * b[i + 2]) / d[i];
+}
+
+cudaError_t launch_gtsv(int n, double* dl, double* d, double* du, double* b, cudaStream_t st) {
+    if (n < 1) return cudaSuccess;
+    gtsv_kernel<<<1, 32, 0, st>>>(n, dl, d, du, b);
+    return cudaGetLastError();
+}
+
 // ---- condition numbers ---------------------------------------------------------------------------
 __global__ void cond_kernel(long long ncases, const CaseMeta* meta, CaseMeta uni, const double* __restrict__ As,
                             int as_stride, double* __restrict__ cond, int warp_doubles) {

@@ -78,6 +78,7 @@ SIGNATURES = {
     "wlsqm_msytrs": (_int, [_int, _i64, _vp, _vp, _vp, _int]),
     "wlsqm_msysv": (_int, [_int, _i64, _vp, _vp, _vp, _int]),
     "wlsqm_msymmetrize": (_int, [_int, _i64, _vp, _int]),
+    "wlsqm_gtsv": (_int, [_int, _vp, _vp, _vp, _vp, _int]),
     "wlsqm_mrescale": (_int, [_int, _int, _i64, _vp, _int, _vp, _vp, _vp, _int]),
 }
 

@@ -20,7 +20,8 @@ import numpy as np
 
 from .. import _lib
 
-__all__ = ["ScalingAlgo", "do_rescale", "mdo_rescale", "mdo_rescalep", "rescale_columns", "rescale_rows", "rescale_twopass",
+__all__ = ["ScalingAlgo", "general", "generalfactor", "generalfactored", "symmetric", "symmetricfactor", "symmetricfactored",
+           "tridiag", "do_rescale", "mdo_rescale", "mdo_rescalep", "rescale_columns", "rescale_rows", "rescale_twopass",
            "rescale_ruiz2001", "rescale_scalgm", "rescale_dgeequ", "mgeneral", "mgeneralp", "mgeneralfactor", "mgeneralfactorp", "mgeneralfactored", "mgeneralfactoredp",
            "msymmetric", "msymmetricp", "msymmetricfactor", "msymmetricfactorp", "msymmetricfactored",
            "msymmetricfactoredp", "msymmetrize", "msymmetrizep"]
@@ -280,3 +281,97 @@ def rescale_ruiz2001(A, device=None):
 def rescale_scalgm(A, device=None):
     """SCALGM of Chiang and Chandler (2008) (``lapackdrivers.pyx:626-847``)"""
     return do_rescale(A, ScalingAlgo.ALGO_SCALGM, device)
+
+
+# ---- the reference's single-system entry points, on top of the batched kernels (a batch of one) ------------------------
+def _as_batch(A, b=None):
+    """(n, n) Fortran matrix [and (n,) vector] as views of shape (n, n, 1) [(n, 1)]: the batched kernels work in place"""
+    _f3(A, "A", np.float64, 2)
+    A3 = A.unsqueeze(2) if _lib._is_torch_tensor(A) else A.reshape(A.shape[0], A.shape[1], 1, order="F")
+    if b is None:
+        return A3
+    if _lib._is_torch_tensor(b):
+        if b.dim() != 1:
+            raise ValueError("b: Buffer has wrong number of dimensions (expected 1, got %d)" % b.dim())
+        return A3, b.unsqueeze(1)
+    b = np.asarray(b) if not isinstance(b, np.ndarray) else b
+    if b.ndim != 1 or b.dtype != np.float64 or not b.flags.c_contiguous:
+        raise ValueError("b: a contiguous float64 vector is required")
+    return A3, b.reshape(b.shape[0], 1, order="F")
+
+
+def general(A, b, device=None):
+    """Solve a general system in place (dgesv; ``lapackdrivers.pyx:1395-1412``): A is destroyed, b becomes the solution."""
+    A3, b2 = _as_batch(A, b)
+    mgeneral(A3, b2, device)
+
+
+def generalfactor(A, device=None):
+    """LU-factor in place, return the pivots (dgetrf; ``lapackdrivers.pyx:1415-1434``)."""
+    A3 = _as_batch(A)
+    n = A3.shape[0]
+    if _lib._is_torch_tensor(A):
+        import torch
+        ipiv = torch.empty((1, n), dtype=torch.int32, device=A.device).t()
+    else:
+        ipiv = np.empty((n, 1), dtype=np.int32, order="F")
+    mgeneralfactor(A3, ipiv, device)
+    return ipiv[:, 0]
+
+
+def generalfactored(LU, ipiv, b, device=None):
+    """Solve with factors from ``generalfactor`` (dgetrs; ``lapackdrivers.pyx:1437-1462``)."""
+    A3, b2 = _as_batch(LU, b)
+    mgeneralfactored(A3, ipiv.reshape(-1, 1) if not _lib._is_torch_tensor(ipiv) else ipiv.unsqueeze(1), b2, device)
+
+
+def symmetric(A, b, device=None):
+    """Solve a symmetric system in place, upper triangle (dsysv; ``lapackdrivers.pyx:918-953``)."""
+    A3, b2 = _as_batch(A, b)
+    msymmetric(A3, b2, device)
+
+
+def symmetricfactor(A, device=None):
+    """U D U^T-factor in place, return the pivots (dsytrf; ``lapackdrivers.pyx:956-1010``)."""
+    A3 = _as_batch(A)
+    n = A3.shape[0]
+    if _lib._is_torch_tensor(A):
+        import torch
+        ipiv = torch.empty((1, n), dtype=torch.int32, device=A.device).t()
+    else:
+        ipiv = np.empty((n, 1), dtype=np.int32, order="F")
+    msymmetricfactor(A3, ipiv, device)
+    return ipiv[:, 0]
+
+
+def symmetricfactored(A, ipiv, b, device=None):
+    """Solve with factors from ``symmetricfactor`` (dsytrs; ``lapackdrivers.pyx:1013-1050``)."""
+    A3, b2 = _as_batch(A, b)
+    msymmetricfactored(A3, ipiv.reshape(-1, 1) if not _lib._is_torch_tensor(ipiv) else ipiv.unsqueeze(1), b2, device)
+
+
+def tridiag(a, b, c, x, device=None):
+    """The reference's minimal example driver (``lapackdrivers.pyx:854-877``): LAPACK's DGTSV with one right-hand side on
+    (DL, D, DU, B) = (a, b, c, x); x becomes the solution, a / b / c are overwritten by the factorisation."""
+    arrs = []
+    for nm, v in (("a", a), ("b", b), ("c", c), ("x", x)):
+        if _lib._is_torch_tensor(v):
+            if not v.is_cuda or v.dtype != _torch_f64() or v.dim() != 1 or (v.shape[0] > 1 and v.stride(0) != 1):
+                raise ValueError(f"{nm}: a contiguous float64 CUDA vector is required")
+            arrs.append((int(v.data_ptr()), v.shape[0], v.device.index))
+        else:
+            if not isinstance(v, np.ndarray) or v.dtype != np.float64 or v.ndim != 1 or not v.flags.c_contiguous:
+                raise ValueError(f"{nm}: Buffer dtype mismatch or wrong layout (a contiguous float64 vector is required)")
+            if not v.flags.writeable:
+                raise ValueError(f"{nm}: buffer source array is read-only")
+            arrs.append((v.ctypes.data, v.shape[0], None))
+    n = arrs[1][1]
+    if any(m < n for _, m, _ in arrs):
+        raise ValueError("a, b, c and x must have at least n = len(b) entries")
+    _lib.check(_lib.lib().wlsqm_gtsv(n, arrs[0][0], arrs[1][0], arrs[2][0], arrs[3][0], int(_dev(device, *(d for _, _, d in arrs)))))
+    return 0
+
+
+def _torch_f64():
+    import torch
+    return torch.float64

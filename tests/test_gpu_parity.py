@@ -472,3 +472,48 @@ def test_batched_scalers_vs_reference_golden():
     assert np.array_equal(B[:, :, 2], B0[:, :, 2]) and np.array_equal(B[:, :, 0], g["sq3/S6"][:, :, 0])
     with pytest.raises(ValueError, match="Unknown algorithm"):
         ld.do_rescale(np.asfortranarray(np.eye(3)), 9)
+
+
+def test_single_system_drivers_vs_lapack():
+    """the reference's single-system entry points (general, symmetric, generalfactor/-factored, symmetricfactor/-factored,
+    tridiag; lapackdrivers.pyx:854-1050, 1395-1462) on top of the batched kernels; tridiag = DGTSV incl. its row
+    interchanges and its in-place factors, against SciPy's LAPACK"""
+    from wlsqm_b200.utils import lapackdrivers as ld
+    from scipy.linalg import lapack
+    rng = np.random.default_rng(5)
+    n = 7
+    A = rng.standard_normal((n, n)); b = rng.standard_normal(n)
+    x_ref = np.linalg.solve(A, b)
+    A1, b1 = np.asfortranarray(A.copy()), b.copy()
+    ld.general(A1, b1)
+    assert np.allclose(b1, x_ref, atol=1e-12)
+    LU = np.asfortranarray(A.copy())
+    ipiv = ld.generalfactor(LU)
+    lu_ref, piv_ref, _ = lapack.dgetrf(A)
+    assert np.array_equal(ipiv, piv_ref + 1) and np.allclose(LU, lu_ref, atol=1e-13)
+    b2 = b.copy()
+    ld.generalfactored(LU, ipiv, b2)
+    assert np.allclose(b2, x_ref, atol=1e-12)
+    S = 0.5 * (A + A.T) + n * np.eye(n)
+    S1, b3 = np.asfortranarray(S.copy()), b.copy()
+    ld.symmetric(S1, b3)
+    assert np.allclose(b3, np.linalg.solve(S, b), atol=1e-12)
+    S2 = np.asfortranarray(S.copy())
+    ip2 = ld.symmetricfactor(S2)
+    b4 = b.copy()
+    ld.symmetricfactored(S2, ip2, b4)
+    assert np.allclose(b4, np.linalg.solve(S, b), atol=1e-12)
+    # the reference's own example (tests/test_lapackdrivers.py:26-39): a[0] IS DL[0]
+    a = np.array([0.0, -1.0, -1.0, -1.0]); d = np.full(4, 2.0); c = np.array([-1.0, -1.0, -1.0, 0.0]); x = np.array([1.0, 0.0, 0.0, 1.0])
+    assert ld.tridiag(a, d, c, x) == 0
+    assert np.allclose(x, [0.625, 0.25, 0.5, 0.75], atol=1e-14)
+    # random systems that need row interchanges: solution AND the overwritten factors equal DGTSV's
+    for trial in range(5):
+        m = 9
+        dl, dd, du, rhs = rng.standard_normal(m), 0.1 * rng.standard_normal(m), rng.standard_normal(m), rng.standard_normal(m)
+        dl2, d2, du2, x2, info = lapack.dgtsv(dl[:m - 1].copy(), dd.copy(), du[:m - 1].copy(), rhs.copy())
+        assert info == 0
+        a_, b_, c_, x_ = dl.copy(), dd.copy(), du.copy(), rhs.copy()
+        ld.tridiag(a_, b_, c_, x_)
+        assert np.allclose(x_, x2, rtol=1e-12, atol=1e-13)
+        assert np.allclose(b_, d2, rtol=1e-13) and np.allclose(a_[:m - 1], dl2, rtol=1e-13) and np.allclose(c_[:m - 1], du2, rtol=1e-13)

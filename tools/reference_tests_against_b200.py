@@ -6,10 +6,10 @@ The reference's tests are not part of this repository.  In the build container,
 copies /root/reference/tests into oracle/_ref/_reftests (git-ignored, travels to the GPU box with the compiled
 reference); on the GPU box,
     python tools/reference_tests_against_b200.py --run
-runs the in-scope files (simple / expert / interp / edge cases / stencil / noise robustness / parallel / package) and
-prints pytest's summary; --unstage removes the copy again.  Out of scope by design:
-test_cimport.py (the .pxd-level API) and test_lapackdrivers.py (single-system LAPACK wrappers).  test_package.py
-(import graph, version, ScalingAlgo, number_of_dofs) needs no device and passes too.
+runs the in-scope files (simple / expert / interp / edge cases / stencil / noise robustness / parallel / package /
+lapackdrivers) and prints pytest's summary; --unstage removes the copy again.  Out of scope by design (SURVEY.md 8b,
+DESIGN.md 8): test_cimport.py (the .pxd-level API).  test_package.py (import graph, version, ScalingAlgo,
+number_of_dofs) needs no device and passes too.
 """
 import shutil
 import subprocess
@@ -19,7 +19,7 @@ from pathlib import Path
 ROOT = Path(__file__).resolve().parent.parent
 STAGE = ROOT / "oracle" / "_ref" / "_reftests"
 IN_SCOPE = ["test_simple.py", "test_expert.py", "test_interp.py", "test_edge_cases.py", "test_stencil.py",
-            "test_noise_robustness.py", "test_parallel.py", "test_package.py"]
+            "test_noise_robustness.py", "test_parallel.py", "test_package.py", "test_lapackdrivers.py"]
 
 
 def main():
