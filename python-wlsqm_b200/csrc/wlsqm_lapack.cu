@@ -608,7 +608,7 @@ __global__ void gtsv_kernel(int n, double* __restrict__ dl, double* __restrict__
             const double fact = dl[i] / d[i];
             d[i + 1] -= fact * du[i];
             b[i + 1] -= fact * b[i];
-            dl[i] = 0.0;
+            if (i < n - 2) dl[i] = 0.0;                   // (DGTSV clears DL only in its main loop, not in the last step)
         } else {                                          // interchange rows i and i + 1
             const double fact = d[i] / dl[i];
             d[i] = dl[i];
