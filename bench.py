@@ -591,6 +591,24 @@ def run_b200(args, rank, world, local_rank):
         del out_buf
     except Exception as exc:
         print("gather leg failed: %r" % (exc,), file=sys.stderr)
+    # ---- extension: the same steps without the solver's own copy of the solution (keep_solution(False): the reference's
+    #      Case_set_fi copy, needed only by interpolate) ----
+    nocopy_ms = None
+    try:
+        s.keep_solution(False)
+        for w in range(3):
+            s.solve(fk_d[w % NBUF], fi_d)
+        barrier()
+        e0.record()
+        for t in range(args.steps):
+            s.solve(fk_d[t % NBUF], fi_d)
+        e1.record()
+        barrier()
+        nocopy_ms = e0.elapsed_time(e1) / args.steps
+    except Exception as exc:
+        print("keep_solution leg failed: %r" % (exc,), file=sys.stderr)
+    finally:
+        s.keep_solution(True)
     # the last device-resident state of fi for the e2e check below
     s.solve(fk_d[(args.steps - 1) % NBUF], fi_d)
     torch.cuda.synchronize()
@@ -666,10 +684,12 @@ def run_b200(args, rank, world, local_rank):
     # ---- max over ranks ----
     if dist is not None:
         g = gather or [0.0, 0.0, 0.0]
-        tt = torch.tensor([total_ms, e2e_ms, prep_ms, kern_ms, hoods_ms or 0.0, g[0], g[1], -g[2]], dtype=torch.float64, device=dev)
+        tt = torch.tensor([total_ms, e2e_ms, prep_ms, kern_ms, hoods_ms or 0.0, g[0], g[1], -g[2], nocopy_ms or 0.0],
+                          dtype=torch.float64, device=dev)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        total_ms, e2e_ms, prep_ms, kern_ms, hm, g0, g1, g2 = (float(v) for v in tt.tolist())
+        total_ms, e2e_ms, prep_ms, kern_ms, hm, g0, g1, g2, ncm = (float(v) for v in tt.tolist())
         hoods_ms = hm if hoods_ms else None
+        nocopy_ms = ncm if nocopy_ms else None
         if gather:
             gather = [g0, g1, -g2]
     sh.close()
@@ -748,6 +768,11 @@ def run_b200(args, rank, world, local_rank):
                                                   "(csrc/wlsqm_host.cu); cudaMemcpy from pageable memory gave 29 ms per step"}
         if oneshot:
             line["one_shot_fits"] = oneshot
+        if nocopy_ms:
+            line["solve_without_solution_copy"] = {
+                "ms_per_step": nocopy_ms, "value": world * n / (nocopy_ms * 1e-3), "unit": UNIT,
+                "note": "ExpertSolver.keep_solution(False): the solver's own copy of fi (the reference's Case_set_fi, read only by "
+                        "interpolate) is not written; 8*no bytes per point less than the headline step"}
         if hoods_ms:
             line["e2e_hoods_extension"] = {
                 "value": world * n * e2e_steps / (hoods_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(n * 8),

@@ -203,6 +203,12 @@ WLSQM_API int wlsqm_solver_nearest_models(wlsqm_solver_t* s, const double* x, in
 WLSQM_API int wlsqm_solver_interpolate_continuous(wlsqm_solver_t* s, const double* x, int64_t x_s0, int64_t nx, double r,
                                         int diff, double* out);
 
+/* The reference keeps the solution twice: in the caller's fi and in each Case (Case_set_fi, infra.pyx:780-786), which is
+ * what interpolate() evaluates (expert.pyx:571-699).  A caller that never interpolates can drop the second copy:
+ * keep = 0 makes solve() with a device-resident fi write the caller's array only (8 * no bytes per case less traffic);
+ * interpolate / get_fi then fail with WLSQM_E_NOTREADY until a solve() with keep = 1.  Default: keep = 1. */
+WLSQM_API int wlsqm_solver_keep_solution(wlsqm_solver_t* s, int keep);
+
 /* ---- fused result gather over NVLink peer memory (multi-GPU, one process per GPU) --------------------------------
  * The reference is one process: all cases of a solver write into one fi array (the prange of expert.pyx:536-557).
  * With the cases sharded over GPUs the same array exists once per GPU; instead of an all-gather after the solve, the

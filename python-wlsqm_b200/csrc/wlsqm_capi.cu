@@ -208,6 +208,8 @@ struct wlsqm_solver {
     signed char* dorder = nullptr;
     double* op = nullptr;
     double* fi_case = nullptr;
+    // wlsqm_solver_keep_solution(s, 0): solve() with a device fi writes the caller's array only; interpolate() needs the copy
+    bool keep_solution = true, fi_case_valid = true;
     double* xi_dev = nullptr;
     double* As = nullptr;
     int as_stride = 0;
@@ -863,6 +865,12 @@ int wlsqm_peer_free(void* ptr) {
     if (ptr && cudaFree(ptr) != cudaSuccess) cudaGetLastError();
     return WLSQM_OK;
 }
+int wlsqm_solver_keep_solution(wlsqm_solver_t* s, int keep) {
+    if (!s) return fail(WLSQM_E_VALUE, "NULL solver");
+    s->keep_solution = keep != 0;
+    return WLSQM_OK;
+}
+
 int wlsqm_solver_set_gather(wlsqm_solver_t* s, int ntargets, void* const* bases, int64_t row0, int64_t row_stride) {
     if (!s) return fail(WLSQM_E_VALUE, "NULL solver");
     if (ntargets < 0 || ntargets > WLSQM_MAX_PEERS) return fail(WLSQM_E_VALUE, "between 0 and %d gather targets", WLSQM_MAX_PEERS);
@@ -1016,6 +1024,7 @@ int wlsqm_solver_solve(wlsqm_solver_t* s, const double* fk, int64_t fk_s0, int64
         P.fk = (const double*)s->st_fk.p; P.fk_s0 = s->maxnk; P.fk_s1 = 1;
     }
     bool deferred = false;
+    s->fi_case_valid = true;
     if (fi_dev) {
         P.fi_in = fi; P.fi_in_s0 = fi_s0;
         // the caller's fk may be a view into fi (expert.pyx:548-555): then write back only after all cases are solved
@@ -1028,6 +1037,8 @@ int wlsqm_solver_solve(wlsqm_solver_t* s, const double* fk, int64_t fk_s0, int64
         }
         if (alias) deferred = true;
         else { P.fi_out = fi; P.fi_out_s0 = fi_s0; }
+        if (!s->keep_solution && !deferred) P.fi_case = nullptr;
+        s->fi_case_valid = P.fi_case != nullptr;
     } else if (s->any_knowns) {
         rc = s->st_fi.reserve((size_t)n * s->maxno * 8);
         if (rc) return rc;
@@ -1228,6 +1239,7 @@ int wlsqm_solver_interpolate(wlsqm_solver_t* s, const double* x, int64_t x_s0, c
     if (!s->ready) return fail(WLSQM_E_NOTREADY, "Solver is not in the ready state; prepare() must be called first");
     if (nx == 0) return WLSQM_OK;
     if (!x || !I || !out) return fail(WLSQM_E_VALUE, "x, I and out must not be NULL");
+    if (!s->fi_case_valid) return fail(WLSQM_E_NOTREADY, "the solver keeps no copy of the solution (wlsqm_solver_keep_solution(s, 0)); solve() again with the copy enabled");
     const int size = number_of_dofs(s->dim, 4);
     if (diff != WLSQM_DIFF_ALL && (diff < 0 || diff >= size)) return fail(WLSQM_E_VALUE, "invalid diff %d", diff);
     int rc = use_device(s);
@@ -1303,6 +1315,7 @@ int wlsqm_solver_memory(wlsqm_solver_t* s, int64_t* used, int64_t* total) {
 int wlsqm_solver_get_fi(wlsqm_solver_t* s, double* out, int64_t out_s0) {
     if (!s || !out) return fail(WLSQM_E_VALUE, "NULL argument");
     if (s->ncases == 0) return WLSQM_OK;
+    if (!s->fi_case_valid) return fail(WLSQM_E_NOTREADY, "the solver keeps no copy of the solution (wlsqm_solver_keep_solution(s, 0)); solve() again with the copy enabled");
     int rc = use_device(s);
     if (rc) return rc;
     rc = from_dense(out, out_s0, s->fi_case, s->maxno, s->ncases, s->maxno, s->stream);
@@ -1444,6 +1457,7 @@ int wlsqm_solver_interpolate_continuous(wlsqm_solver_t* s, const double* x, int6
     if (nx == 0) return WLSQM_OK;
     if (!x || !out) return fail(WLSQM_E_VALUE, "x and out must not be NULL");
     if (!(r > 0.0)) return fail(WLSQM_E_VALUE, "r must be positive");
+    if (!s->fi_case_valid) return fail(WLSQM_E_NOTREADY, "the solver keeps no copy of the solution (wlsqm_solver_keep_solution(s, 0)); solve() again with the copy enabled");
     const int size = number_of_dofs(s->dim, 4);
     if (diff < 0 || diff >= size) return fail(WLSQM_E_VALUE, "invalid diff %d", diff);
     int rc = use_device(s);

@@ -344,7 +344,7 @@ __global__ void __launch_bounds__(PK<DIM, ORD>::MAXT, PK<DIM, ORD>::MINB) prepar
                     const int s = t % no, mk = t / no;
                     KN[mk * NOP + s] = -G[s * LDA + R2O[nr + mk]];
                 }
-                if (lane < nkn) W[nk + lane] = 1.0;
+                for (int m = lane; m < nkn; m += 32) W[nk + m] = 1.0;      // (up to 34 known slots: 3D order 4)
                 __syncwarp();
             }
         }

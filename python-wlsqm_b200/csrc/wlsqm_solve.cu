@@ -399,11 +399,11 @@ solve_kernel(SolveParams P) {
 
         // ---- write-back: solver-owned copy (all `no` entries) and, if allowed, the caller's fi ---
         if (in0) {
-            P.fi_case[c * P.fi_case_ld + lane] = v0;
+            if (P.fi_case) P.fi_case[c * P.fi_case_ld + lane] = v0;
             if (P.fi_out && unk0) P.fi_out[c * P.fi_out_s0 + lane] = v0;
         }
         if (in1) {
-            P.fi_case[c * P.fi_case_ld + lane + 32] = v1;
+            if (P.fi_case) P.fi_case[c * P.fi_case_ld + lane + 32] = v1;
             if (P.fi_out && unk1) P.fi_out[c * P.fi_out_s0 + lane + 32] = v1;
         }
         if (P.ngather) {
@@ -554,7 +554,7 @@ __global__ void __launch_bounds__(SOLVE_MAX_THREADS) solve_pack_kernel(SolvePara
             if (nk + nkn == 0) v = __longlong_as_double(0x7ff8000000000000LL);
         }
         if (valid) {
-            P.fi_case[c * P.fi_case_ld + o] = v;
+            if (P.fi_case) P.fi_case[c * P.fi_case_ld + o] = v;
             if (P.fi_out && !isk) P.fi_out[c * P.fi_out_s0 + o] = v;
             if (P.ngather) {
                 const long long g = (P.gather_row0 + c) * P.gather_s0 + o;

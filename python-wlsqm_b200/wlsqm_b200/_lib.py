@@ -70,6 +70,7 @@ SIGNATURES = {
     "wlsqm_peer_open": (_int, [_int, _vp, C.POINTER(_vp)]),
     "wlsqm_peer_close": (_int, [_vp]),
     "wlsqm_peer_free": (_int, [_vp]),
+    "wlsqm_solver_keep_solution": (_int, [_vp, _int]),
     "wlsqm_solver_set_gather": (_int, [_vp, _int, C.POINTER(_vp), _i64, _i64]),
     "wlsqm_mgetrf": (_int, [_int, _i64, _vp, _vp, _int]),
     "wlsqm_mgetrs": (_int, [_int, _i64, _vp, _vp, _vp, _int]),

@@ -39,6 +39,7 @@ cdef extern from "wlsqm_b200.h" nogil:
     int wlsqm_solver_prepare_guest(wlsqm_solver_t* s)
     int wlsqm_solver_destroy(wlsqm_solver_t* s)
     int wlsqm_solver_set_stream(wlsqm_solver_t* s, void* cuda_stream)
+    int wlsqm_solver_keep_solution(wlsqm_solver_t* s, int keep)
     int wlsqm_solver_synchronize(wlsqm_solver_t* s)
     int wlsqm_set_caller_stream(void* cuda_stream)
     int wlsqm_solver_prepare(wlsqm_solver_t* s, const double* xi, int64_t xi_s0, const double* xk, int64_t xk_s0, int64_t xk_s1)
@@ -494,6 +495,12 @@ class ExpertSolver:
         if sp is not None and sp != self._stream:
             _check(wlsqm_solver_set_stream(_h(self), <void*><uintptr_t>sp))
             self._stream = sp
+
+    def keep_solution(self, keep=True):
+        """Extension: keep=False drops the solver's own copy of the solution (the reference's Case_set_fi, infra.pyx:780-786)
+        for solve() calls with a CUDA-tensor fi: 8*no bytes per case less traffic; interpolate() then raises until a
+        solve() with the copy enabled."""
+        _check(wlsqm_solver_keep_solution(_h(self), 1 if keep else 0))
 
     def synchronize(self):
         """Wait for everything enqueued by this solver (only needed with CUDA-tensor arguments)."""

@@ -162,6 +162,12 @@ class ExpertSolver:
             _lib.check(_lib.lib().wlsqm_solver_set_stream(self._handle, sp))
             self._stream = sp
 
+    def keep_solution(self, keep=True):
+        """Extension: keep=False drops the solver's own copy of the solution (the reference's Case_set_fi, infra.pyx:780-786)
+        for solve() calls with a CUDA-tensor fi: 8*no bytes per case less traffic; interpolate() then raises until a
+        solve() with the copy enabled."""
+        _lib.check(_lib.lib().wlsqm_solver_keep_solution(self._handle, 1 if keep else 0))
+
     def synchronize(self):
         """Wait for everything enqueued by this solver (only needed with CUDA-tensor arguments)."""
         _lib.check(_lib.lib().wlsqm_solver_synchronize(self._handle))

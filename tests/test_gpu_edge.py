@@ -351,3 +351,43 @@ def test_host_sens_and_fi_go_back_in_chunks(hetero, monkeypatch):
     s.solve(fk, fi_l, sens_l)
     assert np.array_equal(fi_l, ref_fi) and np.array_equal(np.nan_to_num(sens_l), np.nan_to_num(ref_sens))
     wlsqm.pinned_free(sens_l); wlsqm.pinned_free(fi_l)
+
+
+@pytest.mark.parametrize("algo", ["basic", "iterative"])
+def test_solution_copy_can_be_dropped_for_device_outputs(algo):
+    """keep_solution(False): solve() with a CUDA-tensor fi writes the same bits into the caller's array and nothing into
+    the solver's own copy (the reference's Case_set_fi); interpolate() refuses until a solve() that keeps the copy;
+    host outputs are unaffected (they are read back from the solver's copy)"""
+    torch = pytest.importorskip("torch")
+    n, k = 3000, 14
+    x, hoods, f = parity.make_case(n, 2, k)
+    nk, od, kn, wm = _meta(n, k, 3, 0b10, 2)                      # (a known DOF: fi keeps the caller's value there)
+    xk, fk = parity.gathered(x, f, hoods)
+    fi0 = np.zeros((n, 10)); fi0[:, 1] = 0.25
+    A = wlsqm.ALGO_ITERATIVE if algo == "iterative" else wlsqm.ALGO_BASIC
+    s = wlsqm.ExpertSolver(2, nk, od, kn, wm, algorithm=A)
+    s.prepare(x, xk)
+    want = fi0.copy()
+    it_want = s.solve(fk, want)
+    xq = x[:50] + 1e-3
+    I = np.arange(50, dtype=np.int64)
+    s.prep_interpolate()
+    out_want, _ = s.interpolate(xq, mode='nearest', diff=0, I=I)
+
+    fk_d = torch.from_numpy(fk).cuda()
+    s.keep_solution(False)
+    got = torch.from_numpy(fi0).cuda()
+    it_got = s.solve(fk_d, got)
+    assert np.array_equal(got.cpu().numpy(), want) and it_got == it_want
+    with pytest.raises(RuntimeError, match="keeps no copy"):
+        s.interpolate(xq, mode='nearest', diff=0, I=I)
+    host = fi0.copy()
+    s.solve(fk, host)                                             # host output: staged through the copy, which is valid again
+    assert np.array_equal(host, want)
+    out, _ = s.interpolate(xq, mode='nearest', diff=0, I=I)
+    assert np.array_equal(out, out_want)
+    s.keep_solution(True)
+    got2 = torch.from_numpy(fi0).cuda()
+    s.solve(fk_d, got2)
+    out, _ = s.interpolate(xq, mode='nearest', diff=0, I=I)
+    assert np.array_equal(got2.cpu().numpy(), want) and np.array_equal(out, out_want)

@@ -121,6 +121,67 @@ def test_heterogeneous_batch(dim, bucketed, monkeypatch):
         assert np.array_equal(np.isnan(sens_g), np.isnan(sens_u))
 
 
+@pytest.mark.parametrize("dim,algo,seed", [(1, 1, 11), (1, 2, 12), (2, 1, 13), (2, 2, 14), (3, 1, 15), (3, 2, 16)])
+def test_random_knowns_masks_orders_and_sizes(dim, algo, seed):
+    """every case draws its own order, ARBITRARY knowns bitmask (any subset of its DOFs, including none and all but
+    one -- the reference's remap(), infra.pyx:145-200, not only the b*_F / b*_XY patterns of its tests), weighting and
+    neighbour count; both algorithms, all three dimensions.  Criterion: the per-order-group noise floor of
+    tests/parity.py; untouched entries (known slots, columns past no_j) stay bit-for-bit."""
+    n = 1500 if dim == 3 else 2500
+    kmax = {1: 12, 2: 30, 3: 60}[dim]
+    nomax = wlsqm.number_of_dofs(dim, 4)
+    x, hoods, f = parity.make_case(n, dim, kmax, seed=seed)
+    xk, fk = parity.gathered(x, f, hoods)
+    rng = np.random.default_rng(seed)
+    od = rng.integers(0, 5, n).astype(np.int32)
+    no = np.array([wlsqm.number_of_dofs(dim, int(o)) for o in od])
+    kn = np.zeros(n, np.int64)
+    for j in range(n):
+        bits = rng.random(no[j]) < rng.choice([0.0, 0.15, 0.5, 0.9])
+        if bits.all():
+            bits[rng.integers(no[j])] = False                     # (at least one unknown)
+        kn[j] = int(sum(1 << o for o in range(no[j]) if bits[o]))
+    nr = np.array([no[j] - bin(int(kn[j])).count("1") for j in range(n)])
+    lo = np.minimum(kmax, np.maximum(nr + 2, (3 * nr) // 2 + 1))
+    nk = rng.integers(lo, kmax + 1).astype(np.int32)
+    wm = rng.integers(1, 3, n).astype(np.int32)
+    # known slots hold the exact derivatives of the sampled field where the model has them (else a fit with made-up
+    # "known" derivatives is far from the data and only tests conditioning), other slots random
+    fi0 = rng.standard_normal((n, nomax))
+    exact, _, _, _ = parity.oracle_solve(dim, np.full(n, kmax, np.int32), np.full(n, 4, np.int32), np.zeros(n, np.int64),
+                                         np.ones(n, np.int32), x, xk, fk, np.zeros((n, nomax)), 1)
+    for j in range(n):
+        for o in range(no[j]):
+            if kn[j] >> o & 1:
+                fi0[j, o] = exact[j, o]
+    fi_g, sens_g, it_g, _ = _run_gpu(dim, nk, od, kn, wm, x, xk, fk, fi0, algo, True, max_iter=6)
+    fi_o, sens_o, it_o, _ = parity.oracle_solve(dim, nk, od, kn, wm, x, xk, fk, fi0, algo, True, max_iter=6)
+    # (the maximum over a few hundred cases is a heavy-tailed statistic -- one case leaving its refinement loop a round
+    # earlier under another summation order moves it by 5x: eight permutations for the floor)
+    a, b = parity.hetero_self_noise(dim, nk, od, kn, wm, x, xk, fk, fi0, algo, max_iter=6, seeds=tuple(range(7, 15)))
+
+    def untouched(fi):
+        for j in range(n):
+            assert np.array_equal(fi[j, no[j]:], fi0[j, no[j]:])
+            for o in range(no[j]):
+                if kn[j] >> o & 1:
+                    assert fi[j, o] == fi0[j, o]
+    untouched(fi_g)
+    print(parity.check_hetero_against_floor(fi_g, fi_o, b + (fi_o - a), dim, od, "random masks %dD algo %d" % (dim, algo)))
+    parity.check_sens(sens_g, sens_o, "random masks %dD algo %d" % (dim, algo))
+    if algo == 2:
+        assert it_g == it_o, (it_g, it_o)
+    # the one-shot entry points on the same batch (simple.pyx fit_*D_many / fit_*D_iterative_many: the fused kernel for
+    # ALGO_BASIC without sens, which eliminates the knowns in its own way)
+    fi_1 = fi0.copy()
+    if algo == 1:
+        getattr(wlsqm, "fit_%dD_many_parallel" % dim)(xk, fk, nk, x, fi_1, None, 0, od, kn, wm)
+    else:
+        getattr(wlsqm, "fit_%dD_iterative_many" % dim)(xk, fk, nk, x, fi_1, None, 0, od, kn, wm, max_iter=6)
+    untouched(fi_1)
+    print(parity.check_hetero_against_floor(fi_1, fi_o, b + (fi_o - a), dim, od, "random masks, one-shot %dD algo %d" % (dim, algo)))
+
+
 @pytest.mark.parametrize("dim,do_sens", [(2, True), (2, False), (3, True), (3, False)])
 def test_heterogeneous_batch_iterative(dim, do_sens):
     """per-case records AND ALGO_ITERATIVE (solve_kernel<DIM, ITER = true, SENS, UNI = false>): the in-kernel refinement
