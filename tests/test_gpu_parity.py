@@ -490,6 +490,41 @@ def test_msymmetric_drivers_vs_reference_golden_and_lapack():
         assert np.array_equal(b_t.cpu().numpy(), x)
 
 
+def test_batched_drivers_every_size():
+    """mgeneral* / msymmetric* for EVERY matrix size from 1 to 72 (the kernels switch layouts at 16, 32 and 64 rows, and the
+    batch count is not a multiple of anything): pivots exact against the oracle's dgetf2 / dsytf2 restatements, solutions
+    against numpy"""
+    from wlsqm_b200.utils import lapackdrivers as ld
+    rng = np.random.default_rng(5)
+    for n in range(1, 73):
+        nlhs = 37
+        A = np.asfortranarray(rng.standard_normal((n, n, nlhs)))
+        b = np.asfortranarray(rng.standard_normal((n, nlhs)))
+        x_ref = np.stack([np.linalg.solve(A[:, :, l], b[:, l]) for l in range(nlhs)], axis=1)
+        LU, ipiv = A.copy(order="F"), np.zeros((n, nlhs), dtype=np.int32, order="F")
+        ld.mgeneralfactor(LU, ipiv)
+        LUo, ipo = A.copy(order="F"), np.zeros_like(ipiv)
+        orc.mgetrf(LUo, ipo)
+        assert np.array_equal(ipiv, ipo), n
+        assert np.allclose(LU, LUo, rtol=1e-8, atol=1e-10), n
+        x = b.copy(order="F")
+        ld.mgeneralfactored(LU, ipiv, x)
+        err = np.abs(x - x_ref).max(axis=0) / np.abs(x_ref).max(axis=0)
+        assert np.median(err) < 1e-11 and err.max() < 1e-6, (n, err.max())
+        S = np.asfortranarray(0.5 * (A + A.transpose(1, 0, 2)))
+        S[np.arange(n), np.arange(n), ::3] *= 1e-3
+        xs_ref = np.stack([np.linalg.solve(S[:, :, l], b[:, l]) for l in range(nlhs)], axis=1)
+        F, ips = S.copy(order="F"), np.zeros((n, nlhs), dtype=np.int32, order="F")
+        ld.msymmetricfactor(F, ips)
+        Fo, ipso = S.copy(order="F"), np.zeros_like(ips)
+        orc.msytrf(Fo, ipso)
+        assert np.array_equal(ips, ipso), n
+        xs = b.copy(order="F")
+        ld.msymmetricfactored(F, ips, xs)
+        err = np.abs(xs - xs_ref).max(axis=0) / np.abs(xs_ref).max(axis=0)
+        assert np.median(err) < 1e-11 and err.max() < 1e-6, (n, err.max())
+
+
 def test_batched_scalers_vs_reference_golden():
     """mdo_rescale / do_rescale / rescale_* (SURVEY 8f item 4): one launch over a batch of matrices against the unmodified
     reference's do_rescale applied matrix by matrix (tests/golden/golden_scale.npz) -- scale vectors and scaled matrices
