@@ -180,6 +180,59 @@ def test_random_knowns_masks_orders_and_sizes(dim, algo, seed):
         getattr(wlsqm, "fit_%dD_iterative_many" % dim)(xk, fk, nk, x, fi_1, None, 0, od, kn, wm, max_iter=6)
     untouched(fi_1)
     print(parity.check_hetero_against_floor(fi_1, fi_o, b + (fi_o - a), dim, od, "random masks, one-shot %dD algo %d" % (dim, algo)))
+    # the fitted models evaluated at random points: every slot in one pass and a few single slots (expert.pyx:687-781;
+    # per-model orders), same coefficients on both sides
+    s = wlsqm.ExpertSolver(dim, nk, od, kn, wm, algorithm=algo, max_iter=6, ntasks=1)
+    s.prepare(x, xk)
+    fi_s = fi0.copy()
+    s.solve(fk, fi_s)
+    s.prep_interpolate()
+    nq = 1501
+    I = rng.integers(0, n, nq).astype(np.int64)
+    xq = x[I] + 2e-3 * rng.uniform(-1, 1, x[I].shape)
+    so = orc.OracleSolver(dim, nk, od, kn, wm)
+    so.xi = x
+    so.fi = fi_s.copy()
+    out_all, _ = s.interpolate(xq, diff='all', I=I)
+    for d in sorted(set([0, nomax - 1] + rng.integers(0, nomax, 3).tolist())):
+        og, _ = s.interpolate(xq, diff=d, I=I)
+        oo = so.interpolate(xq, I, d)
+        assert np.array_equal(np.isnan(og), np.isnan(oo)), d
+        assert np.nanmax(np.abs(og - oo), initial=0.0) <= 1e-12 * max(np.nanmax(np.abs(oo), initial=0.0), 1e-300), d
+        assert np.nanmax(np.abs(out_all[:, d] - oo), initial=0.0) <= 1e-12 * max(np.nanmax(np.abs(oo), initial=0.0), 1e-300), d
+
+
+@pytest.mark.parametrize("dim,order,k,nkn,algo,seed", [
+    (1, 4, 9, 1, 1, 21), (1, 3, 8, 2, 1, 22), (2, 3, 24, 1, 1, 23), (2, 4, 30, 3, 1, 24), (2, 2, 12, 2, 1, 25),
+    (3, 2, 20, 2, 1, 26), (3, 4, 60, 33, 1, 27), (3, 3, 40, 4, 2, 28), (2, 4, 30, 2, 2, 29)])
+def test_random_knowns_patterns_of_equal_count(dim, order, k, nkn, algo, seed):
+    """same sizes everywhere, but every case knows a DIFFERENT set of nkn DOFs: the geometry-uniform kernels (one size
+    record by value, one 8-byte mask per case; the packed solve for the small models) against the oracle"""
+    n = 1200 if dim == 3 else 3000
+    no = wlsqm.number_of_dofs(dim, order)
+    x, hoods, f = parity.make_case(n, dim, k, seed=seed)
+    xk, fk = parity.gathered(x, f, hoods)
+    rng = np.random.default_rng(seed)
+    kn = np.array([int(sum(1 << int(o) for o in rng.choice(no, nkn, replace=False))) for _ in range(n)], np.int64)
+    nk, od, _, wm = _uniform_meta(n, k, order, 0, 2)
+    exact, _, _, _ = parity.oracle_solve(dim, nk, od, np.zeros(n, np.int64), wm, x, xk, fk, np.zeros((n, no)), 1)
+    fi0 = np.where((kn[:, None] >> np.arange(no)[None, :]) & 1, exact, rng.standard_normal((n, no)))
+    fi_g, sens_g, it_g, _ = _run_gpu(dim, nk, od, kn, wm, x, xk, fk, fi0, algo, True, max_iter=5)
+    fi_o, sens_o, it_o, _ = parity.oracle_solve(dim, nk, od, kn, wm, x, xk, fk, fi0, algo, True, max_iter=5)
+    a, b = parity.hetero_self_noise(dim, nk, od, kn, wm, x, xk, fk, fi0, algo, max_iter=5, seeds=tuple(range(7, 13)))
+    known = ((kn[:, None] >> np.arange(no)[None, :]) & 1).astype(bool)
+    assert np.array_equal(fi_g[known], fi0[known])
+    print(parity.check_against_floor(fi_g, fi_o, b + (fi_o - a), dim, order, "equal-count masks %dD o%d" % (dim, order)))
+    parity.check_sens(sens_g, sens_o, "equal-count masks")
+    if algo == 2:
+        assert it_g == it_o
+    # CUDA tensors (no staging; strided fk view)
+    torch = pytest.importorskip("torch")
+    s = wlsqm.ExpertSolver(dim, nk, od, kn, wm, algorithm=algo, max_iter=5)
+    s.prepare(torch.from_numpy(x).cuda(), torch.from_numpy(xk).cuda())
+    fi_d = torch.from_numpy(fi0).cuda()
+    s.solve(torch.from_numpy(fk).cuda(), fi_d)
+    assert np.array_equal(fi_d.cpu().numpy(), fi_g)
 
 
 @pytest.mark.parametrize("dim,do_sens", [(2, True), (2, False), (3, True), (3, False)])
