@@ -1012,6 +1012,7 @@ int wlsqm_solver_solve(wlsqm_solver_t* s, const double* fk, int64_t fk_s0, int64
     P.ngather = s->ngather;
     for (int p = 0; p < s->ngather; ++p) P.gather[p] = s->gather[p];
     P.gather_row0 = s->gather_row0; P.gather_s0 = s->gather_s0;
+    P.gather_full = (s->ngather > 0 && s->gather_s0 % 16 == 0 && s->gather_s0 <= 32 && s->gather_s0 > s->maxno) ? 1 : 0;
 
     // ---- device-side views of the arguments (host arrays get dense device mirrors) -------------------
     const bool staged = !fk_dev || !fi_dev || !sens_dev;

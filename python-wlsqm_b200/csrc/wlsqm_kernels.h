@@ -77,6 +77,7 @@ struct SolveParams {
     int ngather;
     double* gather[WLSQM_MAX_PEERS];
     long long gather_row0, gather_s0;
+    int gather_full;                                 // rows are whole 128 B lines (gather_s0 a multiple of 16, <= 32): the padding is stored too
 };
 
 struct InterpParams {

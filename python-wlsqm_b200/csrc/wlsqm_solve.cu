@@ -411,8 +411,12 @@ solve_kernel(SolveParams P) {
             // over NVLink; 8 * no bytes per peer against the 8 * nq * nr bytes of the block just streamed)
             const long long g = (P.gather_row0 + c) * P.gather_s0;
 #pragma unroll 1
+            // (rows padded to whole 128 B lines: the padding lanes store zeros, so that every row crosses NVLink as full-line
+            // writes instead of two partial ones with byte enables)
+            const bool w0 = in0 || (P.gather_full && lane < (int)P.gather_s0);
+            const double s0v = in0 ? v0 : 0.0;
             for (int p = 0; p < P.ngather; ++p) {
-                if (in0) P.gather[p][g + lane] = v0;
+                if (w0) P.gather[p][g + lane] = s0v;
                 if (in1) P.gather[p][g + lane + 32] = v1;
             }
         }

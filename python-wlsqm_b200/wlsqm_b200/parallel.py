@@ -16,6 +16,7 @@ at all.  The only communication is assembling the global ``fi`` for callers that
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -106,12 +107,13 @@ def all_gather_rows(local, ranges, out=None, group=None):
 class _CudaBuffer:
     """a raw device allocation seen by torch through ``__cuda_array_interface__`` (the fused gather's global array)"""
 
-    def __init__(self, ptr, shape):
+    def __init__(self, ptr, shape, row_stride=None):
         self.ptr, self.shape = int(ptr), tuple(int(s) for s in shape)
+        self.strides = None if row_stride is None or row_stride == self.shape[1] else (8 * int(row_stride), 8)
 
     @property
     def __cuda_array_interface__(self):
-        return {"shape": self.shape, "typestr": "<f8", "data": (self.ptr, False), "version": 2, "strides": None}
+        return {"shape": self.shape, "typestr": "<f8", "data": (self.ptr, False), "version": 2, "strides": self.strides}
 
 
 class ShardedExpertSolver:
@@ -181,7 +183,12 @@ class ShardedExpertSolver:
             raise ValueError("the fused gather serves the GPUs of one NVSwitch domain (<= 8)")
         L = _lib.lib()
         dev = self.solver.device
-        nbytes = max(1, self.n_total * self.maxno * 8)
+        # rows padded to whole 128 B lines where that costs <= 10 % (2D order 4: 15 -> 16 doubles): full-line NVLink writes
+        stride = -(-self.maxno // 16) * 16
+        if stride > 32 or stride > 1.1 * self.maxno or os.environ.get("WLSQM_GATHER_PAD", "1") == "0":
+            stride = self.maxno
+        self.gather_stride = stride
+        nbytes = max(1, self.n_total * stride * 8)
         ptr, handle = C.c_void_p(), (C.c_char * 64)()
         _lib.check(L.wlsqm_peer_alloc(dev, nbytes, C.byref(ptr), handle))
         self._own = ptr
@@ -199,8 +206,8 @@ class ShardedExpertSolver:
                 _lib.check(L.wlsqm_peer_open(dev, handles[r], C.byref(p)))
                 self._peers.append(p)
                 bases[r] = p.value
-        _lib.check(L.wlsqm_solver_set_gather(self.solver._handle, self.world, bases, self.lo, self.maxno))
-        self.fi_global = torch.as_tensor(_CudaBuffer(ptr.value, (self.n_total, self.maxno)), device=torch.device("cuda", dev))
+        _lib.check(L.wlsqm_solver_set_gather(self.solver._handle, self.world, bases, self.lo, stride))
+        self.fi_global = torch.as_tensor(_CudaBuffer(ptr.value, (self.n_total, self.maxno), stride), device=torch.device("cuda", dev))
         self._sync = torch.zeros(1, dtype=torch.int32, device=self.fi_global.device)
         self._group = group
         if self.world > 1:
