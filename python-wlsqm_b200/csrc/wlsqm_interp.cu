@@ -223,6 +223,12 @@ static cudaError_t launch_interp_m(const InterpParams& P, unsigned blocks, size_
     const int minb = forced > 0 ? forced : (DIM == 3 ? 2 : 4);
     if (minb <= 2) return launch_interp_t<DIM, ALL, STAGE, 2>(P, blocks, smem, st);
     if (minb == 3) return launch_interp_t<DIM, ALL, STAGE, 3>(P, blocks, smem, st);
+    if constexpr (!ALL && DIM < 3) {
+        // one slot per call: a short dependent chain (index -> model row -> a dozen FMAs) bound by load latency; more
+        // resident CTAs hide more of it (tuning points: 5 CTAs = 51 registers, 6 CTAs = 42)
+        if (minb == 5) return launch_interp_t<DIM, ALL, STAGE, 5>(P, blocks, smem, st);
+        if (minb >= 6) return launch_interp_t<DIM, ALL, STAGE, 6>(P, blocks, smem, st);
+    }
     return launch_interp_t<DIM, ALL, STAGE, 4>(P, blocks, smem, st);
 }
 
