@@ -31,7 +31,7 @@
 namespace wlsqm {
 
 constexpr int INTERP_THREADS = 256;
-constexpr int INTERP_Q = 4;        // queries per thread
+constexpr int INTERP_Q = 4;        // queries per thread (all slots); the one-slot kernels in 1D / 2D take 2, see launch_interp_m
 
 // In-place Taylor shift of the coefficient array along one axis: afterwards u[(a, b, c)] holds the a-th partial
 // derivative along AXIS, at offset h, of the line of coefficients with the other two exponents fixed.
@@ -61,10 +61,9 @@ __device__ __forceinline__ void taylor_shift(double (&u)[max_no<DIM>()], double 
 // ALL = every derivative slot (WLSQM_DIFF_ALL); STAGE = transpose the warp's results through shared memory.
 // Each thread owns INTERP_Q queries, blockDim apart (coalesced), and issues their index and coordinate loads
 // together before the dependent model-row loads: the kernel is bound by load latency, not by arithmetic.
-template <int DIM, bool ALL, bool STAGE, int MINB>
+template <int DIM, bool ALL, bool STAGE, int MINB, int Q>
 __global__ void __launch_bounds__(INTERP_THREADS, MINB) interpolate_kernel(InterpParams P) {
     constexpr int NO = max_no<DIM>();
-    constexpr int Q = INTERP_Q;
     extern __shared__ __align__(16) double stage[];     // STAGE: [warps][32 * no]
     const long long base = (long long)blockIdx.x * (blockDim.x * Q) + threadIdx.x;
     long long idx[Q];
@@ -206,50 +205,84 @@ cudaError_t launch_interpolate_continuous(const InterpParams& P, const GridView&
     return cudaGetLastError();
 }
 
-template <int DIM, bool ALL, bool STAGE, int MINB>
-static cudaError_t launch_interp_t(const InterpParams& P, unsigned blocks, size_t smem, cudaStream_t st) {
+template <int DIM, bool ALL, bool STAGE, int MINB, int Q>
+static cudaError_t launch_interp_t(const InterpParams& P, size_t smem, cudaStream_t st) {
     if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(interpolate_kernel<DIM, ALL, STAGE, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(interpolate_kernel<DIM, ALL, STAGE, MINB, Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
-    interpolate_kernel<DIM, ALL, STAGE, MINB><<<blocks, INTERP_THREADS, smem, st>>>(P);
+    const long long per_block = (long long)INTERP_THREADS * Q;
+    const unsigned blocks = (unsigned)((P.nx + per_block - 1) / per_block);
+    interpolate_kernel<DIM, ALL, STAGE, MINB, Q><<<blocks, INTERP_THREADS, smem, st>>>(P);
     return cudaGetLastError();
 }
 
-// resident CTAs per SM the register budget is held to (WLSQM_INTERP_MINB overrides, for tuning)
+// Resident CTAs per SM the register budget is held to, and queries per thread (WLSQM_INTERP_MINB / WLSQM_INTERP_Q override,
+// for tuning).  All slots: 4 queries per thread at 4 CTAs (2 in 3D) -- the Taylor shift holds the whole model in
+// registers.  One slot per call (the reference's interface) is a short dependent chain -- query index -> model row -> a
+// dozen FMAs -- bound by load latency: TWO queries per thread fit 32 registers without spills, i.e. 8 CTAs = every warp
+// slot of the SM (measured, 16M queries 2D: 4 queries x 4 CTAs 0.196 ms, 4 x 6 0.164, 4 x 8 with spills 0.151,
+// 2 x 8 0.144 ms; the reference's 15 calls 2.14 -> 1.59 ms = 0.94 of the HBM peak).
 template <int DIM, bool ALL, bool STAGE>
-static cudaError_t launch_interp_m(const InterpParams& P, unsigned blocks, size_t smem, cudaStream_t st) {
+static cudaError_t launch_interp_m(const InterpParams& P, size_t smem, cudaStream_t st) {
     static const int forced = [] { const char* v = getenv("WLSQM_INTERP_MINB"); return (v && *v) ? atoi(v) : 0; }();
-    const int minb = forced > 0 ? forced : (DIM == 3 ? 2 : 4);
-    if (minb <= 2) return launch_interp_t<DIM, ALL, STAGE, 2>(P, blocks, smem, st);
-    if (minb == 3) return launch_interp_t<DIM, ALL, STAGE, 3>(P, blocks, smem, st);
+    static const int forced_q = [] { const char* v = getenv("WLSQM_INTERP_Q"); return (v && *v) ? atoi(v) : 0; }();
     if constexpr (!ALL && DIM < 3) {
-        // one slot per call: a short dependent chain (index -> model row -> a dozen FMAs) bound by load latency; more
-        // resident CTAs hide more of it (tuning points: 5 CTAs = 51 registers, 6 CTAs = 42)
-        if (minb == 5) return launch_interp_t<DIM, ALL, STAGE, 5>(P, blocks, smem, st);
-        if (minb >= 6) return launch_interp_t<DIM, ALL, STAGE, 6>(P, blocks, smem, st);
+        const int minb = forced > 0 ? forced : 8;
+        const int q = forced_q > 0 ? forced_q : 2;
+        if (q >= 4) {
+            if (minb <= 4) return launch_interp_t<DIM, ALL, STAGE, 4, 4>(P, smem, st);
+            if (minb <= 6) return launch_interp_t<DIM, ALL, STAGE, 6, 4>(P, smem, st);
+            return launch_interp_t<DIM, ALL, STAGE, 8, 4>(P, smem, st);
+        }
+        if (q == 1) return launch_interp_t<DIM, ALL, STAGE, 8, 1>(P, smem, st);
+        if (minb <= 4) return launch_interp_t<DIM, ALL, STAGE, 4, 2>(P, smem, st);
+        if (minb <= 6) return launch_interp_t<DIM, ALL, STAGE, 6, 2>(P, smem, st);
+        return launch_interp_t<DIM, ALL, STAGE, 8, 2>(P, smem, st);
+    } else if constexpr (!ALL) {
+        // 3D: 35 coefficients per model; ONE query per thread at 8 CTAs (31 registers, a few spilled words) beats every
+        // other point (8M queries, value / highest slot: 4 x 3 CTAs 0.213 / 0.102 ms, 2 x 6 0.151 / 0.087, 1 x 8 0.141 / 0.085)
+        const int minb = forced > 0 ? forced : 8;
+        const int q = forced_q > 0 ? forced_q : 1;
+        if (q >= 4) {
+            if (minb <= 2) return launch_interp_t<DIM, ALL, STAGE, 2, 4>(P, smem, st);
+            if (minb == 3) return launch_interp_t<DIM, ALL, STAGE, 3, 4>(P, smem, st);
+            return launch_interp_t<DIM, ALL, STAGE, 4, 4>(P, smem, st);
+        }
+        if (q == 1) {
+            if (minb <= 5) return launch_interp_t<DIM, ALL, STAGE, 5, 1>(P, smem, st);
+            if (minb <= 6) return launch_interp_t<DIM, ALL, STAGE, 6, 1>(P, smem, st);
+            return launch_interp_t<DIM, ALL, STAGE, 8, 1>(P, smem, st);
+        }
+        if (minb <= 2) return launch_interp_t<DIM, ALL, STAGE, 2, 2>(P, smem, st);
+        if (minb == 3) return launch_interp_t<DIM, ALL, STAGE, 3, 2>(P, smem, st);
+        if (minb == 4) return launch_interp_t<DIM, ALL, STAGE, 4, 2>(P, smem, st);
+        if (minb == 5) return launch_interp_t<DIM, ALL, STAGE, 5, 2>(P, smem, st);
+        return launch_interp_t<DIM, ALL, STAGE, 6, 2>(P, smem, st);
+    } else {
+        const int minb = forced > 0 ? forced : (DIM == 3 ? 2 : 4);
+        if (minb <= 2) return launch_interp_t<DIM, ALL, STAGE, 2, INTERP_Q>(P, smem, st);
+        if (minb == 3) return launch_interp_t<DIM, ALL, STAGE, 3, INTERP_Q>(P, smem, st);
+        return launch_interp_t<DIM, ALL, STAGE, 4, INTERP_Q>(P, smem, st);
     }
-    return launch_interp_t<DIM, ALL, STAGE, 4>(P, blocks, smem, st);
 }
 
 template <int DIM>
-static cudaError_t launch_interp_d(const InterpParams& P, unsigned blocks, size_t smem, cudaStream_t st) {
-    if (P.diff >= 0) return launch_interp_m<DIM, false, false>(P, blocks, 0, st);
-    if (P.stage_no > 0) return launch_interp_m<DIM, true, true>(P, blocks, smem, st);
-    return launch_interp_m<DIM, true, false>(P, blocks, 0, st);
+static cudaError_t launch_interp_d(const InterpParams& P, size_t smem, cudaStream_t st) {
+    if (P.diff >= 0) return launch_interp_m<DIM, false, false>(P, 0, st);
+    if (P.stage_no > 0) return launch_interp_m<DIM, true, true>(P, smem, st);
+    return launch_interp_m<DIM, true, false>(P, 0, st);
 }
 
 cudaError_t launch_interpolate(const InterpParams& Pin, cudaStream_t st) {
     if (Pin.nx == 0) return cudaSuccess;
     InterpParams P = Pin;
-    const long long per_block = (long long)INTERP_THREADS * INTERP_Q;
-    const unsigned blocks = (unsigned)((P.nx + per_block - 1) / per_block);
     size_t smem = 0;
     if (P.diff < 0 && P.stage_no > 0) smem = (size_t)(INTERP_THREADS / 32) * 32 * P.stage_no * sizeof(double);
     else P.stage_no = 0;
-    if (P.dim == 1) return launch_interp_d<1>(P, blocks, smem, st);
-    if (P.dim == 2) return launch_interp_d<2>(P, blocks, smem, st);
-    return launch_interp_d<3>(P, blocks, smem, st);
+    if (P.dim == 1) return launch_interp_d<1>(P, smem, st);
+    if (P.dim == 2) return launch_interp_d<2>(P, smem, st);
+    return launch_interp_d<3>(P, smem, st);
 }
 
 }  // namespace wlsqm
