@@ -6,6 +6,7 @@
 namespace wlsqm {
 
 constexpr int PREP_MAX_THREADS = 512;        // shared-memory variant (wlsqm_prepare_smem.cu)
+constexpr int PREP_REG_MAX_THREADS = 640;    // largest launch bound among the instantiations (2D order 4: 20 warps at 96 registers)
 constexpr int PREP_REG_THREADS = 512;        // register/DMMA variant (wlsqm_prepare.cu): launch bound; the host picks the CTA size
 constexpr int WLSQM_MAX_PEERS = 8;           // GPUs of one NVSwitch domain that can receive the fused gather
 constexpr int PREP_CB = 36;                  // row stride (doubles) inside a 32-column block of the monomial table
@@ -102,6 +103,7 @@ cudaError_t launch_prepare_smem(int dim, const PrepareParams& P, int blocks, int
 int prep_reg_fit_doubles(int dim, int maxorder, int nb, int nkn_max);
 int prep_reg_warp_doubles(int dim, int maxorder, int nb, int nkn_max);
 int prep_reg_fits_per_warp(int dim, int maxorder);
+int prep_reg_max_threads(int dim, int order);
 cudaError_t prepare_reg_occupancy(int dim, int maxorder, int threads, size_t smem, int* ctas_per_sm, bool direct = false);
 bool prepare_reg_direct_ok(int dim, int maxorder);
 cudaError_t launch_prepare_reg(int dim, int maxorder, const PrepRegParams& P, int blocks, int threads, size_t smem,

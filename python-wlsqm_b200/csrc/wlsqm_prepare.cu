@@ -47,12 +47,21 @@ struct PK {
     static constexpr int T = NOP / 8;
     static constexpr int LDA = NOP + 2;             // row stride of G / LU: LDS.128 by lane = row is conflict free
     static constexpr int BLK = NOP * PREP_CB;       // doubles per 32-column block of CT
-    static constexpr int MAXT = RPL == 2 ? 256 : PREP_REG_THREADS;   // launch bound: 128 registers (RPL == 2: 255)
+    // launch bound: 640 threads = 96 registers (at most 24 B of spills in any instantiation) -- the kernel is latency-bound
+    // and 20 resident warps instead of 16 is what shared memory allows for 2D order 4 (measured: 3.96 -> 3.74 ms per 1M
+    // fits); two rows per lane (3D order 4): 256 threads = 255 registers
+    static constexpr int MAXT = RPL == 2 ? 256 : PREP_REG_MAX_THREADS;
     static constexpr int MINB = 1;
 };
 
 __host__ __device__ constexpr int prep_no(int dim, int ord) {
     return dim == 1 ? ord + 1 : (dim == 2 ? (ord + 1) * (ord + 2) / 2 : (ord + 1) * (ord + 2) * (ord + 3) / 6);
+}
+
+// the launch bound of the instantiation for (dim, order), for the host's choice of the CTA size
+int prep_reg_max_threads(int dim, int order) {
+    const int nrp = (prep_no(dim, order) + 3) & ~3;
+    return nrp > 32 ? 256 : PREP_REG_MAX_THREADS;
 }
 
 int prep_reg_fits_per_warp(int dim, int maxorder) {
