@@ -6,6 +6,7 @@
 namespace wlsqm {
 
 constexpr int PREP_MAX_THREADS = 512;        // shared-memory variant (wlsqm_prepare_smem.cu)
+constexpr int PREP_REG_SMALL_THREADS = 1024; // ... models of at most 8 DOFs: 64 registers, as many warps as shared memory holds
 constexpr int PREP_REG_MAX_THREADS = 640;    // largest launch bound among the instantiations (2D order 4: 20 warps at 96 registers)
 constexpr int PREP_REG_THREADS = 512;        // register/DMMA variant (wlsqm_prepare.cu): launch bound; the host picks the CTA size
 constexpr int WLSQM_MAX_PEERS = 8;           // GPUs of one NVSwitch domain that can receive the fused gather

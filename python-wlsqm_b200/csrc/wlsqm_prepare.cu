@@ -49,8 +49,10 @@ struct PK {
     static constexpr int BLK = NOP * PREP_CB;       // doubles per 32-column block of CT
     // launch bound: 640 threads = 96 registers (at most 24 B of spills in any instantiation) -- the kernel is latency-bound
     // and 20 resident warps instead of 16 is what shared memory allows for 2D order 4 (measured: 3.96 -> 3.74 ms per 1M
-    // fits); two rows per lane (3D order 4): 256 threads = 255 registers
-    static constexpr int MAXT = RPL == 2 ? 256 : PREP_REG_MAX_THREADS;
+    // fits); models of at most 8 DOFs (four fits per warp, ~7 KB of shared memory per warp): 1024 threads = 64 registers
+    // without spills, 28 resident warps (2M fits 1D order 3: 2.29 ms at 16 warps, 1.96 at 20, 1.77 at 24, 1.60 at 28);
+    // two rows per lane (3D order 4): 256 threads = 255 registers
+    static constexpr int MAXT = RPL == 2 ? 256 : (NRP <= 8 ? PREP_REG_SMALL_THREADS : PREP_REG_MAX_THREADS);
     static constexpr int MINB = 1;
 };
 
@@ -61,7 +63,7 @@ __host__ __device__ constexpr int prep_no(int dim, int ord) {
 // the launch bound of the instantiation for (dim, order), for the host's choice of the CTA size
 int prep_reg_max_threads(int dim, int order) {
     const int nrp = (prep_no(dim, order) + 3) & ~3;
-    return nrp > 32 ? 256 : PREP_REG_MAX_THREADS;
+    return nrp > 32 ? 256 : (nrp <= 8 ? PREP_REG_SMALL_THREADS : PREP_REG_MAX_THREADS);
 }
 
 int prep_reg_fits_per_warp(int dim, int maxorder) {
