@@ -48,7 +48,7 @@ for name, stem in (("solve_kernel", "solve"), ("prepare_reg_kernel", "prepare"),
                    ("solve_kernel_3d_iter_sens", "solve3d"), ("solve_pack_kernel", "solvepack"),
                    ("solve_kernel_2d_iterative", "solveiter"), ("interpolate_kernel_one_slot", "interp1"),
                    ("fit_direct_kernel", "fitdirect"), ("lu_reg_kernel", "lureg"), ("prepare_reg_kernel_3d", "prepare3d"),
-                   ("rescale_kernel", "rescale")):
+                   ("rescale_kernel", "rescale"), ("sy_thread_kernel", "sythread"), ("prepare_reg_kernel_1d", "prepare1d")):
     rep = G / f"{stem}_{tag}.ncu-rep"
     if not rep.exists():
         print("missing", rep); continue
