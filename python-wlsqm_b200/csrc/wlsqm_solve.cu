@@ -171,16 +171,19 @@ solve_kernel(SolveParams P) {
         }
         return m;
     };
-    // bulk copies need 16 B alignment and sizes: the host says whether the arrays qualify (f_tma, xk_tma),
-    // the per-case element count has to be even on top of that; otherwise the lanes gather with plain loads
-    auto f_by_tma = [&](const CaseMeta& m) { return P.f_tma && !(m.nk & 1); };
-    auto xk_by_tma = [&](const CaseMeta& m) { return ITER && P.xk_tma && !((m.nk * DIM) & 1); };
+    // bulk copies need 16 B alignment and sizes: the host says whether the arrays qualify (f_tma, xk_tma: 16 B aligned
+    // base, unit stride, EVEN row pitch); otherwise the lanes gather with plain loads.  A row with an odd element count is
+    // copied with one element more -- the pitch is even, so that element exists, and nothing reads it (fext[nk] is either
+    // unused or the first known value, which the lanes then store AFTER the copy has landed: `late_knowns` below).  A lane
+    // gather instead would put an unprefetched global load on the critical path of every such case.
+    auto f_by_tma = [&](const CaseMeta&) { return P.f_tma != 0; };
+    auto xk_by_tma = [&](const CaseMeta&) { return ITER && P.xk_tma; };
     auto issue = [&](int s, long long c) {   // lane 0 only: arm the stage's barrier and start its copies
         const CaseMeta m = get_meta(c);
         const uint32_t st = ring_u32 + (uint32_t)s * stage_bytes, bar = bars_u32 + (uint32_t)s * 8u;
         const uint32_t b_op = ((uint32_t)((m.nk + m.nkn) * (int)m.nr) * 8u + 15u) & ~15u;
-        const uint32_t b_f = f_by_tma(m) ? (uint32_t)m.nk * 8u : 0u;
-        const uint32_t b_x = xk_by_tma(m) ? (uint32_t)(m.nk * DIM) * 8u : 0u;
+        const uint32_t b_f = f_by_tma(m) ? (((uint32_t)m.nk + 1u) & ~1u) * 8u : 0u;
+        const uint32_t b_x = xk_by_tma(m) ? (((uint32_t)(m.nk * DIM) + 1u) & ~1u) * 8u : 0u;
         mbar_expect_tx_u32(bar, b_op + b_f + b_x);
         if (b_op) tma_load_1d_u32(st, P.op + m.op_off, b_op, bar);
         if (b_f) tma_load_1d_u32(st + (uint32_t)P.off_f * 8u, P.fk + c * P.fk_s0, b_f, bar);
@@ -243,7 +246,8 @@ solve_kernel(SolveParams P) {
         const int below1 = __popcll(knowns & ((1LL << (lane + 32)) - 1));
         const int j0 = unk0 ? lane - below0 : 0;
         const int j1 = unk1 ? lane + 32 - below1 : 0;
-        if (nkn) {
+        const bool late_knowns = f_by_tma(mt) && (nk & 1);      // (warp-uniform) the copy writes fext[nk] too
+        if (nkn && !late_knowns) {
             if (in0 && !unk0) fext[nk + below0] = g0;
             if (in1 && !unk1) fext[nk + below1] = g1;
         }
@@ -256,6 +260,11 @@ solve_kernel(SolveParams P) {
         }
         __syncwarp();
         mbar_wait_u32(bars_u32 + (uint32_t)stage * 8u, phase);
+        if (nkn && late_knowns) {
+            if (in0 && !unk0) fext[nk + below0] = g0;
+            if (in1 && !unk1) fext[nk + below1] = g1;
+            __syncwarp();
+        }
 
         // ---- fi[unknown] = Op^T fext ----------------------------------------------------------------
         double v0 = g0, v1 = g1;     // known slots keep the caller's value
