@@ -1424,15 +1424,17 @@ int wlsqm_solver_solve_hoods(wlsqm_solver_t* s, const double* f, int64_t f_s0, d
         fd = (const double*)s->hood_f.p;
         fs0 = 1;
     }
-    rc = s->hood_fk.reserve((size_t)n * s->maxnk * 8);
+    // rows of the gathered fk get an EVEN pitch, so that the solve kernel can fetch them with bulk copies whatever nk is
+    const long long kp = ((long long)s->maxnk + 1) & ~1ll;
+    rc = s->hood_fk.reserve((size_t)n * kp * 8);
     if (rc) return rc;
-    const long long total = n * s->maxnk;
+    const long long total = n * kp;
     // (the indices were validated against [0, hood_points) by prepare_hoods; padding slots are not read)
     gather_hoods_kernel<<<(unsigned)std::min<long long>((total + 255) / 256, (long long)s->sm_count * 32), 256, 0, st>>>(
-        fd, fs0, 1, (const int32_t*)s->hoods_dev.p, s->maxnk, n, s->maxnk, (double*)s->hood_fk.p, s->hood_points, s->dmeta,
+        fd, fs0, 1, (const int32_t*)s->hoods_dev.p, s->maxnk, n, (int)kp, (double*)s->hood_fk.p, s->hood_points, s->dmeta,
         s->uni.nk, nullptr);
     CU(cudaGetLastError());
-    return wlsqm_solver_solve(s, (const double*)s->hood_fk.p, s->maxnk, 1, fi, fi_s0, sens, sens_s0, sens_s1, iters_out);
+    return wlsqm_solver_solve(s, (const double*)s->hood_fk.p, kp, 1, fi, fi_s0, sens, sens_s0, sens_s1, iters_out);
 }
 
 int wlsqm_solver_index_models(wlsqm_solver_t* s) {

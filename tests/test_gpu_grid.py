@@ -90,7 +90,7 @@ def test_device_tensors_and_gather():
     assert torch.equal(xk, xt[hoods.long()]) and torch.equal(fk, ft[hoods.long()])
 
 
-@pytest.mark.parametrize("dim,order,k,algo", [(2, 4, 30, 1), (3, 2, 20, 2), (1, 3, 8, 1)])
+@pytest.mark.parametrize("dim,order,k,algo", [(2, 4, 30, 1), (3, 2, 20, 2), (1, 3, 8, 1), (2, 3, 15, 1), (1, 4, 9, 2), (3, 2, 21, 2)])
 def test_prepare_solve_hoods_equal_gathered_arrays(dim, order, k, algo):
     """prepare_hoods / solve_hoods == prepare / solve on x[hoods], f[hoods], bit for bit (same kernels, same data)"""
     n = 3001
