@@ -200,6 +200,7 @@ struct wlsqm_solver {
     long long ncases = 0;
     int maxnk = 0, maxno = 1, maxnr = 0, maxnq = 0, maxorder = 0, maxnkn = 0;
     bool uniform = true, any_knowns = false, uniform_no = true;
+    bool last_nk_odd = false;   // nk of the LAST case is odd (see the bulk copies of fk rows in wlsqm_solver_solve)
     bool geom_uniform = true;   // same nk / order / weighting / number of knowns everywhere (the knowns pattern may vary)
     CaseMeta uni{};
     long long op_stride = 0, op_total = 0;
@@ -643,6 +644,7 @@ int wlsqm_solver_create(int dimension, int64_t ncases, const int32_t* nk, const 
             if (m.nk != f.nk || m.order != f.order || m.nkn != f.nkn || m.wm != f.wm) s->geom_uniform = false;
         }
     }
+    if (ncases > 0) s->last_nk_odd = (nk[ncases - 1] & 1) != 0;
     if (all_same) off *= ncases;
     s->op_total = off;
     if (ncases > 0) {
@@ -761,7 +763,7 @@ int wlsqm_solver_create_guest(wlsqm_solver_t* host, int algorithm, int do_sens, 
     s->max_iter = max_iter; s->debug = root->debug; s->ncases = root->ncases;
     s->maxnk = root->maxnk; s->maxno = root->maxno; s->maxnr = root->maxnr; s->maxnq = root->maxnq;
     s->maxorder = root->maxorder; s->maxnkn = root->maxnkn;
-    s->uniform = root->uniform; s->any_knowns = root->any_knowns; s->uniform_no = root->uniform_no;
+    s->uniform = root->uniform; s->any_knowns = root->any_knowns; s->uniform_no = root->uniform_no; s->last_nk_odd = root->last_nk_odd;
     s->geom_uniform = root->geom_uniform;
     s->uni = root->uni; s->op_stride = root->op_stride; s->op_total = root->op_total;
     try {
@@ -1172,6 +1174,22 @@ int wlsqm_solver_solve(wlsqm_solver_t* s, const double* fk, int64_t fk_s0, int64
         } else {
             rc = config_solve(s, P, L, rows);
             if (rc) return rc;
+            // Rows of fk with an odd element count are fetched by bulk copies of one element more (inside the even row
+            // pitch, wlsqm_solve.cu).  The storage of a CALLER's strided device array may end with the last element of
+            // its last row: that one case runs in a launch of its own with plain loads.
+            if (fk_dev && P.f_tma && s->last_nk_odd && c1 == n) {
+                if (rows > 1) {
+                    P.ncases = c1 - 1;
+                    rc = config_solve(s, P, L, rows - 1);
+                    if (rc) return rc;
+                    CU(launch_solve(s->dim, P, L.blocks, L.threads, L.smem, st));
+                }
+                P.case_lo = c1 - 1;
+                P.ncases = c1;
+                rc = config_solve(s, P, L, 1);
+                if (rc) return rc;
+                P.f_tma = 0;
+            }
             CU(launch_solve(s->dim, P, L.blocks, L.threads, L.smem, st));
         }
         if (sens_drain) {

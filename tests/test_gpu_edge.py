@@ -391,3 +391,26 @@ def test_solution_copy_can_be_dropped_for_device_outputs(algo):
     s.solve(fk_d, got2)
     out, _ = s.interpolate(xq, mode='nearest', diff=0, I=I)
     assert np.array_equal(got2.cpu().numpy(), want) and np.array_equal(out, out_want)
+
+
+def test_odd_neighbour_counts_in_even_pitched_rows_whose_storage_ends_with_the_last_element():
+    """fk rows with an odd element count travel by bulk copy with one element more (the row pitch is even); the last row of a
+    caller's strided tensor may have no such element -- same results as from a contiguous copy, knowns included"""
+    torch = pytest.importorskip("torch")
+    n, k = 4099, 13
+    x, hoods, f = parity.make_case(n, 2, k)
+    nk, od, kn, wm = _meta(n, k, 3, 0b101, 2)
+    xk, fk = parity.gathered(x, f, hoods)
+    fi0 = np.zeros((n, 10)); fi0[:, 0] = f; fi0[:, 2] = 0.5
+    s = wlsqm.ExpertSolver(2, nk, od, kn, wm)
+    s.prepare(torch.from_numpy(x).cuda(), torch.from_numpy(xk).cuda())
+    want = torch.from_numpy(fi0).cuda()
+    s.solve(torch.from_numpy(fk).cuda(), want)                       # contiguous rows of 13: lane gather (odd pitch)
+    base = torch.full(((n - 1) * 14 + 13,), float("nan"), dtype=torch.float64, device="cuda")
+    view = base.as_strided((n, k), (14, 1))
+    view.copy_(torch.from_numpy(fk).cuda())
+    got = torch.from_numpy(fi0).cuda()
+    s.solve(view, got)                                               # even pitch: bulk copies, the last row by the lanes
+    assert torch.equal(got, want)
+    ref, _, _, _ = parity.oracle_solve(2, nk, od, kn, wm, x, xk, fk, fi0)
+    assert np.abs(got.cpu().numpy() - ref).max() <= 1e-8 * np.abs(ref).max()
