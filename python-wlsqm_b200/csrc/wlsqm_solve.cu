@@ -218,6 +218,11 @@ solve_kernel(SolveParams P) {
             if (sn >= S) sn -= S;
             issue(sn, c + (long long)(S - 1) * GW);
         }
+        // per-case records: the one lane 0 needs at the top of the NEXT iteration (to start the copies of the case after
+        // next) is requested into L1 now -- fetched cold it held up the whole warp there (17 % of the stall samples of the
+        // mixed-size kernel, profiles/r02_solve_kernel_hetero_source_lines.txt)
+        // (with a one-stage ring the record in question is the next case's, which every lane fetches below anyway)
+        if (!UNI && S > 1 && lane == 0 && i + S < n_my) asm volatile("prefetch.global.L1 [%0];" ::"l"(P.meta + (c + (long long)S * GW)));
         const long long knowns = mt.knowns;
         if (UNI) mt = P.uni;   // loop invariant: lets the compiler hoist everything derived from the record
         const int nk = mt.nk, no = mt.no, nr = mt.nr, nkn = mt.nkn, nq = nk + nkn;
