@@ -158,7 +158,8 @@ def test_random_knowns_masks_orders_and_sizes(dim, algo, seed):
     fi_o, sens_o, it_o, _ = parity.oracle_solve(dim, nk, od, kn, wm, x, xk, fk, fi0, algo, True, max_iter=6)
     # (the maximum over a few hundred cases is a heavy-tailed statistic -- one case leaving its refinement loop a round
     # earlier under another summation order moves it by 5x: eight permutations for the floor)
-    a, b = parity.hetero_self_noise(dim, nk, od, kn, wm, x, xk, fk, fi0, algo, max_iter=6, seeds=tuple(range(7, 15)))
+    a, b = parity.hetero_self_noise(dim, nk, od, kn, wm, x, xk, fk, fi0, algo, max_iter=6, seeds=tuple(range(7, 15)),
+                                    iter_rounds=True)
 
     def untouched(fi):
         for j in range(n):
@@ -219,7 +220,8 @@ def test_random_knowns_patterns_of_equal_count(dim, order, k, nkn, algo, seed):
     fi0 = np.where((kn[:, None] >> np.arange(no)[None, :]) & 1, exact, rng.standard_normal((n, no)))
     fi_g, sens_g, it_g, _ = _run_gpu(dim, nk, od, kn, wm, x, xk, fk, fi0, algo, True, max_iter=5)
     fi_o, sens_o, it_o, _ = parity.oracle_solve(dim, nk, od, kn, wm, x, xk, fk, fi0, algo, True, max_iter=5)
-    a, b = parity.hetero_self_noise(dim, nk, od, kn, wm, x, xk, fk, fi0, algo, max_iter=5, seeds=tuple(range(7, 13)))
+    a, b = parity.hetero_self_noise(dim, nk, od, kn, wm, x, xk, fk, fi0, algo, max_iter=5, seeds=tuple(range(7, 13)),
+                                    iter_rounds=True)
     known = ((kn[:, None] >> np.arange(no)[None, :]) & 1).astype(bool)
     assert np.array_equal(fi_g[known], fi0[known])
     print(parity.check_against_floor(fi_g, fi_o, b + (fi_o - a), dim, order, "equal-count masks %dD o%d" % (dim, order)))
