@@ -205,7 +205,8 @@ def test_random_knowns_masks_orders_and_sizes(dim, algo, seed):
 
 @pytest.mark.parametrize("dim,order,k,nkn,algo,seed", [
     (1, 4, 9, 1, 1, 21), (1, 3, 8, 2, 1, 22), (2, 3, 24, 1, 1, 23), (2, 4, 30, 3, 1, 24), (2, 2, 12, 2, 1, 25),
-    (3, 2, 20, 2, 1, 26), (3, 4, 60, 33, 1, 27), (3, 3, 40, 4, 2, 28), (2, 4, 30, 2, 2, 29)])
+    (3, 2, 20, 2, 1, 26), (3, 4, 60, 33, 1, 27), (3, 3, 40, 4, 2, 28), (2, 4, 30, 2, 2, 29), (3, 4, 60, 2, 2, 30),
+    (3, 4, 45, 0, 2, 31), (3, 4, 61, 1, 2, 32)])
 def test_random_knowns_patterns_of_equal_count(dim, order, k, nkn, algo, seed):
     """same sizes everywhere, but every case knows a DIFFERENT set of nkn DOFs: the geometry-uniform kernels (one size
     record by value, one 8-byte mask per case; the packed solve for the small models) against the oracle"""
