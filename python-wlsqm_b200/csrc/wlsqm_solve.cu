@@ -52,7 +52,7 @@ __device__ __forceinline__ double lds_f64(uint32_t addr) {
 // groups leaves the total for reduced DOF j in every lane with (lane & (W-1)) == j.
 // nr > 32 (3D order 4 with < 3 knowns): lanes also own row j + 32, returned in `hi`.
 // op_s / v_s are 32-bit shared-memory addresses.
-template <int LW>
+template <int LW, bool COMPACT>
 __device__ __forceinline__ void warp_matvec_t(uint32_t op_s, uint32_t v_s, int n, int nr, int lane, double& lo,
                                               double& hi) {
     constexpr int W = 1 << LW, G = 32 >> LW;
@@ -105,28 +105,50 @@ __device__ __forceinline__ void warp_matvec_t(uint32_t op_s, uint32_t v_s, int n
             qa += 32u * rs8;
             wa += 256u;
         }
+        if (nr == 33 || !COMPACT) {
+            // (ALGO_BASIC applies the operator once per case and waits on this result: three independent butterflies have
+            // the shorter dependency chain; the refinement loop applies it four times and is bound by instruction issue)
 #pragma unroll
-        for (int off = 16; off > 0; off >>= 1) {
-            h0 += __shfl_xor_sync(0xffffffffu, h0, off);
-            if (nr > 33) h1 += __shfl_xor_sync(0xffffffffu, h1, off);
-            if (nr > 34) h2 += __shfl_xor_sync(0xffffffffu, h2, off);
+            for (int off = 16; off > 0; off >>= 1) {
+                h0 += __shfl_xor_sync(0xffffffffu, h0, off);
+                if (nr > 33) h1 += __shfl_xor_sync(0xffffffffu, h1, off);
+                if (nr > 34) h2 += __shfl_xor_sync(0xffffffffu, h2, off);
+            }
+            hi = lane == 0 ? h0 : (lane == 1 ? h1 : h2);
+        } else {
+            // two or three sums at once: the first exchange halves the data instead of doubling the shuffles -- the lower
+            // 16 lanes go on with column 32, the upper 16 with column 33 (and, for 35 unknowns, the second exchange
+            // leaves lanes 8-15 with column 34): 6 / 7 shuffles per application instead of 10 / 15
+            const bool up = (lane & 16) != 0;
+            double v = (up ? h1 : h0) + __shfl_xor_sync(0xffffffffu, up ? h0 : h1, 16);
+            if (nr > 34) {
+                const double w = (up ? 0.0 : h2) + __shfl_xor_sync(0xffffffffu, up ? h2 : 0.0, 16);   // lanes 0-15: column 34
+                const bool up8 = (lane & 8) != 0;
+                v = (up8 ? w : v) + __shfl_xor_sync(0xffffffffu, up8 ? v : w, 8);
+            } else {
+                v += __shfl_xor_sync(0xffffffffu, v, 8);
+            }
+#pragma unroll
+            for (int off = 4; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+            // column 32 sits in lanes 0-7, column 33 in lanes 16-23, column 34 in lanes 8-15: column 32 + t to lane t
+            hi = __shfl_sync(0xffffffffu, v, lane == 1 ? 16 : (lane == 2 ? 8 : 0));
         }
-        hi = lane == 0 ? h0 : (lane == 1 ? h1 : h2);
     }
     lo = (a0 + a1) + (a2 + a3);
 #pragma unroll
     for (int off = W; off < 32; off <<= 1) lo += __shfl_xor_sync(0xffffffffu, lo, off);
 }
 
+template <bool COMPACT>
 __device__ __forceinline__ void warp_matvec(uint32_t op_s, uint32_t v_s, int n, int nr, const Groups& gr, int lane,
                                             double& lo, double& hi) {
     switch (gr.lw) {   // warp-uniform
-        case 0: warp_matvec_t<0>(op_s, v_s, n, nr, lane, lo, hi); break;
-        case 1: warp_matvec_t<1>(op_s, v_s, n, nr, lane, lo, hi); break;
-        case 2: warp_matvec_t<2>(op_s, v_s, n, nr, lane, lo, hi); break;
-        case 3: warp_matvec_t<3>(op_s, v_s, n, nr, lane, lo, hi); break;
-        case 4: warp_matvec_t<4>(op_s, v_s, n, nr, lane, lo, hi); break;
-        default: warp_matvec_t<5>(op_s, v_s, n, nr, lane, lo, hi); break;
+        case 0: warp_matvec_t<0, COMPACT>(op_s, v_s, n, nr, lane, lo, hi); break;
+        case 1: warp_matvec_t<1, COMPACT>(op_s, v_s, n, nr, lane, lo, hi); break;
+        case 2: warp_matvec_t<2, COMPACT>(op_s, v_s, n, nr, lane, lo, hi); break;
+        case 3: warp_matvec_t<3, COMPACT>(op_s, v_s, n, nr, lane, lo, hi); break;
+        case 4: warp_matvec_t<4, COMPACT>(op_s, v_s, n, nr, lane, lo, hi); break;
+        default: warp_matvec_t<5, COMPACT>(op_s, v_s, n, nr, lane, lo, hi); break;
     }
 }
 
@@ -275,7 +297,7 @@ solve_kernel(SolveParams P) {
         double v0 = g0, v1 = g1;     // known slots keep the caller's value
         if (nr > 0) {
             double lo, hi;
-            warp_matvec(st_u32, st_u32 + (uint32_t)P.off_f * 8u, nq, nr, gr, lane, lo, hi);
+            warp_matvec<ITER>(st_u32, st_u32 + (uint32_t)P.off_f * 8u, nq, nr, gr, lane, lo, hi);
             const double t0 = fetch_reduced(lo, hi, j0);
             if (unk0) v0 = t0;
             if (no > 32) {
@@ -394,7 +416,7 @@ solve_kernel(SolveParams P) {
                 __syncwarp();
                 if (nr > 0) {
                     double lo, hi;
-                    warp_matvec(st_u32, rs_u32, nk, nr, gr, lane, lo, hi);
+                    warp_matvec<ITER>(st_u32, rs_u32, nk, nr, gr, lane, lo, hi);
                     const double t0 = fetch_reduced(lo, hi, j0);
                     if (unk0) { v0 += t0; fis[lane] = v0; }
                     if (no > 32) {
